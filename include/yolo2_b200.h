@@ -1,0 +1,128 @@
+/* libyolo2_b200.so -- C ABI of the B200-native YOLOv2 / Darknet-19 detection hot path.
+ *
+ * The reference (ruiminshen/yolo-tf, pure Python + TensorFlow 1.0) has no FFI: its seam is the
+ * Python call surface that train.py / detect.py drive.  Each entry point below is what a ctypes
+ * binding for that surface calls; the reference interface it replaces is cited per function
+ * (paths relative to the reference repository).  The Python mirror lives in yolo_tf_b200/.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr()),
+ *     16-byte aligned, float32 NHWC / row-major unless stated; `hparam` and scalars are host values;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is asynchronous
+ *     on it; the library never synchronises the device except in y2_create / y2_destroy;
+ *   - return 0 on success, < 0 on error; y2_last_error() gives the thread-local message;
+ *   - no CPU fallback exists: every call either launches sm_100a kernels or fails.
+ */
+#ifndef YOLO2_B200_H
+#define YOLO2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct y2_handle y2_handle;
+
+const char* y2_last_error(void);
+int y2_version(void);
+
+/* ---- network handle ------------------------------------------------------------------------
+ * Replaces the graph + variables that `Builder.__call__` builds through
+ * `inference.darknet(net, classes, num_anchors, training, center)` (model/yolo2/__init__.py:109-112,
+ * model/yolo2/inference.py:61-120).  One handle per (device, network); not thread-safe per handle. */
+int y2_create(y2_handle** out, int device, int classes, int num_anchors);
+void y2_destroy(y2_handle* h);
+
+/* Number of conv layers (22) and the per-layer geometry, in graph order conv0..conv20, conv (final). */
+int y2_num_layers(const y2_handle* h);
+int y2_layer_info(const y2_handle* h, int layer, int* ksize, int* cin, int* cout, int* has_bn);
+
+/* Load one layer's variables (device pointers).  `w_hwio` is the TF layout [k][k][cin][cout]
+ * (`yolo2_darknet/conv{i}/weights`); BN layers take gamma/beta/moving_mean/moving_variance
+ * (`.../BatchNorm/*`, eps = 1e-5, inference.py:63) and bias = NULL; the final layer takes `bias`
+ * (`yolo2_darknet/conv/biases`, inference.py:118) and NULL BN pointers.  The library folds BN with
+ * TF's arithmetic (inv = rsqrt(var+eps)*gamma; y = x*inv + (beta - mean*inv)) and re-packs the
+ * weights into split bf16 planes for the tensor cores.  Replaces slim.assign_from_checkpoint_fn
+ * (detect.py:104-106). */
+int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* gamma, const float* beta,
+                    const float* moving_mean, const float* moving_variance, const float* bias, void* stream);
+
+/* Activation workspace needed by y2_darknet_forward for a [B,H,W,3] batch (H, W multiples of 32,
+ * the assert of utils/__init__.py:52-56). */
+size_t y2_workspace_bytes(const y2_handle* h, int B, int H, int W);
+
+/* x [B,H,W,3] -> out [B,H/32,W/32,A*(5+C)].  Inference mode (BN moving statistics):
+ * `builder(image)` / `darknet(..., training=False)`, detect.py:101-102.
+ * precision: 0 = split-bf16 x3 (fp32-grade, default), 1 = single bf16 pass (fast, ~1e-2). */
+int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float* out, void* ws, size_t ws_bytes,
+                       int precision, void* stream);
+
+/* Copy layer `layer`'s post-activation output of the LAST forward (pre-pool) as float32 NHWC into
+ * `dst` -- the tensors `yolo2_darknet/conv{i}/...` that the reference exposes by name for summaries
+ * (train.py:31-67); used by the per-layer parity tests.  pooled != 0 returns the max-pooled tensor. */
+int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* stream);
+
+/* One conv (+scale/bias +leaky) on float32 NHWC tensors through the same tcgen05 kernel the
+ * network uses (splits operands on the fly).  Diagnostic / test entry point.
+ * block_n = 0 and k_splits = 0 pick defaults. */
+int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
+              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int k_splits,
+              void* stream);
+
+/* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.
+ * out[b, y, x, (dy*stride+dx)*C + c] = in[b, stride*y+dy, stride*x+dx, c]. */
+int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream);
+
+/* ---- head decode -- `Model(net, classes, anchors, training)`, model/yolo2/__init__.py:28-59.
+ * net [B,Hc,Wc,A*(5+C)]; anchors [A][2] float32 (cell units).  Any output pointer may be NULL.
+ * Box index n = cell*A + anchor; all outputs are [B, cells*A, ...]. */
+typedef struct y2_head_outputs {
+    float* conf;          /* [B,N,C]  iou*prob             (:56) */
+    float* xy_min;        /* [B,N,2]  cell units           (:54) */
+    float* xy_max;        /* [B,N,2]                       (:55) */
+    float* iou;           /* [B,N]    sigmoid(k=0)         (:37) */
+    float* prob;          /* [B,N,C]  softmax              (:42) */
+    float* wh;            /* [B,N,2]  exp * anchor         (:40) */
+    float* areas;         /* [B,N]                         (:43) */
+    float* xy;            /* [B,N,2]                       (:53) */
+    float* offset_xy;     /* [B,N,2]                       (:38) */
+    float* offset_xy_min; /* [B,N,2]                       (:45) */
+    float* offset_xy_max; /* [B,N,2]                       (:46) */
+    float* coords;        /* [B,N,4]  (off_x, off_y, sqrt(w01), sqrt(h01))  (:49) */
+    float* wh01;          /* [B,N,2]                       (:47) */
+} y2_head_outputs;
+int y2_head_decode(const float* net, int B, int Hc, int Wc, int A, int C, const float* anchors,
+                   const y2_head_outputs* outs, void* stream);
+
+/* ---- loss -- `Objectives(model, mask, prob, coords, offset_xy_min, offset_xy_max, areas)`
+ * (model/yolo2/__init__.py:62-94) + the weighting of `Builder.create_objectives` (:114-119).
+ * Labels are the 6 tensors of utils/data/__init__.py:112-145 batched: mask [B,cells], prob [B,cells,C],
+ * coords [B,cells,4], offset_xy_min/max [B,cells,2], areas [B,cells].
+ * hparam (HOST) = {prob, iou_best, iou_normal, coords} ([yolo2_hparam], config.ini:98-102).
+ * objectives (device, 4 floats, same order): the UNWEIGHTED objectives the reference stores in
+ * `builder.objectives[key]`.  dnet (nullable) receives d(sum_k hparam_k * objective_k)/d(net). */
+size_t y2_loss_workspace_bytes(int B, int Hc, int Wc);
+int y2_loss_fwd_bwd(const float* net, int B, int Hc, int Wc, int A, int C, const float* anchors, const float* mask,
+                    const float* prob, const float* coords, const float* offset_xy_min, const float* offset_xy_max,
+                    const float* areas, const float hparam[4], float* objectives, float* dnet, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- NMS -- `non_max_suppress(conf, xy_min, xy_max, threshold, threshold_iou)`
+ * (utils/postprocess.py:39-51, iou :21-36), batched over images.  conf [B,N,C] is modified IN PLACE
+ * exactly as the reference mutates its argument.  order_out (nullable, int32 [B,N]) receives the
+ * order of the list the reference returns.  status_out (nullable, int32 [B]) is set to 1 for images
+ * on which the reference's asserts (NaN / xy_min > xy_max, postprocess.py:22-27) would fire. */
+size_t y2_nms_workspace_bytes(int B, int N, int C);
+int y2_nms(float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
+           float threshold_iou, int32_t* order_out, int32_t* status_out, void* ws, size_t ws_bytes, void* stream);
+
+/* The tcgen05 pipelines bound every barrier wait; if one ever expires the kernel drains and records
+ * it.  Call with the device idle (after a synchronize): 0 = clean, < 0 = a watchdog fired (message
+ * in y2_last_error()).  Plays the role of tf.check_numerics-style runtime guards (detect.py:70). */
+int y2_check_async_errors(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO2_B200_H */

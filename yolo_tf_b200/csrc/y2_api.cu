@@ -1,0 +1,461 @@
+// C-ABI of libyolo2_b200.so (include/yolo2_b200.h): network handle, weight loading, forward plan.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/yolo2_b200.h"
+#include "y2_internal.h"
+
+namespace y2 {
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+const char* last_error() { return g_err.c_str(); }
+
+int device_sm_count(int device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    return n;
+}
+
+// declared in y2_head.cu / y2_nms.cu
+int head_decode_launch(const float*, int, int, int, int, int, const float*, const y2_head_outputs*, cudaStream_t);
+size_t loss_workspace_bytes(int, int, int);
+int loss_launch(const float*, int, int, int, int, int, const float*, const float*, const float*, const float*,
+                const float*, const float*, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
+size_t nms_workspace_bytes(int, int, int);
+int nms_launch(float*, const float*, const float*, int, int, int, float, float, int*, int*, void*, size_t,
+               cudaStream_t);
+
+// ---------------------------------------------------------------- network description
+// Darknet-19 + passthrough, model/yolo2/inference.py:70-118.
+struct LayerDesc {
+    int ksize, cin, cout;
+    int pool;          // 2x2 max-pool after (inference.py:74,83,96)
+    int passthrough;   // tapped for reorg (:95)
+    int has_bn;
+};
+static std::vector<LayerDesc> darknet19_layers(int classes, int anchors) {
+    std::vector<LayerDesc> L;
+    int cin = 3, ch = 32;
+    auto add = [&](int k, int cout, int pool, int pt) {
+        L.push_back({k, cin, cout, pool, pt, 1});
+        cin = cout;
+    };
+    for (int i = 0; i < 2; ++i) { add(3, ch, 1, 0); ch *= 2; }
+    for (int i = 0; i < 2; ++i) { add(3, ch, 0, 0); add(1, ch / 2, 0, 0); add(3, ch, 1, 0); ch *= 2; }
+    add(3, ch, 0, 0); add(1, ch / 2, 0, 0); add(3, ch, 0, 0); add(1, ch / 2, 0, 0); add(3, ch, 1, 1);
+    ch *= 2;
+    add(3, ch, 0, 0); add(1, ch / 2, 0, 0); add(3, ch, 0, 0); add(1, ch / 2, 0, 0);
+    add(3, ch, 0, 0); add(3, ch, 0, 0); add(3, ch, 0, 0);
+    cin = 4 * 512 + ch;                      // concat([reorg(passthrough), net]) :115-116
+    add(3, ch, 0, 0);
+    L.push_back({1, ch, anchors * (5 + classes), 0, 0, 0});   // linear + bias :118
+    return L;
+}
+
+struct LayerState {
+    LayerDesc d;
+    int cout_pad = 0, block_n = 0;
+    bf16* wpack = nullptr;     // [2][cout_pad][k*k*cin]
+    float* w_f32 = nullptr;    // conv0 only (CUDA-core kernel reads HWIO fp32)
+    float* scale = nullptr;    // [cout]
+    float* bias = nullptr;     // [cout]
+    bool loaded = false;
+};
+
+struct Plan {
+    bool valid = false;
+    int B = 0, H = 0, W = 0, precision = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    std::vector<bf16*> act;       // conv output planes per layer (layer 0: pooled output)
+    std::vector<bf16*> pooled;    // pooled planes for pool layers (>0)
+    std::vector<int> oh, ow;      // conv output spatial size per layer
+    bf16* concat = nullptr;
+    float* partial = nullptr;
+    std::vector<TcConvLaunch> launch;   // per layer (index 0 unused)
+};
+
+}  // namespace y2
+
+using namespace y2;
+
+struct y2_handle {
+    int device = 0, classes = 0, anchors = 0, num_sms = 148;
+    std::vector<LayerState> layers;
+    Plan plan;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void choose_tiles(int cout, int* block_n, int* cout_pad) {
+    const int p32 = (int)align_up((size_t)cout, 32);
+    const int nt = (p32 + 255) / 256;
+    const int bn = (int)align_up((size_t)((p32 + nt - 1) / nt), 32);
+    *block_n = bn;
+    *cout_pad = bn * nt;
+}
+
+// split-K factor: minimise waves * (k-blocks per split + fixed per-tile overhead); the 13x13 layers at
+// batch 32 have ~172 tiles for 148 SMs and K up to 432 k-blocks.
+static int choose_splits(long long M, int cout_pad, int block_n, int kblocks, int num_sms) {
+    const long long tiles = ((M + 127) / 128) * (cout_pad / block_n);
+    if (tiles >= 4LL * num_sms) return 1;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ks = 1; ks <= 16; ++ks) {
+        const int per = (kblocks + ks - 1) / ks;
+        if (ks > 1 && per < 6) break;
+        const int eff = (kblocks + per - 1) / per;
+        const long long waves = (tiles * eff + num_sms - 1) / num_sms;
+        double cost = (double)waves * (per + 3.0);
+        if (eff > 1) cost += 2.0 + 0.5 * eff;          // partial write + finish pass
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = eff; }
+    }
+    return best;
+}
+
+extern "C" {
+
+const char* y2_last_error(void) { return y2::last_error(); }
+int y2_version(void) { return 100; }
+
+int y2_create(y2_handle** out, int device, int classes, int num_anchors) {
+    Y2_REQUIRE(out, "y2_create: null out");
+    Y2_REQUIRE(classes > 0 && num_anchors > 0, "y2_create: classes and num_anchors must be positive");
+    int ndev = 0;
+    Y2_CUDA(cudaGetDeviceCount(&ndev));
+    Y2_REQUIRE(device >= 0 && device < ndev, "y2_create: device %d not present (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    Y2_CUDA(cudaGetDeviceProperties(&prop, device));
+    Y2_REQUIRE(prop.major == 10, "y2_create: this library contains sm_100a code only; device %d is sm_%d%d", device,
+               prop.major, prop.minor);
+    Y2_CUDA(cudaSetDevice(device));
+    y2_handle* h = new y2_handle();
+    h->device = device; h->classes = classes; h->anchors = num_anchors;
+    h->num_sms = prop.multiProcessorCount;
+    auto descs = darknet19_layers(classes, num_anchors);
+    for (size_t i = 0; i < descs.size(); ++i) {
+        LayerState s;
+        s.d = descs[i];
+        choose_tiles(s.d.cout, &s.block_n, &s.cout_pad);
+        const size_t K = (size_t)s.d.ksize * s.d.ksize * s.d.cin;
+        if (i == 0) {
+            if (cudaMalloc(&s.w_f32, K * s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        } else {
+            if (cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        }
+        if (cudaMalloc(&s.scale, s.d.cout * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&s.bias, s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        h->layers.push_back(s);
+    }
+    *out = h;
+    return 0;
+}
+
+void y2_destroy(y2_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& s : h->layers) {
+        cudaFree(s.wpack); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias);
+    }
+    delete h;
+}
+
+int y2_num_layers(const y2_handle* h) { return h ? (int)h->layers.size() : -1; }
+
+int y2_layer_info(const y2_handle* h, int layer, int* ksize, int* cin, int* cout, int* has_bn) {
+    Y2_REQUIRE(h && layer >= 0 && layer < (int)h->layers.size(), "y2_layer_info: bad layer %d", layer);
+    const LayerDesc& d = h->layers[layer].d;
+    if (ksize) *ksize = d.ksize;
+    if (cin) *cin = d.cin;
+    if (cout) *cout = d.cout;
+    if (has_bn) *has_bn = d.has_bn;
+    return 0;
+}
+
+int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* gamma, const float* beta,
+                    const float* moving_mean, const float* moving_variance, const float* bias, void* stream) {
+    Y2_REQUIRE(h && layer >= 0 && layer < (int)h->layers.size(), "y2_load_weights: bad layer %d", layer);
+    Y2_REQUIRE(w_hwio, "y2_load_weights: null weights");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Y2_CUDA(cudaSetDevice(h->device));
+    LayerState& L = h->layers[layer];
+    const size_t K = (size_t)L.d.ksize * L.d.ksize * L.d.cin;
+    if (layer == 0) {
+        Y2_CUDA(cudaMemcpyAsync(L.w_f32, w_hwio, K * L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        if (pack_weights_launch(w_hwio, L.wpack, L.d.ksize, L.d.cin, L.d.cout, L.cout_pad, s)) return -1;
+    }
+    if (L.d.has_bn) {
+        Y2_REQUIRE(moving_mean && moving_variance, "y2_load_weights: layer %d needs BN statistics", layer);
+        if (bn_fold_launch(gamma, beta, moving_mean, moving_variance, 1e-5f, L.scale, L.bias, L.d.cout, s)) return -1;
+    } else {
+        Y2_REQUIRE(bias, "y2_load_weights: final layer needs biases");
+        Y2_CUDA(cudaMemcpyAsync(L.bias, bias, L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    L.loaded = true;
+    return 0;
+}
+
+// workspace layout is a pure function of (B,H,W): used by both the size query and the planner
+struct WsLayout {
+    std::vector<size_t> act_off, pool_off;
+    std::vector<int> oh, ow;
+    size_t concat_off = 0, partial_off = 0, total = 0;
+    std::vector<int> splits;
+};
+static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* out) {
+    Y2_REQUIRE(B > 0 && H > 0 && W > 0, "workspace: bad shape");
+    Y2_REQUIRE(H % 32 == 0 && W % 32 == 0, "input size %dx%d is not divisible by the downsampling 32 (utils/__init__.py:52-56)", W, H);
+    const int nl = (int)h->layers.size();
+    out->act_off.assign(nl, 0); out->pool_off.assign(nl, 0); out->oh.assign(nl, 0); out->ow.assign(nl, 0);
+    out->splits.assign(nl, 1);
+    size_t off = 0, partial_max = 0;
+    int ch = H, cw = W;
+    for (int i = 0; i < nl; ++i) {
+        const LayerState& L = h->layers[i];
+        out->oh[i] = ch; out->ow[i] = cw;
+        const size_t M = (size_t)B * ch * cw;
+        if (i == 0) {                              // conv0 writes its pooled output only
+            out->act_off[i] = off;
+            off = align_up(off + 2 * (M / 4) * L.d.cout * sizeof(bf16), 1024);
+            ch /= 2; cw /= 2;
+            continue;
+        }
+        const int BK = (L.d.cin % 64 == 0) ? 64 : 32;
+        const int kblocks = L.d.ksize * L.d.ksize * (L.d.cin / BK);
+        out->splits[i] = choose_splits((long long)M, L.cout_pad, L.block_n, kblocks, h->num_sms);
+        if (out->splits[i] > 1) {
+            const size_t pb = (size_t)out->splits[i] * M * L.cout_pad * sizeof(float);
+            if (pb > partial_max) partial_max = pb;
+        }
+        if (i == nl - 1) break;                    // final layer writes the caller's buffer
+        if (i == nl - 3) {                         // conv19 writes into the concat buffer
+            out->act_off[i] = (size_t)-1;
+        } else {
+            out->act_off[i] = off;
+            off = align_up(off + 2 * M * L.d.cout * sizeof(bf16), 1024);
+        }
+        if (L.d.pool) {
+            out->pool_off[i] = off;
+            off = align_up(off + 2 * (M / 4) * L.d.cout * sizeof(bf16), 1024);
+            ch /= 2; cw /= 2;
+        }
+    }
+    out->concat_off = off;
+    off = align_up(off + 2 * (size_t)B * ch * cw * (4 * 512 + 1024) * sizeof(bf16), 1024);
+    out->partial_off = off;
+    off = align_up(off + partial_max, 1024);
+    out->total = off;
+    return 0;
+}
+
+size_t y2_workspace_bytes(const y2_handle* h, int B, int H, int W) {
+    if (!h) return 0;
+    WsLayout l;
+    if (layout_workspace(h, B, H, W, &l)) return 0;
+    return l.total;
+}
+
+static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_bytes, int precision) {
+    WsLayout l;
+    if (layout_workspace(h, B, H, W, &l)) return -1;
+    Y2_REQUIRE(ws && ws_bytes >= l.total, "y2_darknet_forward: workspace too small (%zu < %zu)", ws_bytes, l.total);
+    Y2_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "y2_darknet_forward: workspace must be 1024-byte aligned");
+    Plan& P = h->plan;
+    P = Plan();
+    const int nl = (int)h->layers.size();
+    char* base = static_cast<char*>(ws);
+    P.B = B; P.H = H; P.W = W; P.ws = ws; P.ws_bytes = ws_bytes; P.precision = precision;
+    P.act.assign(nl, nullptr); P.pooled.assign(nl, nullptr); P.oh = l.oh; P.ow = l.ow;
+    P.launch.resize(nl);
+    P.concat = reinterpret_cast<bf16*>(base + l.concat_off);
+    P.partial = reinterpret_cast<float*>(base + l.partial_off);
+    for (int i = 0; i < nl; ++i) {
+        if (l.act_off[i] != (size_t)-1 && i != nl - 1) P.act[i] = reinterpret_cast<bf16*>(base + l.act_off[i]);
+        if (i > 0 && h->layers[i].d.pool) P.pooled[i] = reinterpret_cast<bf16*>(base + l.pool_off[i]);
+    }
+    const int cat_c = 4 * 512 + 1024;
+    const bf16* input = P.act[0];
+    for (int i = 1; i < nl; ++i) {
+        const LayerState& L = h->layers[i];
+        const int oh = l.oh[i], ow = l.ow[i];
+        const size_t M = (size_t)B * oh * ow;
+        if (i == nl - 2) input = P.concat;         // conv20 reads concat([reorg, conv19])
+        TcConvLaunch& T = P.launch[i];
+        if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin, L.d.ksize, L.wpack, L.d.cout, L.cout_pad, L.block_n,
+                         l.splits[i], precision == 0, h->num_sms))
+            return -1;
+        ConvParams& p = T.p;
+        p.scale = L.d.has_bn ? L.scale : nullptr;
+        p.bias = L.bias;
+        p.leaky = L.d.has_bn ? 1 : 0;
+        p.partial = P.partial;
+        if (i == nl - 1) {
+            p.mode = EPI_F32; p.ldc = L.d.cout;    // out pointer patched per call
+        } else if (i == nl - 3) {
+            p.mode = EPI_PLANES; p.ldc = cat_c;
+            p.out_hi = P.concat + 2048;
+            p.out_lo = P.concat + M * cat_c + 2048;
+        } else {
+            p.mode = EPI_PLANES; p.ldc = L.d.cout;
+            p.out_hi = P.act[i];
+            p.out_lo = P.act[i] + M * L.d.cout;
+        }
+        input = L.d.pool ? P.pooled[i] : P.act[i];
+    }
+    P.valid = true;
+    return 0;
+}
+
+int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float* out, void* ws, size_t ws_bytes,
+                       int precision, void* stream) {
+    Y2_REQUIRE(h && x && out, "y2_darknet_forward: null argument");
+    Y2_REQUIRE(precision == 0 || precision == 1, "y2_darknet_forward: precision must be 0 or 1");
+    for (size_t i = 0; i < h->layers.size(); ++i)
+        Y2_REQUIRE(h->layers[i].loaded, "y2_darknet_forward: layer %zu has no weights (y2_load_weights)", i);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Y2_CUDA(cudaSetDevice(h->device));
+    Plan& P = h->plan;
+    if (!P.valid || P.B != B || P.H != H || P.W != W || P.ws != ws || P.precision != precision || P.ws_bytes != ws_bytes)
+        if (build_plan(h, B, H, W, ws, ws_bytes, precision)) return -1;
+    const int nl = (int)h->layers.size();
+    const LayerState& L0 = h->layers[0];
+    {
+        const size_t M0 = (size_t)B * (H / 2) * (W / 2);
+        if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout, B, H, W, s)) return -1;
+    }
+    for (int i = 1; i < nl; ++i) {
+        const LayerState& L = h->layers[i];
+        TcConvLaunch T = P.launch[i];
+        const int final_mode = T.p.mode;
+        if (i == nl - 1) T.p.out_f32 = out;
+        if (T.p.k_splits > 1) T.p.mode = EPI_PARTIAL;
+        if (tc_conv_launch(T, s)) return -1;
+        if (T.p.k_splits > 1 && splitk_finish_launch(T.p, final_mode, s)) return -1;
+        const int oh = P.oh[i], ow = P.ow[i];
+        const size_t M = (size_t)B * oh * ow;
+        if (L.d.passthrough) {
+            // reorg(passthrough) -> concat channels [0, 2048); both planes in one launch (batch 2B)
+            if (reorg_launch(P.act[i], P.concat, 2 * B, oh, ow, L.d.cout, 2, 2, 4 * L.d.cout + 1024, s)) return -1;
+        }
+        if (L.d.pool) {
+            if (maxpool_planes_launch(P.act[i], P.act[i] + M * L.d.cout, P.pooled[i],
+                                      P.pooled[i] + (M / 4) * L.d.cout, B, oh, ow, L.d.cout, s))
+                return -1;
+        }
+    }
+    return 0;
+}
+
+int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* stream) {
+    Y2_REQUIRE(h && dst, "y2_get_activation: null argument");
+    const Plan& P = h->plan;
+    Y2_REQUIRE(P.valid, "y2_get_activation: no forward has run");
+    const int nl = (int)h->layers.size();
+    Y2_REQUIRE(layer >= 0 && layer < nl - 1, "y2_get_activation: layer %d out of range", layer);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const LayerDesc& d = h->layers[layer].d;
+    const size_t M = (size_t)P.B * P.oh[layer] * P.ow[layer];
+    if (layer == 0) {
+        Y2_REQUIRE(pooled, "y2_get_activation: conv0 is fused with its max-pool; only the pooled tensor exists");
+        return merge_planes_launch(P.act[0], P.act[0] + (M / 4) * d.cout, dst, M / 4, d.cout, d.cout, s);
+    }
+    if (pooled) {
+        Y2_REQUIRE(d.pool, "y2_get_activation: layer %d has no pool", layer);
+        return merge_planes_launch(P.pooled[layer], P.pooled[layer] + (M / 4) * d.cout, dst, M / 4, d.cout, d.cout, s);
+    }
+    if (layer == nl - 3) {
+        const int cat_c = 4 * 512 + 1024;
+        return merge_planes_launch(P.concat + 2048, P.concat + M * cat_c + 2048, dst, M, d.cout, cat_c, s);
+    }
+    return merge_planes_launch(P.act[layer], P.act[layer] + M * d.cout, dst, M, d.cout, d.cout, s);
+}
+
+int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
+              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int k_splits,
+              void* stream) {
+    Y2_REQUIRE(x && w_hwio && y, "y2_conv2d: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    Y2_CUDA(cudaGetDevice(&dev));
+    const int num_sms = device_sm_count(dev);
+    int bn = 0, cpad = 0;
+    choose_tiles(cout, &bn, &cpad);
+    if (block_n > 0) { bn = block_n; cpad = (int)align_up((size_t)cout, (size_t)bn); }
+    const size_t M = (size_t)B * H * W, K = (size_t)ksize * ksize * cin;
+    const int BK = (cin % 64 == 0) ? 64 : 32;
+    if (k_splits <= 0) k_splits = choose_splits((long long)M, cpad, bn, ksize * ksize * (cin / BK), num_sms);
+    bf16 *xp = nullptr, *wp = nullptr;
+    float* partial = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&wp, 2 * (size_t)cpad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
+        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
+        if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s)) break;
+        TcConvLaunch T;
+        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, k_splits, precision == 0, num_sms)) break;
+        T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
+        T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
+        if (T.p.k_splits > 1) {
+            if (cudaMalloc(&partial, (size_t)T.p.k_splits * M * cpad * sizeof(float)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
+            T.p.partial = partial;
+            T.p.mode = EPI_PARTIAL;
+        }
+        if (tc_conv_launch(T, s)) break;
+        if (T.p.k_splits > 1 && splitk_finish_launch(T.p, EPI_F32, s)) break;
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (tc_conv_check_watchdog()) break;
+        rc = 0;
+    } while (0);
+    cudaFree(xp); cudaFree(wp); cudaFree(partial);
+    return rc;
+}
+
+int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream) {
+    Y2_REQUIRE(in && out, "y2_reorg: null argument");
+    Y2_REQUIRE(stride >= 1 && H % stride == 0 && W % stride == 0, "y2_reorg: H, W must be divisible by stride");
+    return reorg_launch(in, out, B, H, W, C, stride, 4, (long long)C * stride * stride, static_cast<cudaStream_t>(stream));
+}
+
+int y2_head_decode(const float* net, int B, int Hc, int Wc, int A, int C, const float* anchors,
+                   const y2_head_outputs* outs, void* stream) {
+    return head_decode_launch(net, B, Hc, Wc, A, C, anchors, outs, static_cast<cudaStream_t>(stream));
+}
+
+size_t y2_loss_workspace_bytes(int B, int Hc, int Wc) { return loss_workspace_bytes(B, Hc, Wc); }
+
+int y2_loss_fwd_bwd(const float* net, int B, int Hc, int Wc, int A, int C, const float* anchors, const float* mask,
+                    const float* prob, const float* coords, const float* offset_xy_min, const float* offset_xy_max,
+                    const float* areas, const float hparam[4], float* objectives, float* dnet, void* ws,
+                    size_t ws_bytes, void* stream) {
+    return loss_launch(net, B, Hc, Wc, A, C, anchors, mask, prob, coords, offset_xy_min, offset_xy_max, areas, hparam,
+                       objectives, dnet, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t y2_nms_workspace_bytes(int B, int N, int C) { return nms_workspace_bytes(B, N, C); }
+
+int y2_nms(float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
+           float threshold_iou, int32_t* order_out, int32_t* status_out, void* ws, size_t ws_bytes, void* stream) {
+    return nms_launch(conf, xy_min, xy_max, B, N, C, threshold, threshold_iou, order_out, status_out, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+/* Returns 0 if no tcgen05 pipeline watchdog fired since the last call (device must be idle). */
+int y2_check_async_errors(void) { return tc_conv_check_watchdog(); }
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// conv0 of Darknet-19 (model/yolo2/inference.py:73, first loop iteration): 3x3, Cin=3 -> Cout=32,
+// SAME, + BN (scale/bias) + leaky + 2x2/2 max-pool (:74), fused.  K = 27 is far too small for a
+// tensor-core K-block, and the layer is 0.9 % of the FLOPs, so it runs on the CUDA cores in exact
+// fp32 (fmaf accumulate).  One thread = one pooled pixel (a 4x4x3 input patch in registers,
+// 2x2 conv outputs x 32 channels in two passes of 16); weights are broadcast from shared memory
+// as 128-bit loads.  Output goes straight to the bf16 hi/lo planes conv1's TMA reads.
+#include "y2_internal.h"
+
+namespace y2 {
+
+__global__ void __launch_bounds__(128)
+conv0_pool_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio, const float* __restrict__ scale,
+                  const float* __restrict__ bias, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H,
+                  int W) {
+    __shared__ __align__(16) float sw[27 * 32];
+    __shared__ float ssc[32], sbi[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w_hwio[i];   // HWIO: [(ky*3+kx)*3+c][n]
+    if (threadIdx.x < 32) {
+        ssc[threadIdx.x] = scale[threadIdx.x];
+        sbi[threadIdx.x] = bias[threadIdx.x];
+    }
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)B * Ho * Wo;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(idx % Wo);
+        size_t t = idx / Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        float patch[4][4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int yy = 2 * yo - 1 + r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int xx = 2 * xo - 1 + c;
+                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+                const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
+                patch[r][c][0] = ok ? __ldg(src) : 0.f;
+                patch[r][c][1] = ok ? __ldg(src + 1) : 0.f;
+                patch[r][c][2] = ok ? __ldg(src + 2) : 0.f;
+            }
+        }
+        const size_t obase = (((size_t)b * Ho + yo) * Wo + xo) * 32;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float acc[4][16];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int n = 0; n < 16; ++n) acc[p][n] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4* wr = reinterpret_cast<const float4*>(&sw[((ky * 3 + kx) * 3 + c) * 32 + half * 16]);
+                        float wv[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 q = wr[j];
+                            wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float v = patch[(p >> 1) + ky][(p & 1) + kx][c];
+#pragma unroll
+                            for (int n = 0; n < 16; ++n) acc[p][n] = fmaf(v, wv[n], acc[p][n]);
+                        }
+                    }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int n = 0; n < 16; n += 2) {
+                float m[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float sc = ssc[half * 16 + n + e], bi = sbi[half * 16 + n + e];
+                    float best = -INFINITY;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float tv = acc[p][n + e] * sc + bi;
+                        best = fmaxf(best, fmaxf(tv, 0.1f * tv));
+                    }
+                    m[e] = best;
+                }
+                const bf16 h0 = __float2bfloat16_rn(m[0]), h1 = __float2bfloat16_rn(m[1]);
+                const bf16 l0 = __float2bfloat16_rn(m[0] - __bfloat162float(h0));
+                const bf16 l1 = __float2bfloat16_rn(m[1] - __bfloat162float(h1));
+                hi[n / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[n / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(out_hi + obase + half * 16);
+            uint4* dl = reinterpret_cast<uint4*>(out_lo + obase + half * 16);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+    }
+}
+
+int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,
+                      bf16* out_lo, int B, int H, int W, cudaStream_t s) {
+    Y2_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv0: H and W must be even");
+    const size_t total = (size_t)B * (H / 2) * (W / 2);
+    size_t blocks = (total + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv0_pool_kernel<<<(int)blocks, 128, 0, s>>>(x, w_hwio, scale, bias, out_hi, out_lo, B, H, W);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace y2

@@ -1,0 +1,454 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05) for sm_100a.
+//
+// Replaces the slim.layers.conv2d + slim.batch_norm + leaky_relu triple that the reference
+// stacks 21 times (model/yolo2/inference.py:62-69,73-117) and the final linear 1x1 conv (:118).
+//
+// GEMM view: D[M = B*H*W pixels][N = Cout] = A[M][K = taps*Cin] * W[N][K]^T, stride 1, SAME.
+//   * A is never materialised: each (tap, 64-channel) K-block of an M-tile is fetched by ONE
+//     im2col-mode TMA per plane straight from the NHWC activation (zero fill = SAME padding),
+//     landing in the 128B-swizzled K-major layout tcgen05.mma reads.
+//   * W tiles come from a pre-packed [Cout][tap][Cin] matrix via tiled TMA.
+//   * fp32 parity: operands are split bf16 planes (hi, lo); per K-step the MMA warp issues
+//     hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (lo*lo ~ 2^-32 is dropped).
+//   * Persistent CTAs, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (1 thread),
+//     warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> regs -> BN scale/bias + leaky ->
+//     bf16 hi/lo split -> global).  Two 256-column TMEM accumulators double-buffer the
+//     epilogue against the next tile's MMAs.
+//   * Optional split-K (raw fp32 partials + a finishing kernel) for the 13x13 / 19x19 layers
+//     whose tile count does not fill 148 SMs.
+#include <stdio.h>
+#include <string.h>
+
+#include "y2_internal.h"
+#include "y2_ptx.cuh"
+
+namespace y2 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int NUM_THREADS = 256;
+static constexpr int EPI_WARP0 = 4;
+static constexpr int TMEM_COLS = 512;
+static constexpr int ACC_COLS = 256;
+static constexpr int SMEM_LIMIT = 227 * 1024;
+static constexpr int SB_BYTES = 2 * 256 * 4;      // scale/bias staging for one tile
+static constexpr int BAR_BYTES = 256;
+
+template <int BK, bool SPLIT3>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const ConvParams p) {
+    constexpr int ROW_BYTES = BK * 2;                       // 128 (SW128) or 64 (SW64)
+    constexpr int A_TILE = BLOCK_M * ROW_BYTES;
+    constexpr int PLANES = SPLIT3 ? 2 : 1;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int b_tile = p.block_n * ROW_BYTES;
+    const int stage_bytes = PLANES * (A_TILE + b_tile);
+    const int S = p.num_stages;
+    float* sb = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);       // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + SB_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int units = p.m_tiles * p.n_tiles * p.k_splits;
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int cblocks = p.Cin / BK;
+    const int pad = p.ksize / 2;
+    const int hw = p.H * p.W;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ks = u / tiles_mn;
+                const int r = u - ks * tiles_mn;
+                const int nt = r / p.m_tiles;
+                const int mt = r - nt * p.m_tiles;
+                const int m0 = mt * BLOCK_M;
+                const int img = m0 / hw;
+                const int rem = m0 - img * hw;
+                const int y0 = rem / p.W;
+                const int x0 = rem - y0 * p.W;
+                const int n0 = nt * p.block_n;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kblocks_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tap = kb / cblocks;
+                    const int c0 = (kb - tap * cblocks) * BK;
+                    const int dy = (p.ksize == 3) ? tap / 3 : 0;
+                    const int dx = (p.ksize == 3) ? tap - dy * 3 : 0;
+                    mbar_wait(&empty[stage], phase ^ 1u, 0x100u + stage);
+                    uint8_t* st = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    tma_load_im2col_4d(st, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx,
+                                       (uint16_t)dy);
+                    if (SPLIT3)
+                        tma_load_im2col_4d(st + A_TILE, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
+                                           (uint16_t)dx, (uint16_t)dy);
+                    uint8_t* sbt = st + PLANES * A_TILE;
+                    const int kcoord = tap * p.Cin + c0;
+                    tma_load_2d(sbt, &map_w, &full[stage], kcoord, n0);
+                    if (SPLIT3) tma_load_2d(sbt + b_tile, &map_w, &full[stage], kcoord, p.cout_pad + n0);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one lane) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ks = u / tiles_mn;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kblocks_total, kb0 + p.kb_per_split);
+                mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase, 0x300u + stage);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_lo = a_hi + A_TILE;
+                    const uint32_t b_hi = a_hi + PLANES * A_TILE;
+                    const uint32_t b_lo = b_hi + b_tile;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t koff = k * 32;      // 16 bf16 = 32 bytes along K inside the swizzle row
+                        const uint64_t da_hi = make_kmajor_desc(a_hi + koff, ROW_BYTES);
+                        const uint64_t db_hi = make_kmajor_desc(b_hi + koff, ROW_BYTES);
+                        tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (SPLIT3) {
+                            const uint64_t da_lo = make_kmajor_desc(a_lo + koff, ROW_BYTES);
+                            const uint64_t db_lo = make_kmajor_desc(b_lo + koff, ROW_BYTES);
+                            tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty[stage]);              // smem slot reusable once these MMAs retire
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(&tfull[acc]);                    // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        const int q = warp - EPI_WARP0;
+        const int et = threadIdx.x - EPI_WARP0 * 32;       // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int ks = u / tiles_mn;
+            const int r = u - ks * tiles_mn;
+            const int nt = r / p.m_tiles;
+            const int mt = r - nt * p.m_tiles;
+            const int n0 = nt * p.block_n;
+            const long long row = (long long)mt * BLOCK_M + q * 32 + lane;
+            const bool row_ok = row < p.M;
+
+            // stage this tile's scale/bias (previous tile's readers are past the first barrier)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.mode != EPI_PARTIAL) {
+                for (int i = et; i < p.block_n; i += 128) {
+                    const int n = n0 + i;
+                    sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
+                    sb[256 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+                tmem_ld_wait();
+                if (p.mode == EPI_PARTIAL) {
+                    if (row_ok) {
+                        float4* dst = reinterpret_cast<float4*>(
+                            p.partial + ((size_t)ks * p.M + (size_t)row) * (size_t)(p.n_tiles * p.block_n) + n0 + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    }
+                    continue;
+                }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(v[j]) * sb[c + j] + sb[256 + c + j];
+                    f[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                }
+                if (!row_ok) continue;
+                if (p.mode == EPI_PLANES) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]);
+                        const __nv_bfloat16 h1 = __float2bfloat16_rn(f[2 * j + 1]);
+                        const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
+                        const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+                        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldc + n0 + c);
+                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldc + n0 + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                } else {  // EPI_F32, arbitrary N / pitch: masked scalar stores
+                    float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c + j < p.N) dst[j] = f[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-K finish: out = epilogue(sum_ks partial[ks])
+__global__ void splitk_finish_kernel(ConvParams p, int final_mode) {
+    const int n_pad = p.n_tiles * p.block_n;
+    const size_t total = (size_t)p.M * (size_t)(p.N / 4 + ((p.N % 4) ? 1 : 0));
+    const int nq = p.N / 4 + ((p.N % 4) ? 1 : 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / nq;
+        const int n = (int)(i - row * nq) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ks = 0; ks < p.k_splits; ++ks) {
+            const float4 t = *reinterpret_cast<const float4*>(p.partial + ((size_t)ks * p.M + row) * n_pad + n);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        float f[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = n + j;
+            const float sc = (p.scale && nn < p.N) ? __ldg(p.scale + nn) : 1.0f;
+            const float bi = (p.bias && nn < p.N) ? __ldg(p.bias + nn) : 0.0f;
+            const float t = f[j] * sc + bi;
+            f[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
+        }
+        if (final_mode == EPI_PLANES) {
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = __float2bfloat16_rn(f[j]);
+                l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+            }
+            uint2 hv, lv;
+            hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+            hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+            lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+            lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+            *reinterpret_cast<uint2*>(p.out_hi + row * p.ldc + n) = hv;
+            *reinterpret_cast<uint2*>(p.out_lo + row * p.ldc + n) = lv;
+        } else {
+            float* dst = p.out_f32 + row * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) dst[j] = f[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+
+static int load_driver_entry_points() {
+    if (g_encodeTiled && g_encodeIm2col) return 0;
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    Y2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    Y2_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    g_encodeTiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    fn = nullptr;
+    Y2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    Y2_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available from the driver");
+    g_encodeIm2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+    return 0;
+}
+
+template <int BK, bool SPLIT3>
+static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
+    auto kern = conv_tc_kernel<BK, SPLIT3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        Y2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_set = true;
+    }
+    kern<<<L.grid, NUM_THREADS, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream) {
+    if (L.block_k == 64) return L.split3 ? launch_inst<64, true>(L, stream) : launch_inst<64, false>(L, stream);
+    return L.split3 ? launch_inst<32, true>(L, stream) : launch_inst<32, false>(L, stream);
+}
+
+int tc_conv_check_watchdog() {
+    Watchdog w;
+    Y2_CUDA(cudaMemcpyFromSymbol(&w, g_watchdog, sizeof(w)));
+    if (!w.fired) return 0;
+    Watchdog z;
+    memset(&z, 0, sizeof(z));
+    cudaMemcpyToSymbol(g_watchdog, &z, sizeof(z));
+    set_error("tcgen05 conv: barrier watchdog fired (block %u warp %u wait-site 0x%x parity %u): pipeline deadlock",
+              w.block, w.warp, w.tag, w.parity);
+    return -3;
+}
+
+int splitk_finish_launch(const ConvParams& p, int final_mode, cudaStream_t stream) {
+    const size_t total = (size_t)p.M * (size_t)((p.N + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(p, final_mode);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize, const bf16* wpack,
+                 int cout, int cout_pad, int block_n, int k_splits, int split3, int num_sms) {
+    if (load_driver_entry_points()) return -1;
+    Y2_REQUIRE(ksize == 1 || ksize == 3, "tc conv: ksize must be 1 or 3 (got %d)", ksize);
+    Y2_REQUIRE(Cin % 32 == 0, "tc conv: Cin must be a multiple of 32 (got %d)", Cin);
+    Y2_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, "tc conv: block_n %d invalid", block_n);
+    Y2_REQUIRE(cout_pad % block_n == 0 && cout_pad >= cout, "tc conv: cout_pad %d vs block_n %d", cout_pad, block_n);
+    Y2_REQUIRE((reinterpret_cast<uintptr_t>(in_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0,
+               "tc conv: operands must be 16-byte aligned");
+    memset(L, 0, sizeof(*L));
+    const int BK = (Cin % 64 == 0) ? 64 : 32;
+    const int taps = ksize * ksize;
+    const long long M = (long long)B * H * W;
+    Y2_REQUIRE(M < (1ll << 31), "tc conv: too many pixels");
+    ConvParams& p = L->p;
+    p.M = (int)M; p.N = cout; p.Cin = Cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
+    p.block_n = block_n;
+    p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    p.n_tiles = cout_pad / block_n;
+    p.kblocks_total = taps * (Cin / BK);
+    if (k_splits < 1) k_splits = 1;
+    if (k_splits > p.kblocks_total) k_splits = p.kblocks_total;
+    p.kb_per_split = (p.kblocks_total + k_splits - 1) / k_splits;
+    p.k_splits = (p.kblocks_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+    p.cout_pad = cout_pad;
+    const int planes = split3 ? 2 : 1;
+    const int stage_bytes = planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
+    int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES) / stage_bytes;
+    if (stages > 8) stages = 8;
+    Y2_REQUIRE(stages >= 2, "tc conv: tile does not fit shared memory");
+    p.num_stages = stages;
+    L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
+    L->block_k = BK;
+    L->split3 = split3 ? 1 : 0;
+    const int units = p.m_tiles * p.n_tiles * p.k_splits;
+    L->grid = units < num_sms ? units : num_sms;
+
+    // activation map: (C, W, H, N=2B) bf16, im2col mode, BLOCK_M pixels x BK channels per load
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        const int padv = ksize / 2;
+        int lower[2] = {-padv, -padv};
+        int upper[2] = {padv - (ksize - 1), padv - (ksize - 1)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encodeIm2col(&L->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in_planes), dims,
+                                    strides, lower, upper, (cuuint32_t)BK, (cuuint32_t)BLOCK_M, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) for B=%d H=%d W=%d Cin=%d k=%d", (int)r, B,
+                   H, W, Cin, ksize);
+        // Driver workaround (also applied by CUTLASS): for tensors smaller than 128 KiB old drivers
+        // set a bit in the im2col descriptor that must be cleared.
+        int drv = 0;
+        cudaDriverGetVersion(&drv);
+        if (drv <= 13010 && (size_t)2 * B * H * W * Cin * 2 < 131072)
+            reinterpret_cast<uint64_t*>(&L->map_a)[1] &= ~(1ull << 21);
+    }
+    // weight map: (K, 2*cout_pad) bf16 tiled, BK x block_n box
+    {
+        const cuuint64_t K = (cuuint64_t)taps * Cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)(2 * cout_pad)};
+        cuuint64_t strides[1] = {K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encodeTiled(&L->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(wpack), dims,
+                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights K=%llu cout_pad=%d", (int)r,
+                   (unsigned long long)K, cout_pad);
+    }
+    return 0;
+}
+
+}  // namespace y2

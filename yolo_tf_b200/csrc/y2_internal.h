@@ -1,0 +1,96 @@
+// Internal (non-ABI) declarations shared by the translation units of libyolo2_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace y2 {
+
+// ---- error plumbing (thread-local message behind y2_last_error()) ----
+void set_error(const char* fmt, ...);
+const char* last_error();
+#define Y2_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            y2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+#define Y2_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            y2::set_error(__VA_ARGS__);  \
+            return -1;                   \
+        }                                \
+    } while (0)
+
+int device_sm_count(int device);
+
+// ---- activation storage: "split planes" ----
+// A float32 NHWC tensor T[M][C] lives in HBM as two bf16 planes, hi = bf16(T) and
+// lo = bf16(T - hi), plane p at base + p*M*ld (ld = row pitch in elements). hi+lo carries 16
+// significand bits; the tcgen05 conv multiplies planes pairwise (hi*hi + hi*lo + lo*hi).
+typedef __nv_bfloat16 bf16;
+
+// ---- tcgen05 implicit-GEMM conv (y2_conv_tc.cu) ----
+enum EpilogueMode : int {
+    EPI_PLANES = 0,    // y = leaky?(acc*scale+bias) -> bf16 hi/lo planes
+    EPI_F32 = 1,       // y = leaky?(acc*scale+bias) -> float32 (final layer / debugging)
+    EPI_PARTIAL = 2,   // raw accumulators -> split-K workspace [ks][M][n_pad] float32
+};
+
+struct ConvParams {
+    int M, N, Cin, ksize, B, H, W;
+    int block_n, m_tiles, n_tiles, k_splits, kblocks_total, kb_per_split;
+    int cout_pad;            // rows per weight plane in the packed weight matrix
+    int num_stages;
+    int mode;                // EpilogueMode
+    int leaky;
+    const float* scale;      // [N] (null -> 1)
+    const float* bias;       // [N] (null -> 0)
+    bf16* out_hi;            // EPI_PLANES (already offset to the first output channel)
+    bf16* out_lo;
+    float* out_f32;          // EPI_F32
+    float* partial;          // EPI_PARTIAL
+    long long ldc;           // output row pitch, elements
+};
+
+struct TcConvLaunch {
+    CUtensorMap map_a;       // im2col map over the input planes (C, W, H, 2B)
+    CUtensorMap map_w;       // tiled map over packed weights (K, 2*cout_pad)
+    ConvParams p;
+    int grid, smem_bytes, block_k, split3;
+};
+
+// Builds tensor maps + launch geometry for one conv.  in_planes: bf16 [2][B][H][W][Cin].
+// wpack: bf16 [2][cout_pad][ksize*ksize*Cin] (k = tap*Cin + c).  Returns 0 or <0 (error set).
+int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
+                 const bf16* wpack, int cout, int cout_pad, int block_n, int k_splits, int split3, int num_sms);
+int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
+// Reads and clears the barrier watchdog; returns 0 if it never fired, else sets the error.
+int tc_conv_check_watchdog();
+// Sum split-K partials and apply the epilogue (mode EPI_PLANES or EPI_F32 fields of p).
+int splitk_finish_launch(const ConvParams& p, int final_mode, cudaStream_t stream);
+
+// ---- elementwise / layout kernels (y2_layout.cu) ----
+int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s);
+int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows, int cols, long long ld,
+                        cudaStream_t s);
+int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad,
+                        cudaStream_t s);
+int bn_fold_launch(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                   float* scale, float* bias, int n, cudaStream_t s);
+int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
+                          int C, cudaStream_t s);
+// reorg (space-to-depth 2) on 16-byte vectors; elem_bytes in {2,4}; out row pitch in elements.
+int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes,
+                 long long out_ld, cudaStream_t s);
+
+// ---- SIMT convs (y2_conv_simt.cu) ----
+// conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.
+int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,
+                      bf16* out_lo, int B, int H, int W, cudaStream_t s);
+}  // namespace y2

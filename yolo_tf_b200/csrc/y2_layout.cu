@@ -1,0 +1,214 @@
+// HBM-bound layout kernels around the conv stack: split/merge of bf16 hi/lo planes, weight
+// packing, BN folding, 2x2 max-pool on planes, reorg (space-to-depth).  All use 128-bit
+// accesses on the contiguous NHWC channel runs and grid-stride loops sized to the SM count.
+#include "y2_internal.h"
+
+namespace y2 {
+
+static inline int grid_for(size_t work_items, int threads) {
+    size_t blocks = (work_items + threads - 1) / threads;
+    const size_t cap = 148 * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
+           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ---------------------------------------------------------------- split fp32 -> planes
+__global__ void split_planes_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                    size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+        const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+        hi[i] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+        lo[i] = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+    }
+}
+int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s) {
+    Y2_REQUIRE(n % 4 == 0, "split_planes: element count must be a multiple of 4");
+    split_planes_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                           reinterpret_cast<uint2*>(dst_hi),
+                                                           reinterpret_cast<uint2*>(dst_lo), n / 4);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- merge planes -> fp32
+__global__ void merge_planes_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ dst,
+                                    size_t rows, int cols, long long ld) {
+    const int c4 = cols / 4;
+    const size_t total = rows * (size_t)c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + r * ld + c));
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + r * ld + c));
+        float4 o;
+        o.x = bf16_lo_f(h.x) + bf16_lo_f(l.x);
+        o.y = bf16_hi_f(h.x) + bf16_hi_f(l.x);
+        o.z = bf16_lo_f(h.y) + bf16_lo_f(l.y);
+        o.w = bf16_hi_f(h.y) + bf16_hi_f(l.y);
+        *reinterpret_cast<float4*>(dst + r * (size_t)cols + c) = o;
+    }
+}
+int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows, int cols, long long ld,
+                        cudaStream_t s) {
+    Y2_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "merge_planes: cols and pitch must be multiples of 4");
+    merge_planes_kernel<<<grid_for(rows * (size_t)(cols / 4), 256), 256, 0, s>>>(hi, lo, dst, rows, cols, ld);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- weights HWIO fp32 -> [2][cout_pad][tap*Cin] bf16
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int taps, int cin, int cout,
+                                    int cout_pad) {
+    const size_t K = (size_t)taps * cin;
+    const size_t total = (size_t)cout_pad * K;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / K;
+        const size_t k = i - n * K;            // k = tap*cin + c ; HWIO index = (tap*cin + c)*cout + n
+        float v = 0.f;
+        if (n < (size_t)cout) v = __ldg(w + k * cout + n);
+        const bf16 h = __float2bfloat16_rn(v);
+        out[i] = h;
+        out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad, cudaStream_t s) {
+    const size_t total = (size_t)cout_pad * ksize * ksize * cin;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, wpack, ksize * ksize, cin, cout, cout_pad);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- BN inference fold (TF arithmetic)
+// inv = rsqrt(var + eps) * gamma ; scale = inv ; bias = beta - mean * inv   (tf.nn.batch_normalization)
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               float* scale, float* bias, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float inv = __fmul_rn(rsqrtf(__fadd_rn(var[i], eps)), gamma ? gamma[i] : 1.0f);
+    scale[i] = inv;
+    bias[i] = __fsub_rn(beta ? beta[i] : 0.0f, __fmul_rn(mean[i], inv));
+}
+int bn_fold_launch(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                   float* bias, int n, cudaStream_t s) {
+    bn_fold_kernel<<<(n + 127) / 128, 128, 0, s>>>(gamma, beta, mean, var, eps, scale, bias, n);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- 2x2/2 max-pool on planes
+// One thread = 8 channels of one pooled pixel (16-byte vectors of each plane).  The winner is
+// chosen on the exact value hi+lo (16 significand bits, exact in fp32) and its (hi,lo) pair copied.
+__global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                      bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W,
+                                      int C) {
+    const int Ho = H / 2, Wo = W / 2, c8 = C / 8;
+    const size_t total = (size_t)B * Ho * Wo * c8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % c8);
+        size_t t = i / c8;
+        const int xo = (int)(t % Wo);
+        t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const size_t base = (((size_t)b * H + 2 * yo) * W + 2 * xo) * C + (size_t)cv * 8;
+        uint4 h[4], l[4];
+        h[0] = __ldg(reinterpret_cast<const uint4*>(in_hi + base));
+        h[1] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + C));
+        h[2] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + (size_t)W * C));
+        h[3] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + (size_t)W * C + C));
+        l[0] = __ldg(reinterpret_cast<const uint4*>(in_lo + base));
+        l[1] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + C));
+        l[2] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + (size_t)W * C));
+        l[3] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + (size_t)W * C + C));
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t* hw0 = reinterpret_cast<const uint32_t*>(&h[0]);
+            const uint32_t* lw0 = reinterpret_cast<const uint32_t*>(&l[0]);
+            // low half / high half of word w, over the 4 window positions
+            float best_a = -INFINITY, best_b = -INFINITY;
+            uint32_t ha = 0, la = 0, hb = 0, lb = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t hw = hw0[q * 4 + w], lw = lw0[q * 4 + w];
+                const float va = bf16_lo_f(hw) + bf16_lo_f(lw);
+                const float vb = bf16_hi_f(hw) + bf16_hi_f(lw);
+                if (va > best_a || q == 0) { best_a = va; ha = hw & 0xFFFFu; la = lw & 0xFFFFu; }
+                if (vb > best_b || q == 0) { best_b = vb; hb = hw & 0xFFFF0000u; lb = lw & 0xFFFF0000u; }
+            }
+            oh[w] = ha | hb;
+            ol[w] = la | lb;
+        }
+        const size_t ob = (((size_t)b * Ho + yo) * Wo + xo) * C + (size_t)cv * 8;
+        *reinterpret_cast<uint4*>(out_hi + ob) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<uint4*>(out_lo + ob) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    }
+}
+int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
+                          int C, cudaStream_t s) {
+    Y2_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C%%8, H%%2, W%%2 must be 0");
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- reorg (space-to-depth)
+// model/yolo2/function.py:22-29: out[b, y, x, (dy*s+dx)*C + c] = in[b, s*y+dy, s*x+dx, c].
+// Pure permutation of contiguous C-runs, moved as 16-byte vectors.
+template <typename V>
+__global__ void reorg_kernel(const V* __restrict__ in, V* __restrict__ out, int B, int H, int W, int cvec,
+                             int stride, long long out_ld_vec) {
+    const int Ho = H / stride, Wo = W / stride;
+    const int ss = stride * stride;
+    const size_t total = (size_t)B * Ho * Wo * ss * cvec;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvec);
+        size_t t = i / cvec;
+        const int d = (int)(t % ss);
+        t /= ss;
+        const int xo = (int)(t % Wo);
+        t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int dy = d / stride, dx = d - dy * stride;
+        const size_t src = (((size_t)b * H + (size_t)yo * stride + dy) * W + (size_t)xo * stride + dx) * cvec + cv;
+        const size_t dst = (((size_t)b * Ho + yo) * Wo + xo) * (size_t)out_ld_vec + (size_t)d * cvec + cv;
+        out[dst] = in[src];
+    }
+}
+template <typename V>
+static int reorg_dispatch(const void* in, void* out, int B, int H, int W, size_t row_bytes, int stride,
+                          size_t out_ld_bytes, cudaStream_t s) {
+    const int cvec = (int)(row_bytes / sizeof(V));
+    const size_t total = (size_t)B * H * W * cvec;
+    reorg_kernel<V><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const V*>(in), reinterpret_cast<V*>(out), B,
+                                                        H, W, cvec, stride, (long long)(out_ld_bytes / sizeof(V)));
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+// Widest vector (16/8/4/2 bytes) that divides the channel run, the output pitch and both base addresses.
+int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes, long long out_ld,
+                 cudaStream_t s) {
+    Y2_REQUIRE(stride >= 1 && H % stride == 0 && W % stride == 0, "reorg: H, W must be divisible by stride");
+    Y2_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "reorg: elem_bytes must be 2 or 4");
+    if ((size_t)B * H * W * C == 0) return 0;
+    const size_t row_bytes = (size_t)C * elem_bytes, ld_bytes = (size_t)out_ld * elem_bytes;
+    const uintptr_t mix = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | row_bytes | ld_bytes;
+    if ((mix & 15) == 0) return reorg_dispatch<uint4>(in, out, B, H, W, row_bytes, stride, ld_bytes, s);
+    if ((mix & 7) == 0) return reorg_dispatch<uint2>(in, out, B, H, W, row_bytes, stride, ld_bytes, s);
+    if ((mix & 3) == 0) return reorg_dispatch<uint32_t>(in, out, B, H, W, row_bytes, stride, ld_bytes, s);
+    return reorg_dispatch<uint16_t>(in, out, B, H, W, row_bytes, stride, ld_bytes, s);
+}
+
+}  // namespace y2

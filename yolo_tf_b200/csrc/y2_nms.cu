@@ -1,0 +1,232 @@
+// Greedy per-class IoU NMS, bit-exact with the reference's utils/postprocess.py:21-51
+// (iou :21-36, non_max_suppress :39-51) as executed under NumPy >= 2 (float32 everywhere).
+//
+// Reference semantics reproduced exactly:
+//   * class c visits boxes in the order of Python's stable descending sort carried across classes
+//     = lexicographic (conf[:,c] desc, conf[:,c-1] desc, ..., conf[:,0] desc, index asc) on the
+//     ORIGINAL scores;
+//   * a box whose class score is > threshold when reached ("live") zeroes the class score of EVERY
+//     later box - candidate or not - whose IoU with it is >= threshold_iou; zeroed boxes never act;
+//   * IoU uses the float32 operation order of iou() with no FMA contraction (explicit _rn intrinsics).
+//
+// Three kernels, no host round trip:
+//   select : one warp per (image, class).  Compacts the candidates (> threshold) in index order,
+//            rank-sorts them with the lexicographic comparator (ties descend into earlier class
+//            columns, which are still unmodified because nothing is written here), then runs the
+//            sequential greedy sweep with a shared-memory alive bitmask -> list of KEPT boxes.
+//   order  : (optional) final permutation of the N boxes = the order of the list the reference returns.
+//   apply  : one thread per score.  A candidate is zeroed iff it is not kept; a non-candidate (it
+//            sorts after every candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
+// Scores are read once by select (class-strided, L2-resident) and once by apply (coalesced).
+#include "y2_internal.h"
+
+namespace y2 {
+
+static constexpr int NMS_WARPS = 8;
+static constexpr int NMS_MAX_N = 8192;     // alive bitmask: 256 words per warp
+
+__device__ __forceinline__ float iou_ref(float4 a, float4 b) {   // (xmin, ymin, xmax, ymax)
+    const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float den = fmaxf(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-10f);
+    return __fdiv_rn(inter, den);
+}
+__device__ __forceinline__ float4 load_box(const float* __restrict__ xy_min, const float* __restrict__ xy_max,
+                                           size_t i) {
+    const float2 lo = __ldg(reinterpret_cast<const float2*>(xy_min) + i);
+    const float2 hi = __ldg(reinterpret_cast<const float2*>(xy_max) + i);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// does box i come before box j in class c's visiting order? (i != j)
+__device__ __forceinline__ bool precedes(const float* __restrict__ conf_img, int C, int c, int i, float vi, int j,
+                                         float vj) {
+    if (vi > vj) return true;
+    if (vi < vj) return false;
+    for (int cc = c - 1; cc >= 0; --cc) {
+        const float a = __ldg(conf_img + (size_t)i * C + cc), b = __ldg(conf_img + (size_t)j * C + cc);
+        if (a > b) return true;
+        if (a < b) return false;
+    }
+    return i < j;
+}
+
+struct NmsArgs {
+    float* conf;
+    const float* xy_min;
+    const float* xy_max;
+    int B, N, C;
+    float thr, thr_iou;
+    uint16_t* cand;      // [B][C][N] candidates in index order, overwritten with the kept list
+    uint16_t* sorted;    // [B][C][N] scratch: candidates in visiting order
+    int* kept_cnt;       // [B][C]
+    int* status;         // [B] nullable: 1 = a reference assert (NaN / xy_min > xy_max) would fire
+    int* order_out;      // [B][N] nullable
+};
+
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
+    __shared__ uint32_t alive_sm[NMS_WARPS][NMS_MAX_N / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * NMS_WARPS + warp;
+    const int b = blockIdx.y;
+    if (c >= a.C) return;
+    const float* conf_img = a.conf + (size_t)b * a.N * a.C;
+    const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+    const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+    uint16_t* cand = a.cand + ((size_t)b * a.C + c) * a.N;
+    uint16_t* sorted = a.sorted + ((size_t)b * a.C + c) * a.N;
+    uint32_t* alive = alive_sm[warp];
+
+    // 1. compact candidates, index order
+    int K = 0;
+    for (int n0 = 0; n0 < a.N; n0 += 32) {
+        const int n = n0 + lane;
+        const bool is_c = (n < a.N) && (__ldg(conf_img + (size_t)n * a.C + c) > a.thr);
+        const uint32_t m = __ballot_sync(0xffffffffu, is_c);
+        if (is_c) cand[K + __popc(m & ((1u << lane) - 1u))] = (uint16_t)n;
+        K += __popc(m);
+    }
+    if (K == 0) {
+        if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = 0;
+        return;
+    }
+    __syncwarp();
+    // reference asserts fire as soon as one live box is compared with the rest: every box is checked
+    if (a.status && a.N >= 2) {
+        bool bad = false;
+        for (int n = lane; n < a.N; n += 32) {
+            const float4 q = load_box(bmin, bmax, n);
+            bad |= !(q.x <= q.z) || !(q.y <= q.w);        // also true for NaN
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(a.status + b, 1);
+    }
+    // 2. rank sort into visiting order
+    for (int j0 = 0; j0 < K; j0 += 32) {
+        const int jj = j0 + lane;
+        const int j = (jj < K) ? cand[jj] : 0;
+        const float vj = (jj < K) ? __ldg(conf_img + (size_t)j * a.C + c) : 0.f;
+        int rank = 0;
+        for (int ii = 0; ii < K; ++ii) {
+            const int i = cand[ii];
+            const float vi = __ldg(conf_img + (size_t)i * a.C + c);
+            if (jj < K && i != j && precedes(conf_img, a.C, c, i, vi, j, vj)) ++rank;
+        }
+        if (jj < K) sorted[rank] = (uint16_t)j;
+    }
+    for (int w = lane; w < (K + 31) / 32; w += 32) alive[w] = 0xffffffffu;
+    __syncwarp();
+    // 3. greedy sweep in visiting order
+    int kept = 0;
+    for (int r = 0; r < K; ++r) {
+        if (!((alive[r >> 5] >> (r & 31)) & 1u)) continue;           // warp-uniform
+        const int i = sorted[r];
+        const float4 bi = load_box(bmin, bmax, i);
+        if (lane == 0) cand[kept] = (uint16_t)i;                     // kept list reuses cand[] (kept <= r)
+        ++kept;
+        for (int j0 = (r + 1) & ~31; j0 < K; j0 += 32) {
+            const int jj = j0 + lane;
+            bool kill = false;
+            if (jj > r && jj < K && ((alive[jj >> 5] >> (jj & 31)) & 1u)) {
+                const float4 bj = load_box(bmin, bmax, sorted[jj]);
+                kill = iou_ref(bi, bj) >= a.thr_iou;
+            }
+            const uint32_t km = __ballot_sync(0xffffffffu, kill);
+            if (km && lane == 0) alive[j0 >> 5] &= ~km;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+}
+
+// Final permutation: rank sort of all N boxes under the class-(C-1) visiting order. One CTA per image.
+__global__ void __launch_bounds__(256) nms_order_kernel(NmsArgs a) {
+    extern __shared__ float last_col[];          // [N]
+    const int b = blockIdx.x;
+    const float* conf_img = a.conf + (size_t)b * a.N * a.C;
+    const int c = a.C - 1;
+    for (int n = threadIdx.x; n < a.N; n += blockDim.x) last_col[n] = __ldg(conf_img + (size_t)n * a.C + c);
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+        const float vj = last_col[j];
+        int rank = 0;
+        for (int i = 0; i < a.N; ++i)
+            if (i != j && precedes(conf_img, a.C, c, i, last_col[i], j, vj)) ++rank;
+        a.order_out[(size_t)b * a.N + rank] = j;
+    }
+}
+
+__global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
+    const size_t per_img = (size_t)a.N * a.C;
+    const size_t total = (size_t)a.B * per_img;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / per_img);
+        const size_t r = e - (size_t)b * per_img;
+        const int n = (int)(r / a.C);
+        const int c = (int)(r - (size_t)n * a.C);
+        const int cnt = __ldg(a.kept_cnt + (size_t)b * a.C + c);
+        if (cnt == 0) continue;
+        const float v = a.conf[e];
+        const bool is_cand = v > a.thr;
+        const uint16_t* kept = a.cand + ((size_t)b * a.C + c) * a.N;
+        const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+        const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+        bool zero;
+        if (is_cand) {
+            bool found = false;
+            for (int t = 0; t < cnt; ++t) found |= (kept[t] == n);
+            zero = !found;
+        } else {
+            const float4 bn = load_box(bmin, bmax, n);
+            bool hit = false;
+            for (int t = 0; t < cnt && !hit; ++t) hit = iou_ref(load_box(bmin, bmax, kept[t]), bn) >= a.thr_iou;
+            zero = hit;
+        }
+        if (zero) a.conf[e] = 0.0f;
+    }
+}
+
+size_t nms_workspace_bytes(int B, int N, int C) {
+    const size_t lists = (size_t)B * C * N * sizeof(uint16_t);
+    const size_t a16 = (lists + 15) & ~(size_t)15;
+    return 2 * a16 + (((size_t)B * C * sizeof(int)) + 15 & ~(size_t)15);
+}
+
+int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
+               float threshold_iou, int* order_out, int* status_out, void* ws, size_t ws_bytes, cudaStream_t s) {
+    Y2_REQUIRE(conf && xy_min && xy_max && ws, "nms: null argument");
+    Y2_REQUIRE(B >= 0 && N >= 0 && C >= 0, "nms: negative extent");
+    Y2_REQUIRE(N <= NMS_MAX_N, "nms: at most %d boxes per image are supported (got %d)", NMS_MAX_N, N);
+    Y2_REQUIRE(ws_bytes >= nms_workspace_bytes(B, N, C), "nms: workspace too small (%zu < %zu)", ws_bytes,
+               nms_workspace_bytes(B, N, C));
+    Y2_REQUIRE((reinterpret_cast<uintptr_t>(xy_min) & 7) == 0 && (reinterpret_cast<uintptr_t>(xy_max) & 7) == 0,
+               "nms: box arrays must be 8-byte aligned");
+    if (status_out) Y2_CUDA(cudaMemsetAsync(status_out, 0, (size_t)B * sizeof(int), s));
+    if (B == 0 || N == 0 || C == 0) return 0;
+    Y2_REQUIRE(B <= 65535, "nms: batch too large for one launch");
+    NmsArgs a;
+    a.conf = conf; a.xy_min = xy_min; a.xy_max = xy_max; a.B = B; a.N = N; a.C = C;
+    a.thr = threshold; a.thr_iou = threshold_iou;
+    const size_t a16 = ((size_t)B * C * N * sizeof(uint16_t) + 15) & ~(size_t)15;
+    a.cand = reinterpret_cast<uint16_t*>(ws);
+    a.sorted = reinterpret_cast<uint16_t*>(static_cast<char*>(ws) + a16);
+    a.kept_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + 2 * a16);
+    a.status = status_out;
+    a.order_out = order_out;
+    dim3 grid((C + NMS_WARPS - 1) / NMS_WARPS, B);
+    nms_select_kernel<<<grid, NMS_WARPS * 32, 0, s>>>(a);
+    Y2_CUDA(cudaGetLastError());
+    if (order_out) {
+        nms_order_kernel<<<B, 256, (size_t)N * sizeof(float), s>>>(a);
+        Y2_CUDA(cudaGetLastError());
+    }
+    const size_t total = (size_t)B * N * C;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a);
+    Y2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace y2

@@ -1,0 +1,116 @@
+"""model/yolo2/inference.py -- the ``inference`` functions string-dispatched from the INI config
+(``getattr(inference, config.get('yolo2', 'inference'))``, model/yolo2/__init__.py:107).
+
+``darknet`` keeps the reference signature and return value ``(scope, net)`` (inference.py:61-120).
+The graph it stands for -- 21x (3x3|1x1 conv -> BN -> leaky), 5 max-pools, the passthrough reorg +
+concat, the final linear 1x1 conv -- runs as hand-written sm_100a kernels behind one C-ABI call
+(y2_darknet_forward); weights live in the variable store under the reference's TF names.
+"""
+import inspect
+
+from ... import _lib
+from ... import variables as V
+
+
+class _Engine(object):
+    """One y2_handle per (device, classes, anchors); re-uploads weights when the store changes."""
+    _cache = {}
+
+    def __init__(self, device_index, classes, num_anchors):
+        import ctypes
+        self.h = ctypes.c_void_p()
+        _lib.check(_lib.lib().y2_create(ctypes.byref(self.h), device_index, classes, num_anchors))
+        self.classes, self.num_anchors = classes, num_anchors
+        self.loaded_version = None
+        self.loaded_store = None
+        self.ws = None
+        L = _lib.lib()
+        self.layers = []
+        for i in range(L.y2_num_layers(self.h)):
+            k, cin, cout, bn = (ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int())
+            _lib.check(L.y2_layer_info(self.h, i, ctypes.byref(k), ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(bn)))
+            self.layers.append((k.value, cin.value, cout.value, bn.value))
+
+    @classmethod
+    def get(cls, device, classes, num_anchors):
+        key = (device.index or 0, classes, num_anchors)
+        if key not in cls._cache:
+            cls._cache[key] = cls(key[0], classes, num_anchors)
+        return cls._cache[key]
+
+    def sync_weights(self, scope, store, device, center=True):
+        if self.loaded_store is store and self.loaded_version == store.version:
+            return
+        L = _lib.lib()
+        n = len(self.layers)
+        for i, (k, cin, cout, bn) in enumerate(self.layers):
+            name = "%s/conv%d" % (scope, i) if i < n - 1 else "%s/conv" % scope
+            w = store.get(name + "/weights", (k, k, cin, cout), V.xavier_uniform, device)
+            if bn:
+                g = store.get(name + "/BatchNorm/gamma", (cout,), V.ones, device)
+                # center=False (the `_darknet` variant, inference.py:62-66): no beta, a separate `biases` variable added after BN
+                b = store.get(name + ("/BatchNorm/beta" if center else "/biases"), (cout,), V.zeros, device)
+                m = store.get(name + "/BatchNorm/moving_mean", (cout,), V.zeros, device)
+                v = store.get(name + "/BatchNorm/moving_variance", (cout,), V.ones, device)
+                _lib.check(L.y2_load_weights(self.h, i, _lib.ptr(w), _lib.ptr(g), _lib.ptr(b), _lib.ptr(m), _lib.ptr(v),
+                                             None, _lib.current_stream()))
+            else:
+                bias = store.get(name + "/biases", (cout,), V.zeros, device)
+                _lib.check(L.y2_load_weights(self.h, i, _lib.ptr(w), None, None, None, None, _lib.ptr(bias),
+                                             _lib.current_stream()))
+        self.loaded_store, self.loaded_version = store, store.version
+
+    def forward(self, x, precision=0):
+        import torch
+        L = _lib.lib()
+        b, h, w, c = x.shape
+        if c != 3:
+            raise ValueError("darknet expects NHWC input with 3 channels, got %s" % (tuple(x.shape),))
+        need = L.y2_workspace_bytes(self.h, b, h, w)
+        if need == 0:
+            raise _lib.Y2Error(L.y2_last_error().decode())
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+        off = (-self.ws.data_ptr()) % 1024
+        out = torch.empty((b, h // 32, w // 32, self.num_anchors * (5 + self.classes)), dtype=torch.float32, device=x.device)
+        import ctypes
+        _lib.check(L.y2_darknet_forward(self.h, _lib.ptr(x, torch.float32), b, h, w, _lib.ptr(out),
+                                        ctypes.c_void_p(self.ws.data_ptr() + off), need, precision, _lib.current_stream()))
+        return out
+
+    def activation(self, layer, pooled, shape):
+        import torch
+        out = torch.empty(shape, dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().y2_get_activation(self.h, layer, int(pooled), _lib.ptr(out), _lib.current_stream()))
+        return out
+
+
+def darknet(net, classes, num_anchors, training=False, center=True, precision=0):
+    """Darknet-19 + passthrough backbone (inference.py:61-120).
+
+    net: float32 CUDA tensor [B, H, W, 3] NHWC.  Returns ``(scope, output)`` with
+    output [B, H/32, W/32, num_anchors*(5+classes)] and scope == 'yolo2_darknet' (inference.py:67).
+    """
+    scope = __name__.split('.')[-2] + '_' + inspect.stack()[0][3]
+    if training:
+        raise NotImplementedError(
+            "training-mode backbone (BN batch statistics + backward) is not built yet on this backend; "
+            "the head loss fwd+bwd (Objectives) is. No silent fallback is provided.")
+    if not net.is_cuda:
+        raise _lib.Y2Error("darknet: input must be a CUDA tensor (no CPU path exists)")
+    eng = _Engine.get(net.device, classes, num_anchors)
+    eng.sync_weights(scope, V.default_store(), net.device, center=center)
+    out = eng.forward(net.contiguous(), precision=precision)
+    return scope, out
+
+
+DARKNET_DOWNSAMPLING = (2 ** 5, 2 ** 5)      # inference.py:122
+
+
+def _darknet(net, classes, num_anchors, training=False):
+    """inference.py:125-126: BN without beta + separate bias.  With beta == 0 the arithmetic is
+    identical, so the variant shares the kernels (the separate 'biases' variable maps to beta)."""
+    return darknet(net, classes, num_anchors, training, False)
+
+
+_DARKNET_DOWNSAMPLING = (2 ** 5, 2 ** 5)
