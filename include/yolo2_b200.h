@@ -58,6 +58,15 @@ size_t y2_workspace_bytes(const y2_handle* h, int B, int H, int W);
 int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float* out, void* ws, size_t ws_bytes,
                        int precision, void* stream);
 
+/* Per-layer device timing of y2_darknet_forward (CUDA events on the launching stream): conv_ms[i] =
+ * conv kernel(s) of layer i (incl. the split-K finishing pass), post_ms[i] = its max-pool / reorg
+ * passes; both host arrays of y2_num_layers() floats, valid for the last forward once it finished.
+ * y2_launch_count() = kernels launched by this library in this process (all entry points).
+ * The reference has no profiler; these feed bench.py's roofline numbers. */
+int y2_set_profiling(y2_handle* h, int enable);
+int y2_get_layer_ms(y2_handle* h, float* conv_ms, float* post_ms);
+unsigned long long y2_launch_count(void);
+
 /* Copy layer `layer`'s post-activation output of the LAST forward (pre-pool) as float32 NHWC into
  * `dst` -- the tensors `yolo2_darknet/conv{i}/...` that the reference exposes by name for summaries
  * (train.py:31-67); used by the per-layer parity tests.  pooled != 0 returns the max-pooled tensor. */

@@ -1,0 +1,186 @@
+"""-m gpu parity tests for the conv stack: the tcgen05 implicit-GEMM kernel per layer shape
+(vs torch fp64 conv on the same device and the CPU oracle), and the whole Darknet-19 forward
+through the reference-shaped API vs the CPU oracle, layer by layer.
+
+Tolerance (north_star): 1e-4 relative, measured as max|a-b| / max|b| per output tensor.
+"""
+import numpy as np
+import pytest
+
+from oracle import head_oracle as ho
+from oracle.darknet_oracle import conv_bn_leaky_oracle, darknet_oracle, init_params, layer_table
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, k_splits=0):
+    import torch
+    from yolo_tf_b200 import _lib
+    xs, ws = torch.as_tensor(x).to(cuda), torch.as_tensor(w).to(cuda)
+    sc = torch.as_tensor(scale).to(cuda) if scale is not None else None
+    bi = torch.as_tensor(bias).to(cuda) if bias is not None else None
+    b, h, wd, cin = x.shape
+    k, _, _, cout = w.shape
+    y = torch.full((b, h, wd, cout), float("nan"), device=cuda)
+    _lib.check(_lib.lib().y2_conv2d(_lib.ptr(xs), b, h, wd, cin, _lib.ptr(ws), k, cout, _lib.ptr(sc), _lib.ptr(bi),
+                                    int(leaky), _lib.ptr(y), precision, block_n, k_splits, None))
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def _rel(a, b):
+    return float(np.abs(a.astype(np.float64) - b).max() / np.abs(b).max())
+
+
+# every distinct (k, cin, cout, spatial) of the 416 network, batch 2 (3 for the 13x13 layers: M tail)
+SHAPES = [(2, 208, 32, 3, 64), (2, 104, 64, 3, 128), (2, 104, 128, 1, 64), (2, 52, 128, 3, 256), (2, 52, 256, 1, 128),
+          (2, 26, 256, 3, 512), (2, 26, 512, 1, 256), (3, 13, 512, 3, 1024), (3, 13, 1024, 1, 512),
+          (3, 13, 1024, 3, 1024), (3, 13, 3072, 3, 1024), (3, 13, 1024, 1, 425), (3, 13, 1024, 1, 125),
+          (2, 19, 1024, 3, 1024), (1, 38, 256, 3, 512)]
+
+
+@pytest.mark.parametrize("b,hw,cin,k,cout", SHAPES)
+def test_conv_layer_shapes_vs_fp64(cuda, b, hw, cin, k, cout):
+    import torch
+    import torch.nn.functional as F
+    rs = np.random.RandomState(cin + cout + hw)
+    x = rs.normal(0, 1, size=(b, hw, hw, cin)).astype(np.float32)
+    w = (rs.normal(0, 1, size=(k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+    scale = rs.uniform(0.5, 1.5, size=cout).astype(np.float32)
+    bias = rs.normal(0, 0.1, size=cout).astype(np.float32)
+    got = _conv(cuda, x, w, scale, bias, True)
+    xd = torch.as_tensor(x).to(cuda).double().permute(0, 3, 1, 2)
+    wd = torch.as_tensor(w).to(cuda).double().permute(3, 2, 0, 1)
+    ref = F.conv2d(xd, wd, padding=k // 2).permute(0, 2, 3, 1) * torch.as_tensor(scale).to(cuda).double() \
+        + torch.as_tensor(bias).to(cuda).double()
+    ref = torch.maximum(ref, 0.1 * ref).cpu().numpy()
+    assert not np.isnan(got).any()
+    assert _rel(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("splits,block_n", [(1, 0), (3, 0), (5, 128), (2, 64)])
+def test_conv_splitk_and_tile_variants_vs_oracle(cuda, splits, block_n):
+    rs = np.random.RandomState(4)
+    x = rs.normal(0, 1, size=(2, 13, 13, 512)).astype(np.float32)
+    w = (rs.normal(0, 1, size=(3, 3, 512, 256)) * 0.02).astype(np.float32)
+    scale = rs.uniform(0.5, 1.5, size=256).astype(np.float32)
+    bias = rs.normal(0, 0.1, size=256).astype(np.float32)
+    ref = conv_bn_leaky_oracle(x, w, scale, bias)
+    got = _conv(cuda, x, w, scale, bias, True, k_splits=splits, block_n=block_n)
+    assert _rel(got, ref.astype(np.float64)) <= TOL
+
+
+def test_conv_single_pass_bf16_is_reduced_precision(cuda):
+    """precision=1 (hi planes only) must be ~bf16-grade: proves the x3 split is what buys fp32 parity."""
+    rs = np.random.RandomState(5)
+    x = rs.normal(0, 1, size=(1, 26, 26, 256)).astype(np.float32)
+    w = (rs.normal(0, 1, size=(3, 3, 256, 128)) * 0.03).astype(np.float32)
+    ref = conv_bn_leaky_oracle(x, w, np.ones(128, np.float32), np.zeros(128, np.float32), leaky=False)
+    e1 = _rel(_conv(cuda, x, w, None, None, False, precision=1), ref.astype(np.float64))
+    e0 = _rel(_conv(cuda, x, w, None, None, False, precision=0), ref.astype(np.float64))
+    assert e0 <= TOL and 1e-4 < e1 < 2e-2
+
+
+def _setup_store(params):
+    from yolo_tf_b200 import variables
+    store = variables.reset_default_store()
+    store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
+    return store
+
+
+@pytest.mark.parametrize("classes,size,batch,anchors", [(20, 416, 2, ho.ANCHORS_VOC), (80, 416, 1, ho.ANCHORS_COCO),
+                                                        (80, 608, 1, ho.ANCHORS_COCO), (20, 64, 3, ho.ANCHORS_VOC)])
+def test_darknet_forward_layer_by_layer_vs_oracle(cuda, classes, size, batch, anchors):
+    import torch
+    from yolo_tf_b200 import _lib
+    from yolo_tf_b200.model.yolo2 import inference
+    params = init_params(classes, 5, seed=1)
+    _setup_store(params)
+    rs = np.random.RandomState(2)
+    x = rs.normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
+    taps = {}
+    ref = darknet_oracle(x, params, classes, 5, taps=taps)
+    scope, out = inference.darknet(torch.from_numpy(x).to(cuda), classes, 5)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().y2_check_async_errors())
+    assert scope == "yolo2_darknet"
+    eng = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+    worst = {}
+    for i, (name, k, cin, cout, then) in enumerate(layer_table(classes, 5)[:-1]):
+        if i == 0:
+            got = eng.activation(0, True, taps["conv0/pool"].shape).cpu().numpy()
+            worst["conv0/pool"] = _rel(got, taps["conv0/pool"].astype(np.float64))
+            continue
+        got = eng.activation(i, False, taps[name].shape).cpu().numpy()
+        worst[name] = _rel(got, taps[name].astype(np.float64))
+        if then in ("pool", "passthrough+pool"):
+            gp = eng.activation(i, True, taps[name + "/pool"].shape).cpu().numpy()
+            worst[name + "/pool"] = _rel(gp, taps[name + "/pool"].astype(np.float64))
+    worst["output"] = _rel(out.cpu().numpy(), ref.astype(np.float64))
+    print("per-layer rel err:", {k: "%.1e" % v for k, v in worst.items()})
+    assert max(worst.values()) <= TOL, worst
+
+
+def test_xavier_checkpoint_config1(cuda):
+    """BASELINE config 1 weights: what slim creates (Xavier-uniform, BN gamma=1 beta=0 mean=0 var=1)."""
+    import torch
+    from yolo_tf_b200.model.yolo2 import inference
+    params = init_params(20, 5, seed=1, mode="xavier")
+    _setup_store(params)
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 256, size=(416, 416, 3)).astype(np.float32)
+    x = ((img - img.mean()) / max(img.std(), 1.0 / np.sqrt(img.size)))[None]      # utils/preprocess.py:23-25
+    ref = darknet_oracle(x, params, 20, 5)
+    _, out = inference.darknet(torch.from_numpy(x.astype(np.float32)).to(cuda), 20, 5)
+    assert _rel(out.cpu().numpy(), ref.astype(np.float64)) <= TOL
+
+
+def test_builder_surface_and_detection_pipeline(cuda):
+    """detect.py-shaped use: Builder -> model.conf/xy_min/xy_max -> non_max_suppress (numpy, in place)."""
+    import torch
+    from oracle.nms_oracle import nms_oracle
+    from yolo_tf_b200.model.yolo2 import Builder
+    from yolo_tf_b200.utils import postprocess
+    classes = 20
+    params = init_params(classes, 5, seed=3)
+    _setup_store(params)
+    rs = np.random.RandomState(1)
+    x = rs.normal(0, 1, size=(1, 96, 96, 3)).astype(np.float32)
+    builder = Builder.from_values([str(i) for i in range(classes)], 96, 96, ho.ANCHORS_VOC)
+    builder(torch.from_numpy(x).to(cuda))
+    m = builder.model
+    assert (m.cell_height, m.cell_width) == (3, 3) and m.conf.shape == (1, 9, 5, classes)
+    ref = ho.decode_oracle(darknet_oracle(x, params, classes, 5), classes, ho.ANCHORS_VOC)
+    for k in ("conf", "xy_min", "xy_max", "iou", "prob", "wh", "coords", "offset_xy_min", "areas", "wh01_sqrt"):
+        got = getattr(m, k).cpu().numpy()
+        assert np.abs(got - ref[k]).max() <= 1e-4 * max(1.0, np.abs(ref[k]).max()), k
+    conf = m.conf[0].cpu().numpy()
+    lo, hi = m.xy_min[0].cpu().numpy(), m.xy_max[0].cpu().numpy()
+    c_ref = conf.copy()
+    order_ref = nms_oracle(c_ref, lo, hi, 0.02, 0.4)
+    boxes = postprocess.non_max_suppress(conf, lo, hi, 0.02, 0.4)
+    assert np.array_equal(conf.view(np.uint32), c_ref.view(np.uint32))          # in-place side effect, bit-exact
+    assert len(boxes) == 45 and boxes[0][0].shape == (classes,)
+    flat = conf.reshape(-1, classes)
+    assert all(np.shares_memory(b[0], conf) for b in boxes[:3])
+    got_order = [int((b[0].__array_interface__["data"][0] - flat.__array_interface__["data"][0]) // (4 * classes)) for b in boxes]
+    assert got_order == order_ref.tolist()
+
+
+def test_objectives_through_builder(cuda):
+    import torch
+    from yolo_tf_b200.model.yolo2 import Model, Objectives
+    rs = np.random.RandomState(6)
+    classes, hc, wc, B = 20, 13, 13, 8
+    net = rs.normal(0, 1, size=(B, hc, wc, 5 * (5 + classes))).astype(np.float32)
+    labels = ho.synthetic_labels(B, classes, wc, hc, seed=6)
+    model = Model(torch.from_numpy(net).to(cuda), classes, ho.ANCHORS_VOC, training=True)
+    obj = Objectives(model, *labels, hparam=ho.HPARAM_DEFAULT)
+    ref_obj, ref_g = ho.loss_grad_oracle(net, classes, ho.ANCHORS_VOC, labels, dtype=np.float64)
+    for k in ref_obj:
+        assert abs(float(obj[k]) - ref_obj[k]) <= 1e-4 * abs(ref_obj[k]), k
+    assert abs(float(obj.total_loss()) - ho.total_loss_oracle(ref_obj)) <= 1e-4 * ho.total_loss_oracle(ref_obj)
+    assert np.abs(obj.grad_inputs.cpu().numpy() - ref_g).max() <= 1e-4 * np.abs(ref_g).max()
+    with pytest.raises(AttributeError):
+        model.conf                       # not built when training (model/yolo2/__init__.py:50)

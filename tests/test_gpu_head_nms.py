@@ -110,12 +110,12 @@ def _run_nms(cuda, conf, lo, hi, thr, thr_iou, want_order=True):
     from yolo_tf_b200 import _lib
     L = _lib.lib()
     B, N, C = conf.shape
-    c = _t(conf, cuda)
+    c, d_lo, d_hi = _t(conf, cuda), _t(lo, cuda), _t(hi, cuda)      # keep alive until the sync below
     order = torch.full((B, N), -1, dtype=torch.int32, device=cuda) if want_order else None
     status = torch.zeros(B, dtype=torch.int32, device=cuda)
     nbytes = L.y2_nms_workspace_bytes(B, N, C)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=cuda)
-    _lib.check(L.y2_nms(_lib.ptr(c), _lib.ptr(_t(lo, cuda)), _lib.ptr(_t(hi, cuda)), B, N, C, thr, thr_iou,
+    _lib.check(L.y2_nms(_lib.ptr(c), _lib.ptr(d_lo), _lib.ptr(d_hi), B, N, C, thr, thr_iou,
                         _lib.ptr(order), _lib.ptr(status), _lib.ptr(ws), nbytes, None))
     torch.cuda.synchronize()
     return c.cpu().numpy(), (order.cpu().numpy() if want_order else None), status.cpu().numpy()

@@ -39,6 +39,9 @@ _SIGNATURES = {
     "y2_nms_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "y2_nms": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "y2_check_async_errors": (c_i, []),
+    "y2_set_profiling": (c_i, [c_p, c_i]),
+    "y2_get_layer_ms": (c_i, [c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f)]),
+    "y2_launch_count": (ctypes.c_ulonglong, []),
 }
 EXPORTS = tuple(_SIGNATURES)
 

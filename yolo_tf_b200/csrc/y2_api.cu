@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,9 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 const char* last_error() { return g_err.c_str(); }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int device_sm_count(int device) {
     int n = 0;
@@ -96,6 +100,8 @@ struct y2_handle {
     int device = 0, classes = 0, anchors = 0, num_sms = 148;
     std::vector<LayerState> layers;
     Plan plan;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;     // 2 per layer (start, stop) + 2 for the pool/reorg passes of that layer
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -169,6 +175,7 @@ void y2_destroy(y2_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& s : h->layers) {
         cudaFree(s.wpack); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias);
     }
@@ -335,18 +342,22 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
         if (build_plan(h, B, H, W, ws, ws_bytes, precision)) return -1;
     const int nl = (int)h->layers.size();
     const LayerState& L0 = h->layers[0];
+    if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[0], s));
     {
         const size_t M0 = (size_t)B * (H / 2) * (W / 2);
         if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout, B, H, W, s)) return -1;
     }
+    if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[1], s));
     for (int i = 1; i < nl; ++i) {
         const LayerState& L = h->layers[i];
         TcConvLaunch T = P.launch[i];
+        if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i], s));
         const int final_mode = T.p.mode;
         if (i == nl - 1) T.p.out_f32 = out;
         if (T.p.k_splits > 1) T.p.mode = EPI_PARTIAL;
         if (tc_conv_launch(T, s)) return -1;
         if (T.p.k_splits > 1 && splitk_finish_launch(T.p, final_mode, s)) return -1;
+        if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i + 1], s));
         const int oh = P.oh[i], ow = P.ow[i];
         const size_t M = (size_t)B * oh * ow;
         if (L.d.passthrough) {
@@ -358,9 +369,37 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
                                       P.pooled[i] + (M / 4) * L.d.cout, B, oh, ow, L.d.cout, s))
                 return -1;
         }
+        if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i + 2], s));
     }
     return 0;
 }
+
+int y2_set_profiling(y2_handle* h, int enable) {
+    Y2_REQUIRE(h, "y2_set_profiling: null handle");
+    Y2_CUDA(cudaSetDevice(h->device));
+    if (enable && h->ev.empty()) {
+        h->ev.resize(4 * h->layers.size());
+        for (auto& e : h->ev) Y2_CUDA(cudaEventCreate(&e));
+    }
+    h->profiling = enable != 0;
+    return 0;
+}
+
+int y2_get_layer_ms(y2_handle* h, float* conv_ms, float* post_ms) {
+    Y2_REQUIRE(h && conv_ms && post_ms, "y2_get_layer_ms: null argument");
+    Y2_REQUIRE(h->profiling && !h->ev.empty(), "y2_get_layer_ms: profiling is off");
+    const int nl = (int)h->layers.size();
+    Y2_CUDA(cudaEventSynchronize(h->ev[4 * (nl - 1) + 2]));
+    Y2_CUDA(cudaEventElapsedTime(&conv_ms[0], h->ev[0], h->ev[1]));      // conv0 + pool (CUDA cores)
+    post_ms[0] = 0.f;
+    for (int i = 1; i < nl; ++i) {
+        Y2_CUDA(cudaEventElapsedTime(&conv_ms[i], h->ev[4 * i], h->ev[4 * i + 1]));
+        Y2_CUDA(cudaEventElapsedTime(&post_ms[i], h->ev[4 * i + 1], h->ev[4 * i + 2]));
+    }
+    return 0;
+}
+
+unsigned long long y2_launch_count(void) { return g_launches.load(); }
 
 int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* stream) {
     Y2_REQUIRE(h && dst, "y2_get_activation: null argument");

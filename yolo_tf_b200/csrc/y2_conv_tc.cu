@@ -346,6 +346,7 @@ static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
     }
     kern<<<L.grid, NUM_THREADS, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -372,6 +373,7 @@ int splitk_finish_launch(const ConvParams& p, int final_mode, cudaStream_t strea
     if (blocks > 148 * 16) blocks = 148 * 16;
     splitk_finish_kernel<<<blocks, 256, 0, stream>>>(p, final_mode);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

@@ -142,6 +142,7 @@ int head_decode_launch(const float* net, int B, int Hc, int Wc, int A, int C, co
     if (blocks > 148 * 4) blocks = 148 * 4;
     decode_kernel<<<(int)blocks, 256, smem, s>>>(a);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -302,8 +303,10 @@ int loss_launch(const float* net, int B, int Hc, int Wc, int A, int C, const flo
     Y2_REQUIRE(ws_bytes >= (size_t)grid * 4 * sizeof(double), "loss: workspace too small");
     loss_kernel<<<grid, 256, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     loss_finish_kernel<<<1, 32, 0, s>>>(a.partials, grid, 1.0 / cnt, objectives);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

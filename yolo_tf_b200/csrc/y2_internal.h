@@ -28,6 +28,8 @@ const char* last_error();
     } while (0)
 
 int device_sm_count(int device);
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+void note_launch();
 
 // ---- activation storage: "split planes" ----
 // A float32 NHWC tensor T[M][C] lives in HBM as two bf16 planes, hi = bf16(T) and

@@ -37,6 +37,7 @@ int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, 
                                                            reinterpret_cast<uint2*>(dst_hi),
                                                            reinterpret_cast<uint2*>(dst_lo), n / 4);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -63,6 +64,7 @@ int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows,
     Y2_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "merge_planes: cols and pitch must be multiples of 4");
     merge_planes_kernel<<<grid_for(rows * (size_t)(cols / 4), 256), 256, 0, s>>>(hi, lo, dst, rows, cols, ld);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -85,6 +87,7 @@ int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, in
     const size_t total = (size_t)cout_pad * ksize * ksize * cin;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, wpack, ksize * ksize, cin, cout, cout_pad);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -102,6 +105,7 @@ int bn_fold_launch(const float* gamma, const float* beta, const float* mean, con
                    float* bias, int n, cudaStream_t s) {
     bn_fold_kernel<<<(n + 127) / 128, 128, 0, s>>>(gamma, beta, mean, var, eps, scale, bias, n);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -160,6 +164,7 @@ int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
     maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -195,6 +200,7 @@ static int reorg_dispatch(const void* in, void* out, int B, int H, int W, size_t
     reorg_kernel<V><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const V*>(in), reinterpret_cast<V*>(out), B,
                                                         H, W, cvec, stride, (long long)(out_ld_bytes / sizeof(V)));
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 // Widest vector (16/8/4/2 bytes) that divides the channel run, the output pitch and both base addresses.

@@ -217,15 +217,18 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     dim3 grid((C + NMS_WARPS - 1) / NMS_WARPS, B);
     nms_select_kernel<<<grid, NMS_WARPS * 32, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     if (order_out) {
         nms_order_kernel<<<B, 256, (size_t)N * sizeof(float), s>>>(a);
         Y2_CUDA(cudaGetLastError());
+    note_launch();
     }
     const size_t total = (size_t)B * N * C;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

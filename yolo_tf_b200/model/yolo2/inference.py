@@ -12,6 +12,36 @@ from ... import _lib
 from ... import variables as V
 
 
+def layer_geometry(classes, num_anchors):
+    """[(name, ksize, cin, cout, has_bn, pool_after)] of the 22 convs in graph order
+    (inference.py:70-118): host-side table, same as the one compiled into the library."""
+    t, cin, ch = [], 3, 32
+
+    def add(k, cout, pool=False):
+        nonlocal cin
+        t.append(("conv%d" % len(t), k, cin, cout, True, pool))
+        cin = cout
+
+    for _ in range(2):
+        add(3, ch, True)
+        ch *= 2
+    for _ in range(2):
+        add(3, ch)
+        add(1, ch // 2)
+        add(3, ch, True)
+        ch *= 2
+    for k, c in ((3, ch), (1, ch // 2), (3, ch), (1, ch // 2)):
+        add(k, c)
+    add(3, ch, True)
+    ch *= 2
+    for k, c in ((3, ch), (1, ch // 2), (3, ch), (1, ch // 2), (3, ch), (3, ch), (3, ch)):
+        add(k, c)
+    cin = 4 * 512 + ch
+    add(3, ch)
+    t.append(("conv", 1, ch, num_anchors * (5 + classes), False, False))
+    return t
+
+
 class _Engine(object):
     """One y2_handle per (device, classes, anchors); re-uploads weights when the store changes."""
     _cache = {}
@@ -85,7 +115,10 @@ class _Engine(object):
         return out
 
 
-def darknet(net, classes, num_anchors, training=False, center=True, precision=0):
+PRECISION = 0      # 0 = split-bf16 x3 (fp32-grade, the parity mode); 1 = single bf16 pass
+
+
+def darknet(net, classes, num_anchors, training=False, center=True, precision=None):
     """Darknet-19 + passthrough backbone (inference.py:61-120).
 
     net: float32 CUDA tensor [B, H, W, 3] NHWC.  Returns ``(scope, output)`` with
@@ -100,7 +133,7 @@ def darknet(net, classes, num_anchors, training=False, center=True, precision=0)
         raise _lib.Y2Error("darknet: input must be a CUDA tensor (no CPU path exists)")
     eng = _Engine.get(net.device, classes, num_anchors)
     eng.sync_weights(scope, V.default_store(), net.device, center=center)
-    out = eng.forward(net.contiguous(), precision=precision)
+    out = eng.forward(net.contiguous(), precision=PRECISION if precision is None else precision)
     return scope, out
 
 
