@@ -74,9 +74,10 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
 
 /* One conv (+scale/bias +leaky) on float32 NHWC tensors through the same tcgen05 kernel the
  * network uses (splits operands on the fly).  Diagnostic / test entry point.
- * block_n = 0 and k_splits = 0 pick defaults. */
+ * block_n = 0 picks the tile width; max_ctas = 0 uses every SM (smaller values change how the
+ * stream-K scheduler cuts tiles across CTAs -- used by tests to exercise the partial hand-off). */
 int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
-              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int k_splits,
+              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int max_ctas,
               void* stream);
 
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.

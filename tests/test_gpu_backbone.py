@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, k_splits=0):
+def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, max_ctas=0):
     import torch
     from yolo_tf_b200 import _lib
     xs, ws = torch.as_tensor(x).to(cuda), torch.as_tensor(w).to(cuda)
@@ -24,7 +24,7 @@ def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, k_splits=0):
     k, _, _, cout = w.shape
     y = torch.full((b, h, wd, cout), float("nan"), device=cuda)
     _lib.check(_lib.lib().y2_conv2d(_lib.ptr(xs), b, h, wd, cin, _lib.ptr(ws), k, cout, _lib.ptr(sc), _lib.ptr(bi),
-                                    int(leaky), _lib.ptr(y), precision, block_n, k_splits, None))
+                                    int(leaky), _lib.ptr(y), precision, block_n, max_ctas, None))
     torch.cuda.synchronize()
     return y.cpu().numpy()
 
@@ -59,15 +59,28 @@ def test_conv_layer_shapes_vs_fp64(cuda, b, hw, cin, k, cout):
     assert _rel(got, ref) <= TOL
 
 
-@pytest.mark.parametrize("splits,block_n", [(1, 0), (3, 0), (5, 128), (2, 64)])
-def test_conv_splitk_and_tile_variants_vs_oracle(cuda, splits, block_n):
+@pytest.mark.parametrize("max_ctas,block_n", [(0, 0), (1, 0), (3, 0), (5, 128), (37, 64), (148, 32)])
+def test_conv_streamk_and_tile_variants_vs_oracle(cuda, max_ctas, block_n):
+    """Stream-K hand-off: 3 m-tiles x K=72 k-blocks cut across 1..72 CTAs (up to ~24 contributors per tile)."""
     rs = np.random.RandomState(4)
     x = rs.normal(0, 1, size=(2, 13, 13, 512)).astype(np.float32)
     w = (rs.normal(0, 1, size=(3, 3, 512, 256)) * 0.02).astype(np.float32)
     scale = rs.uniform(0.5, 1.5, size=256).astype(np.float32)
     bias = rs.normal(0, 0.1, size=256).astype(np.float32)
     ref = conv_bn_leaky_oracle(x, w, scale, bias)
-    got = _conv(cuda, x, w, scale, bias, True, k_splits=splits, block_n=block_n)
+    got = _conv(cuda, x, w, scale, bias, True, max_ctas=max_ctas, block_n=block_n)
+    assert _rel(got, ref.astype(np.float64)) <= TOL
+    again = _conv(cuda, x, w, scale, bias, True, max_ctas=max_ctas, block_n=block_n)
+    assert np.array_equal(got.view(np.uint32), again.view(np.uint32))      # fixed summation order: bit-reproducible
+
+
+def test_conv_streamk_many_contributors(cuda):
+    """2 tiles x 144 k-blocks over 72 CTAs: every tile is assembled from ~36 partials."""
+    rs = np.random.RandomState(8)
+    x = rs.normal(0, 1, size=(1, 13, 13, 1024)).astype(np.float32)
+    w = (rs.normal(0, 1, size=(3, 3, 1024, 256)) * 0.015).astype(np.float32)
+    ref = conv_bn_leaky_oracle(x, w, np.ones(256, np.float32), np.zeros(256, np.float32))
+    got = _conv(cuda, x, w, None, None, True)
     assert _rel(got, ref.astype(np.float64)) <= TOL
 
 

@@ -29,7 +29,7 @@ def ref_conv(x, w, scale, bias, leaky):
     return y
 
 
-def run_case(name, B, H, W, cin, k, cout, precision=0, block_n=0, k_splits=0, pattern="random", leaky=1, affine=True,
+def run_case(name, B, H, W, cin, k, cout, precision=0, block_n=0, max_ctas=0, pattern="random", leaky=1, affine=True,
              dump=False):
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(hash(name) % 1000)
@@ -45,10 +45,10 @@ def run_case(name, B, H, W, cin, k, cout, precision=0, block_n=0, k_splits=0, pa
     y = torch.full((B, H, W, cout), float("nan"), device="cuda")
     t0 = time.time()
     rc = L.y2_conv2d(_lib.ptr(x), B, H, W, cin, _lib.ptr(w), k, cout, _lib.ptr(scale), _lib.ptr(bias), leaky,
-                     _lib.ptr(y), precision, block_n, k_splits, None)
+                     _lib.ptr(y), precision, block_n, max_ctas, None)
     torch.cuda.synchronize()
     res = {"name": name, "shape": [B, H, W, cin, k, cout], "precision": precision, "block_n": block_n,
-           "k_splits": k_splits, "rc": rc, "secs": round(time.time() - t0, 3)}
+           "max_ctas": max_ctas, "rc": rc, "secs": round(time.time() - t0, 3)}
     if rc != 0:
         res["error"] = L.y2_last_error().decode()
         return res
@@ -86,7 +86,7 @@ def main():
         dict(name="h_3x3_c64_multi_image", B=3, H=13, W=13, cin=64, k=3, cout=128, precision=0),
         dict(name="i_3x3_c32_sw64", B=2, H=16, W=16, cin=32, k=3, cout=64, precision=0),
         dict(name="j_1x1_n425_tail", B=3, H=13, W=13, cin=1024, k=1, cout=425, precision=0, leaky=0),
-        dict(name="k_3x3_splitk4", B=2, H=13, W=13, cin=512, k=3, cout=256, precision=0, k_splits=4),
+        dict(name="k_3x3_splitk4", B=2, H=13, W=13, cin=512, k=3, cout=256, precision=0, max_ctas=4),
         dict(name="l_3x3_n512_two_ntiles", B=2, H=26, W=26, cin=256, k=3, cout=512, precision=0),
         dict(name="m_3x3_bn128", B=2, H=26, W=26, cin=128, k=3, cout=256, precision=0, block_n=128),
         dict(name="n_conv1_shape", B=2, H=208, W=208, cin=32, k=3, cout=64, precision=0),

@@ -88,7 +88,7 @@ struct Plan {
     std::vector<bf16*> pooled;    // pooled planes for pool layers (>0)
     std::vector<int> oh, ow;      // conv output spatial size per layer
     bf16* concat = nullptr;
-    float* partial = nullptr;
+    void* streamk = nullptr;
     std::vector<TcConvLaunch> launch;   // per layer (index 0 unused)
 };
 
@@ -112,25 +112,6 @@ static void choose_tiles(int cout, int* block_n, int* cout_pad) {
     const int bn = (int)align_up((size_t)((p32 + nt - 1) / nt), 32);
     *block_n = bn;
     *cout_pad = bn * nt;
-}
-
-// split-K factor: minimise waves * (k-blocks per split + fixed per-tile overhead); the 13x13 layers at
-// batch 32 have ~172 tiles for 148 SMs and K up to 432 k-blocks.
-static int choose_splits(long long M, int cout_pad, int block_n, int kblocks, int num_sms) {
-    const long long tiles = ((M + 127) / 128) * (cout_pad / block_n);
-    if (tiles >= 4LL * num_sms) return 1;
-    int best = 1;
-    double best_cost = 1e30;
-    for (int ks = 1; ks <= 16; ++ks) {
-        const int per = (kblocks + ks - 1) / ks;
-        if (ks > 1 && per < 6) break;
-        const int eff = (kblocks + per - 1) / per;
-        const long long waves = (tiles * eff + num_sms - 1) / num_sms;
-        double cost = (double)waves * (per + 3.0);
-        if (eff > 1) cost += 2.0 + 0.5 * eff;          // partial write + finish pass
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = eff; }
-    }
-    return best;
 }
 
 extern "C" {
@@ -222,16 +203,14 @@ int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* g
 struct WsLayout {
     std::vector<size_t> act_off, pool_off;
     std::vector<int> oh, ow;
-    size_t concat_off = 0, partial_off = 0, total = 0;
-    std::vector<int> splits;
+    size_t concat_off = 0, streamk_off = 0, total = 0;
 };
 static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* out) {
     Y2_REQUIRE(B > 0 && H > 0 && W > 0, "workspace: bad shape");
     Y2_REQUIRE(H % 32 == 0 && W % 32 == 0, "input size %dx%d is not divisible by the downsampling 32 (utils/__init__.py:52-56)", W, H);
     const int nl = (int)h->layers.size();
     out->act_off.assign(nl, 0); out->pool_off.assign(nl, 0); out->oh.assign(nl, 0); out->ow.assign(nl, 0);
-    out->splits.assign(nl, 1);
-    size_t off = 0, partial_max = 0;
+    size_t off = 0;
     int ch = H, cw = W;
     for (int i = 0; i < nl; ++i) {
         const LayerState& L = h->layers[i];
@@ -242,13 +221,6 @@ static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* o
             off = align_up(off + 2 * (M / 4) * L.d.cout * sizeof(bf16), 1024);
             ch /= 2; cw /= 2;
             continue;
-        }
-        const int BK = (L.d.cin % 64 == 0) ? 64 : 32;
-        const int kblocks = L.d.ksize * L.d.ksize * (L.d.cin / BK);
-        out->splits[i] = choose_splits((long long)M, L.cout_pad, L.block_n, kblocks, h->num_sms);
-        if (out->splits[i] > 1) {
-            const size_t pb = (size_t)out->splits[i] * M * L.cout_pad * sizeof(float);
-            if (pb > partial_max) partial_max = pb;
         }
         if (i == nl - 1) break;                    // final layer writes the caller's buffer
         if (i == nl - 3) {                         // conv19 writes into the concat buffer
@@ -265,8 +237,8 @@ static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* o
     }
     out->concat_off = off;
     off = align_up(off + 2 * (size_t)B * ch * cw * (4 * 512 + 1024) * sizeof(bf16), 1024);
-    out->partial_off = off;
-    off = align_up(off + partial_max, 1024);
+    out->streamk_off = off;
+    off = align_up(off + tc_conv_streamk_bytes(h->num_sms), 1024);
     out->total = off;
     return 0;
 }
@@ -278,7 +250,7 @@ size_t y2_workspace_bytes(const y2_handle* h, int B, int H, int W) {
     return l.total;
 }
 
-static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_bytes, int precision) {
+static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_bytes, int precision, cudaStream_t s) {
     WsLayout l;
     if (layout_workspace(h, B, H, W, &l)) return -1;
     Y2_REQUIRE(ws && ws_bytes >= l.total, "y2_darknet_forward: workspace too small (%zu < %zu)", ws_bytes, l.total);
@@ -291,7 +263,8 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
     P.act.assign(nl, nullptr); P.pooled.assign(nl, nullptr); P.oh = l.oh; P.ow = l.ow;
     P.launch.resize(nl);
     P.concat = reinterpret_cast<bf16*>(base + l.concat_off);
-    P.partial = reinterpret_cast<float*>(base + l.partial_off);
+    P.streamk = base + l.streamk_off;
+    Y2_CUDA(cudaMemsetAsync(P.streamk, 0, 4096, s));          // hand-off flags start at 0 (epochs are >= 1)
     for (int i = 0; i < nl; ++i) {
         if (l.act_off[i] != (size_t)-1 && i != nl - 1) P.act[i] = reinterpret_cast<bf16*>(base + l.act_off[i]);
         if (i > 0 && h->layers[i].d.pool) P.pooled[i] = reinterpret_cast<bf16*>(base + l.pool_off[i]);
@@ -305,13 +278,12 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
         if (i == nl - 2) input = P.concat;         // conv20 reads concat([reorg, conv19])
         TcConvLaunch& T = P.launch[i];
         if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin, L.d.ksize, L.wpack, L.d.cout, L.cout_pad, L.block_n,
-                         l.splits[i], precision == 0, h->num_sms))
+                         0, precision == 0, h->num_sms, P.streamk))
             return -1;
         ConvParams& p = T.p;
         p.scale = L.d.has_bn ? L.scale : nullptr;
         p.bias = L.bias;
         p.leaky = L.d.has_bn ? 1 : 0;
-        p.partial = P.partial;
         if (i == nl - 1) {
             p.mode = EPI_F32; p.ldc = L.d.cout;    // out pointer patched per call
         } else if (i == nl - 3) {
@@ -339,7 +311,7 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
     Y2_CUDA(cudaSetDevice(h->device));
     Plan& P = h->plan;
     if (!P.valid || P.B != B || P.H != H || P.W != W || P.ws != ws || P.precision != precision || P.ws_bytes != ws_bytes)
-        if (build_plan(h, B, H, W, ws, ws_bytes, precision)) return -1;
+        if (build_plan(h, B, H, W, ws, ws_bytes, precision, s)) return -1;
     const int nl = (int)h->layers.size();
     const LayerState& L0 = h->layers[0];
     if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[0], s));
@@ -352,11 +324,8 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
         const LayerState& L = h->layers[i];
         TcConvLaunch T = P.launch[i];
         if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i], s));
-        const int final_mode = T.p.mode;
         if (i == nl - 1) T.p.out_f32 = out;
-        if (T.p.k_splits > 1) T.p.mode = EPI_PARTIAL;
         if (tc_conv_launch(T, s)) return -1;
-        if (T.p.k_splits > 1 && splitk_finish_launch(T.p, final_mode, s)) return -1;
         if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i + 1], s));
         const int oh = P.oh[i], ow = P.ow[i];
         const size_t M = (size_t)B * oh * ow;
@@ -426,7 +395,7 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
 }
 
 int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
-              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int k_splits,
+              const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int max_ctas,
               void* stream) {
     Y2_REQUIRE(x && w_hwio && y, "y2_conv2d: null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -437,31 +406,25 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
     choose_tiles(cout, &bn, &cpad);
     if (block_n > 0) { bn = block_n; cpad = (int)align_up((size_t)cout, (size_t)bn); }
     const size_t M = (size_t)B * H * W, K = (size_t)ksize * ksize * cin;
-    const int BK = (cin % 64 == 0) ? 64 : 32;
-    if (k_splits <= 0) k_splits = choose_splits((long long)M, cpad, bn, ksize * ksize * (cin / BK), num_sms);
     bf16 *xp = nullptr, *wp = nullptr;
-    float* partial = nullptr;
+    void* sk = nullptr;
     int rc = -1;
     do {
-        if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&wp, 2 * (size_t)cpad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
+        if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&wp, 2 * (size_t)cpad * K * sizeof(bf16)) != cudaSuccess ||
+            cudaMalloc(&sk, tc_conv_streamk_bytes(num_sms)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
+        if (cudaMemsetAsync(sk, 0, 4096, s) != cudaSuccess) { set_error("y2_conv2d: memset failed"); break; }
         if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
         if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s)) break;
         TcConvLaunch T;
-        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, k_splits, precision == 0, num_sms)) break;
+        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk)) break;
         T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
         T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
-        if (T.p.k_splits > 1) {
-            if (cudaMalloc(&partial, (size_t)T.p.k_splits * M * cpad * sizeof(float)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
-            T.p.partial = partial;
-            T.p.mode = EPI_PARTIAL;
-        }
         if (tc_conv_launch(T, s)) break;
-        if (T.p.k_splits > 1 && splitk_finish_launch(T.p, EPI_F32, s)) break;
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         if (tc_conv_check_watchdog()) break;
         rc = 0;
     } while (0);
-    cudaFree(xp); cudaFree(wp); cudaFree(partial);
+    cudaFree(xp); cudaFree(wp); cudaFree(sk);
     return rc;
 }
 

@@ -45,11 +45,12 @@ conv0_pool_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio,
         const size_t obase = (((size_t)b * Ho + yo) * Wo + xo) * 32;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            float acc[4][16];
+            // packed fp32 FMA (FFMA2, sm_100): two output channels per instruction
+            float2 acc2[4][8];
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int n = 0; n < 16; ++n) acc[p][n] = 0.f;
+                for (int n = 0; n < 8; ++n) acc2[p][n] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -57,19 +58,29 @@ conv0_pool_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio,
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float4* wr = reinterpret_cast<const float4*>(&sw[((ky * 3 + kx) * 3 + c) * 32 + half * 16]);
-                        float wv[16];
+                        float2 wv[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 q = wr[j];
-                            wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
+                            wv[2 * j] = make_float2(q.x, q.y);
+                            wv[2 * j + 1] = make_float2(q.z, q.w);
                         }
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const float v = patch[(p >> 1) + ky][(p & 1) + kx][c];
+                            const float2 vv = make_float2(v, v);
 #pragma unroll
-                            for (int n = 0; n < 16; ++n) acc[p][n] = fmaf(v, wv[n], acc[p][n]);
+                            for (int n = 0; n < 8; ++n) acc2[p][n] = __ffma2_rn(vv, wv[n], acc2[p][n]);
                         }
                     }
+            float acc[4][16];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    acc[p][2 * n] = acc2[p][n].x;
+                    acc[p][2 * n + 1] = acc2[p][n].y;
+                }
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int n = 0; n < 16; n += 2) {

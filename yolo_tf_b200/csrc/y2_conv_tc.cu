@@ -14,10 +14,16 @@
 //     warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> regs -> BN scale/bias + leaky ->
 //     bf16 hi/lo split -> global).  Two 256-column TMEM accumulators double-buffer the
 //     epilogue against the next tile's MMAs.
-//   * Optional split-K (raw fp32 partials + a finishing kernel) for the 13x13 / 19x19 layers
-//     whose tile count does not fill 148 SMs.
+//   * Stream-K scheduling: the (tile, k-block) iteration space of a layer is cut into gridDim.x equal
+//     contiguous ranges, so every SM gets the same number of MMAs whatever the tile count (the 13x13
+//     layers at batch 32 have 172 tiles for 148 SMs).  A range that starts inside a tile produces a
+//     raw fp32 partial (one 128 x block_n slot per CTA, L2-resident) and raises a flag; the CTA that
+//     owns the tile's first k-block runs last in time, adds the partials in fixed order
+//     (deterministic) and applies the epilogue.  No second kernel, no atomics.
 #include <stdio.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "y2_internal.h"
 #include "y2_ptx.cuh"
@@ -32,6 +38,26 @@ static constexpr int ACC_COLS = 256;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 static constexpr int SB_BYTES = 2 * 256 * 4;      // scale/bias staging for one tile
 static constexpr int BAR_BYTES = 256;
+
+// stream-K hand-off flags: one word per CTA, value = launch epoch (monotonic, never reset)
+__device__ __forceinline__ void flag_set(unsigned int* f, unsigned int epoch) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const unsigned int* f, unsigned int epoch, uint32_t tag) {
+    const long long t0 = clock64();
+    unsigned int v, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == epoch) return;
+        if ((++spins & 63u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int*>(&g_watchdog.fired)) return;
+            if (clock64() - t0 > 2000000000LL) {
+                watchdog_fire(tag, epoch);
+                return;
+            }
+        }
+    }
+}
 
 template <int BK, bool SPLIT3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -78,8 +104,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int units = p.m_tiles * p.n_tiles * p.k_splits;
-    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int KB = p.kblocks_total;
+    const long long sk_total = (long long)p.m_tiles * p.n_tiles * KB;
+    const long long sk_begin = sk_total * blockIdx.x / gridDim.x;
+    const long long sk_end = sk_total * (blockIdx.x + 1) / gridDim.x;
     const int cblocks = p.Cin / BK;
     const int pad = p.ksize / 2;
     const int hw = p.H * p.W;
@@ -89,19 +117,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ks = u / tiles_mn;
-                const int r = u - ks * tiles_mn;
-                const int nt = r / p.m_tiles;
-                const int mt = r - nt * p.m_tiles;
+            for (long long cur = sk_begin; cur < sk_end;) {
+                const int tile = (int)(cur / KB);
+                const int kb0 = (int)(cur - (long long)tile * KB);
+                const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
+                cur += kb1 - kb0;
+                const int nt = tile / p.m_tiles;
+                const int mt = tile - nt * p.m_tiles;
                 const int m0 = mt * BLOCK_M;
                 const int img = m0 / hw;
                 const int rem = m0 - img * hw;
                 const int y0 = rem / p.W;
                 const int x0 = rem - y0 * p.W;
                 const int n0 = nt * p.block_n;
-                const int kb0 = ks * p.kb_per_split;
-                const int kb1 = min(p.kblocks_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int tap = kb / cblocks;
                     const int c0 = (kb - tap * cblocks) * BK;
@@ -134,10 +162,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ks = u / tiles_mn;
-                const int kb0 = ks * p.kb_per_split;
-                const int kb1 = min(p.kblocks_total, kb0 + p.kb_per_split);
+            for (long long cur = sk_begin; cur < sk_end;) {
+                const int tile = (int)(cur / KB);
+                const int kb0 = (int)(cur - (long long)tile * KB);
+                const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
+                cur += kb1 - kb0;
                 mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -178,18 +207,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int et = threadIdx.x - EPI_WARP0 * 32;       // 0..127
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int ks = u / tiles_mn;
-            const int r = u - ks * tiles_mn;
-            const int nt = r / p.m_tiles;
-            const int mt = r - nt * p.m_tiles;
+        float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
+        for (long long cur = sk_begin; cur < sk_end;) {
+            const int tile = (int)(cur / KB);
+            const int kb0 = (int)(cur - (long long)tile * KB);
+            const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
+            cur += kb1 - kb0;
+            const int nt = tile / p.m_tiles;
+            const int mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
             const long long row = (long long)mt * BLOCK_M + q * 32 + lane;
             const bool row_ok = row < p.M;
+            const bool is_head = (kb0 == 0);                 // owns the tile's output
+            // CTAs blockIdx.x+1 .. last_contrib start inside this tile and hold its other k-ranges
+            int last_contrib = blockIdx.x;
+            if (is_head && kb1 < KB) {
+                const long long tile_end = (long long)(tile + 1) * KB;
+                while (last_contrib + 1 < (int)gridDim.x &&
+                       sk_total * (last_contrib + 1) / gridDim.x < tile_end)
+                    ++last_contrib;
+            }
 
             // stage this tile's scale/bias (previous tile's readers are past the first barrier)
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (p.mode != EPI_PARTIAL) {
+            if (is_head) {
                 for (int i = et; i < p.block_n; i += 128) {
                     const int n = n0 + i;
                     sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
@@ -200,26 +241,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
             mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
             tc_fence_after();
+            // the other contributors ran at the START of their ranges: normally long done
+            for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {
+                if (lane == 0) flag_wait(p.sk_flags + h, p.epoch, 0x500u);
+                __syncwarp();
+            }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
-                if (p.mode == EPI_PARTIAL) {
-                    if (row_ok) {
-                        float4* dst = reinterpret_cast<float4*>(
-                            p.partial + ((size_t)ks * p.M + (size_t)row) * (size_t)(p.n_tiles * p.block_n) + n0 + c);
+                if (!is_head) {                              // raw partial -> this CTA's slot
+                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     continue;
                 }
                 float f[32];
 #pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {      // fixed order: deterministic sum
+                    const float4* src = reinterpret_cast<const float4*>(
+                        p.sk_partial + (size_t)h * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = __ldcg(src + j);
+                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                    }
+                }
+#pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float t = __uint_as_float(v[j]) * sb[c + j] + sb[256 + c + j];
+                    float t = f[j] * sb[c + j] + sb[256 + c + j];
                     f[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
                 }
                 if (!row_ok) continue;
@@ -251,6 +305,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (!is_head) {                                  // publish the partial: all 128 rows written -> flag
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) flag_set(p.sk_flags + blockIdx.x, p.epoch);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -261,52 +320,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// split-K finish: out = epilogue(sum_ks partial[ks])
-__global__ void splitk_finish_kernel(ConvParams p, int final_mode) {
-    const int n_pad = p.n_tiles * p.block_n;
-    const size_t total = (size_t)p.M * (size_t)(p.N / 4 + ((p.N % 4) ? 1 : 0));
-    const int nq = p.N / 4 + ((p.N % 4) ? 1 : 0);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t row = i / nq;
-        const int n = (int)(i - row * nq) * 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ks = 0; ks < p.k_splits; ++ks) {
-            const float4 t = *reinterpret_cast<const float4*>(p.partial + ((size_t)ks * p.M + row) * n_pad + n);
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
-        float f[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int nn = n + j;
-            const float sc = (p.scale && nn < p.N) ? __ldg(p.scale + nn) : 1.0f;
-            const float bi = (p.bias && nn < p.N) ? __ldg(p.bias + nn) : 0.0f;
-            const float t = f[j] * sc + bi;
-            f[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
-        }
-        if (final_mode == EPI_PLANES) {
-            __nv_bfloat16 h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                h[j] = __float2bfloat16_rn(f[j]);
-                l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
-            }
-            uint2 hv, lv;
-            hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-            hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-            lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-            lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-            *reinterpret_cast<uint2*>(p.out_hi + row * p.ldc + n) = hv;
-            *reinterpret_cast<uint2*>(p.out_lo + row * p.ldc + n) = lv;
-        } else {
-            float* dst = p.out_f32 + row * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (n + j < p.N) dst[j] = f[j];
-        }
     }
 }
 
@@ -350,7 +363,15 @@ static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
     return 0;
 }
 
-int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream) {
+static std::atomic<unsigned int> g_epoch{0};
+
+size_t tc_conv_streamk_bytes(int num_sms) { return (size_t)num_sms * (BLOCK_M * 256 * sizeof(float)) + 4096; }
+
+int tc_conv_launch(const TcConvLaunch& Lc, cudaStream_t stream) {
+    TcConvLaunch L = Lc;
+    unsigned int e = g_epoch.fetch_add(1) + 1;
+    if (e == 0) e = g_epoch.fetch_add(1) + 1;          // 0 is the "never written" value of a fresh flag buffer
+    L.p.epoch = e;
     if (L.block_k == 64) return L.split3 ? launch_inst<64, true>(L, stream) : launch_inst<64, false>(L, stream);
     return L.split3 ? launch_inst<32, true>(L, stream) : launch_inst<32, false>(L, stream);
 }
@@ -367,18 +388,8 @@ int tc_conv_check_watchdog() {
     return -3;
 }
 
-int splitk_finish_launch(const ConvParams& p, int final_mode, cudaStream_t stream) {
-    const size_t total = (size_t)p.M * (size_t)((p.N + 3) / 4);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(p, final_mode);
-    Y2_CUDA(cudaGetLastError());
-    note_launch();
-    return 0;
-}
-
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize, const bf16* wpack,
-                 int cout, int cout_pad, int block_n, int k_splits, int split3, int num_sms) {
+                 int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws) {
     if (load_driver_entry_points()) return -1;
     Y2_REQUIRE(ksize == 1 || ksize == 3, "tc conv: ksize must be 1 or 3 (got %d)", ksize);
     Y2_REQUIRE(Cin % 32 == 0, "tc conv: Cin must be a multiple of 32 (got %d)", Cin);
@@ -397,11 +408,10 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
     p.n_tiles = cout_pad / block_n;
     p.kblocks_total = taps * (Cin / BK);
-    if (k_splits < 1) k_splits = 1;
-    if (k_splits > p.kblocks_total) k_splits = p.kblocks_total;
-    p.kb_per_split = (p.kblocks_total + k_splits - 1) / k_splits;
-    p.k_splits = (p.kblocks_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
     p.cout_pad = cout_pad;
+    Y2_REQUIRE(sk_ws && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0, "tc conv: stream-K workspace missing/unaligned");
+    p.sk_flags = static_cast<unsigned int*>(sk_ws);                         // [num_sms] (first 4 KiB)
+    p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
     const int planes = split3 ? 2 : 1;
     const int stage_bytes = planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
     int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES) / stage_bytes;
@@ -411,8 +421,14 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
-    const int units = p.m_tiles * p.n_tiles * p.k_splits;
-    L->grid = units < num_sms ? units : num_sms;
+    // stream-K grid: every CTA gets the same number of k-blocks; never fewer than 4 per CTA
+    const long long total_kb = (long long)p.m_tiles * p.n_tiles * p.kblocks_total;
+    long long grid = num_sms;
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (grid > total_kb / 4) grid = total_kb / 4;
+    if (grid < 1) grid = 1;
+    Y2_REQUIRE(grid <= 1024, "tc conv: grid too large for the flag page");
+    L->grid = (int)grid;
 
     // activation map: (C, W, H, N=2B) bf16, im2col mode, BLOCK_M pixels x BK channels per load
     {

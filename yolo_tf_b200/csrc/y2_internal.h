@@ -41,12 +41,11 @@ typedef __nv_bfloat16 bf16;
 enum EpilogueMode : int {
     EPI_PLANES = 0,    // y = leaky?(acc*scale+bias) -> bf16 hi/lo planes
     EPI_F32 = 1,       // y = leaky?(acc*scale+bias) -> float32 (final layer / debugging)
-    EPI_PARTIAL = 2,   // raw accumulators -> split-K workspace [ks][M][n_pad] float32
 };
 
 struct ConvParams {
     int M, N, Cin, ksize, B, H, W;
-    int block_n, m_tiles, n_tiles, k_splits, kblocks_total, kb_per_split;
+    int block_n, m_tiles, n_tiles, kblocks_total;
     int cout_pad;            // rows per weight plane in the packed weight matrix
     int num_stages;
     int mode;                // EpilogueMode
@@ -56,7 +55,9 @@ struct ConvParams {
     bf16* out_hi;            // EPI_PLANES (already offset to the first output channel)
     bf16* out_lo;
     float* out_f32;          // EPI_F32
-    float* partial;          // EPI_PARTIAL
+    float* sk_partial;       // stream-K: [grid][128][block_n] raw fp32 partial tiles
+    unsigned int* sk_flags;  // stream-K: [grid] hand-off flags (value = launch epoch)
+    unsigned int epoch;      // set per launch
     long long ldc;           // output row pitch, elements
 };
 
@@ -70,12 +71,13 @@ struct TcConvLaunch {
 // Builds tensor maps + launch geometry for one conv.  in_planes: bf16 [2][B][H][W][Cin].
 // wpack: bf16 [2][cout_pad][ksize*ksize*Cin] (k = tap*Cin + c).  Returns 0 or <0 (error set).
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
-                 const bf16* wpack, int cout, int cout_pad, int block_n, int k_splits, int split3, int num_sms);
+                 const bf16* wpack, int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms,
+                 void* streamk_ws);
+// bytes of the stream-K scratch (flags page + one partial tile per SM); must be zeroed once before first use
+size_t tc_conv_streamk_bytes(int num_sms);
 int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 // Reads and clears the barrier watchdog; returns 0 if it never fired, else sets the error.
 int tc_conv_check_watchdog();
-// Sum split-K partials and apply the epilogue (mode EPI_PLANES or EPI_F32 fields of p).
-int splitk_finish_launch(const ConvParams& p, int final_mode, cudaStream_t stream);
 
 // ---- elementwise / layout kernels (y2_layout.cu) ----
 int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s);
