@@ -67,6 +67,24 @@ int y2_set_profiling(y2_handle* h, int enable);
 int y2_get_layer_ms(y2_handle* h, float* conv_ms, float* post_ms);
 unsigned long long y2_launch_count(void);
 
+/* ---- training step (BASELINE config 3) ------------------------------------------------------
+ * `builder(batch, training=True)` (train.py:109-110): forward with BATCH statistics
+ * (slim.batch_norm(is_training=True): population variance over (B,H,W), moving averages updated with
+ * decay 0.999 as slim's UPDATE_OPS do), activations kept in `ws` for the backward.
+ * y2_darknet_backward = the tf.gradients part of slim.learning.create_train_op (train.py:127-129):
+ * dnet = d(total_loss)/d(out) (from y2_loss_fwd_bwd) -> gradients of every variable in ONE flat float32
+ * bucket of y2_param_count() elements, laid out per layer (conv0..conv20, conv) as
+ * [weights HWIO | gamma | beta] or [weights | biases] (y2_param_offsets) -- the unit of the single NCCL
+ * all-reduce per step.  y2_get_bn_state reads back gamma/beta/moving statistics (device pointers). */
+size_t y2_train_workspace_bytes(const y2_handle* h, int B, int H, int W);
+int y2_darknet_forward_train(y2_handle* h, const float* x, int B, int H, int W, float* out, void* ws, size_t ws_bytes,
+                             void* stream);
+int y2_darknet_backward(y2_handle* h, const float* dnet, float* flat_grads, void* stream);
+size_t y2_param_count(const y2_handle* h);
+int y2_param_offsets(const y2_handle* h, int layer, size_t* w_off, size_t* gamma_off, size_t* beta_or_bias_off);
+int y2_get_bn_state(y2_handle* h, int layer, float* gamma, float* beta, float* moving_mean, float* moving_variance,
+                    void* stream);
+
 /* Copy layer `layer`'s post-activation output of the LAST forward (pre-pool) as float32 NHWC into
  * `dst` -- the tensors `yolo2_darknet/conv{i}/...` that the reference exposes by name for summaries
  * (train.py:31-67); used by the per-layer parity tests.  pooled != 0 returns the max-pooled tensor. */
@@ -79,6 +97,11 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
 int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
               const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int max_ctas,
               void* stream);
+
+/* Weight gradient of one conv on float32 NHWC tensors through the tcgen05 wgrad kernel the training step uses:
+ * dw[k][k][cin][cout] = sum over pixels of x[p + tap][cin] * dy[p][cout] (SAME padding).  Diagnostic / test entry. */
+int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* dy, int ksize, int cout, float* dw,
+                    int max_ctas, void* stream);
 
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.
  * out[b, y, x, (dy*stride+dx)*C + c] = in[b, stride*y+dy, stride*x+dx, c]. */

@@ -39,6 +39,13 @@ _SIGNATURES = {
     "y2_nms_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "y2_nms": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "y2_check_async_errors": (c_i, []),
+    "y2_conv2d_wgrad": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p]),
+    "y2_train_workspace_bytes": (c_sz, [c_p, c_i, c_i, c_i]),
+    "y2_darknet_forward_train": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),
+    "y2_darknet_backward": (c_i, [c_p, c_p, c_p, c_p]),
+    "y2_param_count": (c_sz, [c_p]),
+    "y2_param_offsets": (c_i, [c_p, c_i] + [ctypes.POINTER(c_sz)] * 3),
+    "y2_get_bn_state": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     "y2_set_profiling": (c_i, [c_p, c_i]),
     "y2_get_layer_ms": (c_i, [c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f)]),
     "y2_launch_count": (ctypes.c_ulonglong, []),

@@ -74,9 +74,32 @@ struct LayerState {
     int cout_pad = 0, block_n = 0;
     bf16* wpack = nullptr;     // [2][cout_pad][k*k*cin]
     float* w_f32 = nullptr;    // conv0 only (CUDA-core kernel reads HWIO fp32)
-    float* scale = nullptr;    // [cout]
-    float* bias = nullptr;     // [cout]
+    float* scale = nullptr;    // [cout]  inference fold: gamma * rsqrt(moving_var + eps)
+    float* bias = nullptr;     // [cout]  inference fold: beta - moving_mean * scale   (final layer: biases)
+    // raw variables (training + re-folding): gamma, beta, moving_mean, moving_variance
+    float *gamma = nullptr, *beta = nullptr, *mmean = nullptr, *mvar = nullptr;
+    bf16* wpack_dgrad = nullptr;   // [2][cin_pad][k*k*cout_pad]: 180-degree rotated, channels swapped (lazy)
+    int dg_cin_pad = 0, dg_cout_pad = 0, dg_block_n = 0;
+    bool dgrad_fresh = false;
     bool loaded = false;
+};
+
+// training-step state inside the caller's workspace (valid between forward_train and backward)
+struct TrainPlan {
+    bool valid = false;
+    int B = 0, H = 0, W = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    std::vector<int> oh, ow;
+    std::vector<float*> z;          // raw conv outputs
+    std::vector<bf16*> y, pooled;   // activations (planes); y[19] lives in the concat buffer
+    std::vector<float*> stat;       // per layer: mean, inv, scale, bias, m1, m2 (6 * cout floats)
+    bf16* concat = nullptr;
+    float *g0 = nullptr, *g1 = nullptr, *gcat = nullptr;
+    bf16* dx = nullptr;
+    double* red = nullptr;
+    void* streamk = nullptr;
+    const float* x = nullptr;
 };
 
 struct Plan {
@@ -100,6 +123,7 @@ struct y2_handle {
     int device = 0, classes = 0, anchors = 0, num_sms = 148;
     std::vector<LayerState> layers;
     Plan plan;
+    TrainPlan tplan;
     bool profiling = false;
     std::vector<cudaEvent_t> ev;     // 2 per layer (start, stop) + 2 for the pool/reorg passes of that layer
 };
@@ -139,13 +163,12 @@ int y2_create(y2_handle** out, int device, int classes, int num_anchors) {
         s.d = descs[i];
         choose_tiles(s.d.cout, &s.block_n, &s.cout_pad);
         const size_t K = (size_t)s.d.ksize * s.d.ksize * s.d.cin;
-        if (i == 0) {
-            if (cudaMalloc(&s.w_f32, K * s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
-        } else {
-            if (cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
-        }
+        if (cudaMalloc(&s.w_f32, K * s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        if (i > 0 && cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
         if (cudaMalloc(&s.scale, s.d.cout * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&s.bias, s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+            cudaMalloc(&s.bias, s.d.cout * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        s.beta = s.gamma + s.d.cout; s.mmean = s.beta + s.d.cout; s.mvar = s.mmean + s.d.cout;
         h->layers.push_back(s);
     }
     *out = h;
@@ -158,7 +181,7 @@ void y2_destroy(y2_handle* h) {
     cudaDeviceSynchronize();
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& s : h->layers) {
-        cudaFree(s.wpack); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias);
+        cudaFree(s.wpack); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias); cudaFree(s.gamma); cudaFree(s.wpack_dgrad);
     }
     delete h;
 }
@@ -183,14 +206,21 @@ int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* g
     Y2_CUDA(cudaSetDevice(h->device));
     LayerState& L = h->layers[layer];
     const size_t K = (size_t)L.d.ksize * L.d.ksize * L.d.cin;
-    if (layer == 0) {
+    if (w_hwio != L.w_f32)
         Y2_CUDA(cudaMemcpyAsync(L.w_f32, w_hwio, K * L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    } else {
-        if (pack_weights_launch(w_hwio, L.wpack, L.d.ksize, L.d.cin, L.d.cout, L.cout_pad, s)) return -1;
-    }
+    if (layer > 0 && pack_weights_launch(L.w_f32, L.wpack, L.d.ksize, L.d.cin, L.d.cout, L.cout_pad, s)) return -1;
+    L.dgrad_fresh = false;
     if (L.d.has_bn) {
         Y2_REQUIRE(moving_mean && moving_variance, "y2_load_weights: layer %d needs BN statistics", layer);
-        if (bn_fold_launch(gamma, beta, moving_mean, moving_variance, 1e-5f, L.scale, L.bias, L.d.cout, s)) return -1;
+        const size_t cb = L.d.cout * sizeof(float);
+        if (gamma) Y2_CUDA(cudaMemcpyAsync(L.gamma, gamma, cb, cudaMemcpyDeviceToDevice, s));
+        else Y2_CUDA(cudaMemsetAsync(L.gamma, 0, cb, s));      // never used: gamma == NULL means "1" below
+        if (beta) Y2_CUDA(cudaMemcpyAsync(L.beta, beta, cb, cudaMemcpyDeviceToDevice, s));
+        else Y2_CUDA(cudaMemsetAsync(L.beta, 0, cb, s));
+        Y2_CUDA(cudaMemcpyAsync(L.mmean, moving_mean, cb, cudaMemcpyDeviceToDevice, s));
+        Y2_CUDA(cudaMemcpyAsync(L.mvar, moving_variance, cb, cudaMemcpyDeviceToDevice, s));
+        Y2_REQUIRE(gamma, "y2_load_weights: layer %d needs gamma (scale=True in the reference, inference.py:63)", layer);
+        if (bn_fold_launch(L.gamma, L.beta, L.mmean, L.mvar, 1e-5f, L.scale, L.bias, L.d.cout, s)) return -1;
     } else {
         Y2_REQUIRE(bias, "y2_load_weights: final layer needs biases");
         Y2_CUDA(cudaMemcpyAsync(L.bias, bias, L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -428,6 +458,34 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
     return rc;
 }
 
+// Diagnostic twin of y2_conv2d for the weight-gradient GEMM: dw[k][k][cin][cout] from fp32 NHWC x and dy.
+int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* dy, int ksize, int cout, float* dw,
+                    int max_ctas, void* stream) {
+    Y2_REQUIRE(x && dy && dw, "y2_conv2d_wgrad: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    Y2_CUDA(cudaGetDevice(&dev));
+    const int num_sms = device_sm_count(dev);
+    const size_t M = (size_t)B * H * W;
+    const int dpitch = (int)align_up((size_t)cout, 64);
+    bf16 *xp = nullptr, *dp = nullptr;
+    void* sk = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&dp, 2 * M * dpitch * sizeof(bf16)) != cudaSuccess ||
+            cudaMalloc(&sk, tc_conv_streamk_bytes(num_sms)) != cudaSuccess) { set_error("y2_conv2d_wgrad: cudaMalloc failed"); break; }
+        if (cudaMemsetAsync(sk, 0, 4096, s) != cudaSuccess) { set_error("y2_conv2d_wgrad: memset failed"); break; }
+        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
+        if (split_planes_pad_launch(dy, cout, dp, dp + M * dpitch, M, cout, dpitch, s)) break;
+        if (wgrad_tc_run(xp, B, H, W, cin, ksize, dp, cout, dpitch, dw, max_ctas, num_sms, sk, s)) break;
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d_wgrad: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (wgrad_check_watchdog()) break;
+        rc = 0;
+    } while (0);
+    cudaFree(xp); cudaFree(dp); cudaFree(sk);
+    return rc;
+}
+
 int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream) {
     Y2_REQUIRE(in && out, "y2_reorg: null argument");
     Y2_REQUIRE(stride >= 1 && H % stride == 0 && W % stride == 0, "y2_reorg: H, W must be divisible by stride");
@@ -458,6 +516,12 @@ int y2_nms(float* conf, const float* xy_min, const float* xy_max, int B, int N, 
 }
 
 /* Returns 0 if no tcgen05 pipeline watchdog fired since the last call (device must be idle). */
-int y2_check_async_errors(void) { return tc_conv_check_watchdog(); }
+int y2_check_async_errors(void) {
+    const int a = tc_conv_check_watchdog();
+    const int b = wgrad_check_watchdog();
+    return a ? a : b;
+}
 
 }  // extern "C"
+
+#include "y2_train_api.inc"

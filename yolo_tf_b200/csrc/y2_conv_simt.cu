@@ -112,6 +112,128 @@ conv0_pool_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training mode: conv0 WITHOUT BN/pool (batch statistics need the raw output first): z[B,H,W,32] fp32.
+__global__ void __launch_bounds__(128)
+conv0_raw_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio, float* __restrict__ z, int B, int H, int W) {
+    __shared__ __align__(16) float sw[27 * 32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w_hwio[i];
+    __syncthreads();
+    const size_t total = (size_t)B * H * W;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int xx0 = (int)(idx % W);
+        size_t t = idx / W;
+        const int yy0 = (int)(t % H);
+        const int b = (int)(t / H);
+        float patch[27];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int yy = yy0 - 1 + r, xx = xx0 - 1 + c;
+                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+                const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) patch[(r * 3 + c) * 3 + ch] = ok ? __ldg(src + ch) : 0.f;
+            }
+        float2 acc[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) acc[n] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const float2 vv = make_float2(patch[k], patch[k]);
+            const float4* wr = reinterpret_cast<const float4*>(&sw[k * 32]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 q = wr[j];
+                acc[2 * j] = __ffma2_rn(vv, make_float2(q.x, q.y), acc[2 * j]);
+                acc[2 * j + 1] = __ffma2_rn(vv, make_float2(q.z, q.w), acc[2 * j + 1]);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(z + idx * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+    }
+}
+int conv0_raw_launch(const float* x, const float* w_hwio, float* z, int B, int H, int W, cudaStream_t s) {
+    const size_t total = (size_t)B * H * W;
+    size_t blocks = (total + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv0_raw_kernel<<<(int)blocks, 128, 0, s>>>(x, w_hwio, z, B, H, W);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// conv0 weight gradient: dW[27][32] = sum_p patch(p)[27] * dx(p)[32].  Warp w of a block owns output channels
+// [4w, 4w+4); lane = pixel lane; each thread keeps 27x4 partial sums; shuffle-reduce per warp, per-block
+// partials in fp64, fixed-order finish (deterministic).
+static constexpr int C0W_BLOCKS = 148 * 4;
+__global__ void __launch_bounds__(256)
+conv0_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dx_hi, const bf16* __restrict__ dx_lo,
+                   double* __restrict__ partial, int B, int H, int W) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t total = (size_t)B * H * W;
+    float acc[27][4];
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+    for (size_t idx = (size_t)blockIdx.x * 32 + lane; idx < total; idx += (size_t)gridDim.x * 32) {
+        const int xx0 = (int)(idx % W);
+        size_t t = idx / W;
+        const int yy0 = (int)(t % H);
+        const int b = (int)(t / H);
+        const uint2 h = __ldg(reinterpret_cast<const uint2*>(dx_hi + idx * 32 + warp * 4));
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(dx_lo + idx * 32 + warp * 4));
+        float d[4];
+        d[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+        d[1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+        d[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+        d[3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int yy = yy0 - 1 + r, xx = xx0 - 1 + c;
+                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+                const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float v = ok ? __ldg(src + ch) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[(r * 3 + c) * 3 + ch][j] = fmaf(v, d[j], acc[(r * 3 + c) * 3 + ch][j]);
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = acc[k][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) partial[((size_t)blockIdx.x * 27 + k) * 32 + warp * 4 + j] = (double)v;
+        }
+}
+__global__ void conv0_wgrad_finish_kernel(const double* partial, int nblocks, float* dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 27 * 32) return;
+    double s = 0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 27 * 32 + i];
+    dw[i] = (float)s;
+}
+int conv0_wgrad_launch(const float* x, const bf16* dx_hi, const bf16* dx_lo, float* dw, double* partial, int B, int H, int W,
+                       cudaStream_t s) {
+    conv0_wgrad_kernel<<<C0W_BLOCKS, 256, 0, s>>>(x, dx_hi, dx_lo, partial, B, H, W);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    conv0_wgrad_finish_kernel<<<(27 * 32 + 127) / 128, 128, 0, s>>>(partial, C0W_BLOCKS, dw);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
 int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,
                       bf16* out_lo, int B, int H, int W, cudaStream_t s) {
     Y2_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv0: H and W must be even");

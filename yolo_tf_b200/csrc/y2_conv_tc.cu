@@ -105,9 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     const int KB = p.kblocks_total;
-    const long long sk_total = (long long)p.m_tiles * p.n_tiles * KB;
-    const long long sk_begin = sk_total * blockIdx.x / gridDim.x;
-    const long long sk_end = sk_total * (blockIdx.x + 1) / gridDim.x;
+    const long long sk_total = (long long)(p.m_tiles * p.n_tiles - p.dp_tiles) * KB;   // stream-K part
     const int cblocks = p.Cin / BK;
     const int pad = p.ksize / 2;
     const int hw = p.H * p.W;
@@ -117,11 +115,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long cur = sk_begin; cur < sk_end;) {
-                const int tile = (int)(cur / KB);
-                const int kb0 = (int)(cur - (long long)tile * KB);
-                const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
-                cur += kb1 - kb0;
+            SegIter it;
+            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+            int tile, kb0, kb1;
+            while (it.next(tile, kb0, kb1)) {
                 const int nt = tile / p.m_tiles;
                 const int mt = tile - nt * p.m_tiles;
                 const int m0 = mt * BLOCK_M;
@@ -162,11 +159,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long cur = sk_begin; cur < sk_end;) {
-                const int tile = (int)(cur / KB);
-                const int kb0 = (int)(cur - (long long)tile * KB);
-                const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
-                cur += kb1 - kb0;
+            SegIter it;
+            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+            int tile, kb0, kb1;
+            while (it.next(tile, kb0, kb1)) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -208,24 +204,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
-        for (long long cur = sk_begin; cur < sk_end;) {
-            const int tile = (int)(cur / KB);
-            const int kb0 = (int)(cur - (long long)tile * KB);
-            const int kb1 = kb0 + (int)min((long long)(KB - kb0), sk_end - cur);
-            cur += kb1 - kb0;
+        SegIter it;
+        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        int tile, kb0, kb1;
+        while (it.next(tile, kb0, kb1)) {
             const int nt = tile / p.m_tiles;
             const int mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
             const long long row = (long long)mt * BLOCK_M + q * 32 + lane;
             const bool row_ok = row < p.M;
             const bool is_head = (kb0 == 0);                 // owns the tile's output
-            // CTAs blockIdx.x+1 .. last_contrib start inside this tile and hold its other k-ranges
+            // stream-K CTAs blockIdx.x+1 .. last_contrib start inside this tile and hold its other k-ranges
             int last_contrib = blockIdx.x;
             if (is_head && kb1 < KB) {
-                const long long tile_end = (long long)(tile + 1) * KB;
-                while (last_contrib + 1 < (int)gridDim.x &&
-                       sk_total * (last_contrib + 1) / gridDim.x < tile_end)
-                    ++last_contrib;
+                const long long tile_end = (long long)(tile - p.dp_tiles + 1) * KB;
+                while (last_contrib + 1 < p.sk_ctas && sk_total * (last_contrib + 1) / p.sk_ctas < tile_end) ++last_contrib;
             }
 
             // stage this tile's scale/bias (previous tile's readers are past the first barrier)
@@ -295,11 +288,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                         dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
-                } else {  // EPI_F32, arbitrary N / pitch: masked scalar stores
+                } else {  // EPI_F32: 128-bit stores when aligned, else masked scalar stores (N = 425, 125)
                     float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c;
+                    if ((p.ldc & 3) == 0 && n0 + c + 32 <= p.N) {
+                        float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c + j < p.N) dst[j] = f[j];
+                        for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c + j < p.N) dst[j] = f[j];
+                    }
                 }
             }
             tc_fence_before();
@@ -421,14 +420,8 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
-    // stream-K grid: every CTA gets the same number of k-blocks; never fewer than 4 per CTA
-    const long long total_kb = (long long)p.m_tiles * p.n_tiles * p.kblocks_total;
-    long long grid = num_sms;
-    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-    if (grid > total_kb / 4) grid = total_kb / 4;
-    if (grid < 1) grid = 1;
-    Y2_REQUIRE(grid <= 1024, "tc conv: grid too large for the flag page");
-    L->grid = (int)grid;
+    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, &p.dp_tiles, &p.sk_ctas, &L->grid);
+    Y2_REQUIRE(L->grid <= 1024, "tc conv: grid too large for the flag page");
 
     // activation map: (C, W, H, N=2B) bf16, im2col mode, BLOCK_M pixels x BK channels per load
     {

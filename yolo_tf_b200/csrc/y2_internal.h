@@ -46,6 +46,7 @@ enum EpilogueMode : int {
 struct ConvParams {
     int M, N, Cin, ksize, B, H, W;
     int block_n, m_tiles, n_tiles, kblocks_total;
+    int dp_tiles, sk_ctas;   // schedule (choose_schedule)
     int cout_pad;            // rows per weight plane in the packed weight matrix
     int num_stages;
     int mode;                // EpilogueMode
@@ -60,6 +61,35 @@ struct ConvParams {
     unsigned int epoch;      // set per launch
     long long ldc;           // output row pitch, elements
 };
+
+// Hybrid schedule for `tiles` output tiles of `KB` k-blocks on `ctas` persistent CTAs (max_ctas > 0 caps it):
+// full waves of whole tiles run data-parallel; the last partial wave of r tiles is either one more
+// data-parallel wave (cost KB) or a stream-K split over all CTAs (cost r*KB/ctas + hand-off overhead),
+// whichever is cheaper.  max_ctas < 0 forces stream-K for everything (tests).
+static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, int* dp_tiles, int* sk_ctas,
+                                   int* grid) {
+    const double HANDOFF_KB = 10.0;          // partial write + flag + read, in k-block times
+    long long G = num_sms;
+    const bool force_sk = max_ctas < 0;
+    if (max_ctas < 0) max_ctas = -max_ctas;
+    if (max_ctas > 0 && max_ctas < G) G = max_ctas;
+    long long full = (tiles / G) * G, r = tiles - full;
+    if (force_sk) { full = 0; r = tiles; }
+    long long sk = 0;
+    if (r > 0) {
+        sk = G;
+        if (sk > r * KB / 4) sk = r * KB / 4;          // never fewer than 4 k-blocks per CTA
+        if (sk < 1) sk = 1;
+        const double sk_cost = (double)r * KB / (double)sk + HANDOFF_KB;
+        if (!force_sk && (sk_cost >= (double)KB || sk <= r)) { full = tiles; r = 0; sk = 0; }   // plain extra wave
+    }
+    *dp_tiles = (int)full;
+    *sk_ctas = (int)sk;
+    long long g = full < G ? full : G;
+    if (sk > g) g = sk;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+}
 
 struct TcConvLaunch {
     CUtensorMap map_a;       // im2col map over the input planes (C, W, H, 2B)
@@ -92,6 +122,35 @@ int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf
 // reorg (space-to-depth 2) on 16-byte vectors; elem_bytes in {2,4}; out row pitch in elements.
 int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes,
                  long long out_ld, cudaStream_t s);
+
+// ---- training-step kernels (y2_train.cu, y2_wgrad_tc.cu) ----
+size_t bn_partial_bytes();
+int bn_stats_launch(const float* z, size_t rows, int C, const float* gamma, const float* beta, float eps, float decay,
+                    float* mean, float* inv, float* scale, float* bias, float* moving_mean, float* moving_var,
+                    double* partial, cudaStream_t s);
+int bn_apply_launch(const float* z, const float* scale, const float* bias, bf16* y_hi, bf16* y_lo, size_t rows, int C,
+                    long long ldy, cudaStream_t s);
+int bn_bwd_reduce_launch(const float* z, const float* g, long long ldg, size_t rows, int C, const float* scale,
+                         const float* bias, const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1,
+                         float* m2, double* partial, cudaStream_t s);
+int bn_bwd_apply_launch(const float* z, const float* g, long long ldg, const float* scale, const float* bias,
+                        const float* mean, const float* inv, const float* m1, const float* m2, bf16* dx_hi, bf16* dx_lo,
+                        size_t rows, int C, cudaStream_t s);
+int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* dbias, double* partial, cudaStream_t s);
+int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, size_t rows, int C, int Cpad, cudaStream_t s);
+int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
+                       int C, cudaStream_t s);
+int reorg_bwd_add_launch(const float* gr, long long ldr, float* g, int B, int H, int W, int C, cudaStream_t s);
+int pack_dgrad_weights_launch(const float* w_hwio, bf16* out, int ksize, int cin, int cout, int cin_pad, int cout_pad,
+                              cudaStream_t s);
+// dW[k*k][Cin][Cout] = sum_p x_in[p+tap][cin] * dx[p][cout] on tcgen05 (MN-major operands, split planes)
+int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, const bf16* dx_planes, int Cout,
+                 int dpitch, float* dw, int max_ctas, int num_sms, void* sk_ws, cudaStream_t stream);
+int wgrad_check_watchdog();
+// conv0 (Cin = 3) on the CUDA cores: raw forward (training) and weight gradient
+int conv0_raw_launch(const float* x, const float* w_hwio, float* z, int B, int H, int W, cudaStream_t s);
+int conv0_wgrad_launch(const float* x, const bf16* dx_hi, const bf16* dx_lo, float* dw, double* partial, int B, int H, int W,
+                       cudaStream_t s);
 
 // ---- SIMT convs (y2_conv_simt.cu) ----
 // conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.

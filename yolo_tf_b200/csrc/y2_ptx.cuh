@@ -50,7 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __noinline__ void watchdog_fire(uint32_t tag, uint32_t parity) {
+static __device__ __noinline__ void watchdog_fire(uint32_t tag, uint32_t parity) {
     if (atomicCAS(&g_watchdog.fired, 0u, 1u) == 0u) {
         g_watchdog.block = blockIdx.x;
         g_watchdog.warp = threadIdx.x >> 5;
@@ -145,6 +145,40 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- tile schedule (hybrid data-parallel + stream-K)
+// Tiles [0, dp_tiles) are processed whole, round-robin over the grid (all CTAs walk K in lockstep, which keeps the
+// operand slices they share hot in L2).  The remaining tiles form a stream-K space of (tiles - dp_tiles) * KB
+// k-blocks cut into sk_ctas equal contiguous ranges; a range that starts inside a tile yields a partial.
+struct SegIter {
+    int dp_next, dp_tiles, stride, KB;
+    long long cur, end;
+    __device__ __forceinline__ void init(int dp_tiles_, int sk_ctas, long long sk_total, int KB_) {
+        dp_next = blockIdx.x; dp_tiles = dp_tiles_; stride = gridDim.x; KB = KB_;
+        if ((int)blockIdx.x < sk_ctas) {
+            cur = sk_total * blockIdx.x / sk_ctas;
+            end = sk_total * (blockIdx.x + 1) / sk_ctas;
+        } else {
+            cur = end = 0;
+        }
+    }
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+        if (dp_next < dp_tiles) {
+            tile = dp_next; kb0 = 0; kb1 = KB; dp_next += stride;
+            return true;
+        }
+        if (cur < end) {
+            const int rt = (int)(cur / KB);
+            tile = dp_tiles + rt;
+            kb0 = (int)(cur - (long long)rt * KB);
+            const long long left = end - cur;
+            kb1 = kb0 + (int)((long long)(KB - kb0) < left ? (long long)(KB - kb0) : left);
+            cur += kb1 - kb0;
+            return true;
+        }
+        return false;
+    }
+};
 
 // Shared-memory matrix descriptor, K-major operand, rows of `row_bytes` (128 -> SWIZZLE_128B,
 // 64 -> SWIZZLE_64B); 8-row groups are `8*row_bytes` apart (SBO). Bit layout as in the PTX ISA

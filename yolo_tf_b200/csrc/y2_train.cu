@@ -1,0 +1,434 @@
+// Training-mode kernels around the tcgen05 GEMMs (HBM-bound passes):
+//   batch-norm with BATCH statistics, forward and backward  <- slim.batch_norm(is_training=True,
+//     decay=0.999, epsilon=1e-5), model/yolo2/inference.py:62-66, and its tf.gradients
+//   leaky-ReLU backward (slope 1 for x >= 0, 0.1 below)       <- model/yolo/function.py:21-24
+//   2x2 max-pool backward (first maximum wins)                <- slim.layers.max_pool2d, inference.py:69
+//   reorg backward (depth-to-space)                           <- model/yolo2/function.py:22-29
+//   bias gradient, fp32 -> split-plane conversion with padded pitch, dgrad weight packing
+// Reductions over pixels are two-stage and deterministic: per-block fp64 partials, fixed-order finish.
+#include "y2_internal.h"
+
+namespace y2 {
+
+static constexpr int RED_THREADS = 256;
+
+static inline int red_blocks(size_t rows, int cols) {
+    // each block strides over rows; enough blocks to fill the GPU, few enough to keep the finish cheap
+    size_t work = rows * (size_t)((cols + 3) / 4);
+    size_t b = (work + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
+    if (b > 148 * 4) b = 148 * 4;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+size_t bn_partial_bytes() { return (size_t)148 * 4 * 2 * 3072 * sizeof(double); }   // [blocks][2][C<=3072]
+
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+__device__ __forceinline__ void split4(const float f[4], uint2* hi, uint2* lo) {
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+    *hi = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    *lo = make_uint2(pack2(f[0] - h[0], f[1] - h[1]), pack2(f[2] - h[2], f[3] - h[3]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic two-quantity column reduction over a [rows][C] fp32 matrix (4 channels per thread):
+//   MODE 0 (bn stats):   q1 = z,  q2 = z*z
+//   MODE 1 (bn bwd):     q1 = dz, q2 = dz * zhat   with dz = g * leaky'(z*scale+bias), zhat = (z-mean)*inv
+//   MODE 2 (bias grad):  q1 = g,  q2 unused
+struct RedArgs {
+    const float* z;        // [rows][C] (pitch C)
+    const float* g;        // [rows][*] pitch ldg (MODE 1, 2)
+    long long ldg;
+    const float *scale, *bias, *mean, *inv;
+    size_t rows;
+    int C;
+    double* partial;       // [gridDim.x][2][C]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(RedArgs a) {
+    const int c4 = (a.C + 3) / 4;                 // channel groups of 4
+    // thread -> (row lane, channel group): consecutive threads take consecutive channel groups (coalesced)
+    const int groups_per_pass = RED_THREADS < c4 ? RED_THREADS : c4;
+    const int rows_per_pass = RED_THREADS / groups_per_pass;
+    for (int cg0 = 0; cg0 < c4; cg0 += groups_per_pass) {
+        const int cg = cg0 + (int)(threadIdx.x % groups_per_pass);
+        const int rlane = threadIdx.x / groups_per_pass;
+        const bool active = cg < c4 && rlane < rows_per_pass;
+        const int c = cg * 4;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+        float sc[4] = {1, 1, 1, 1}, bi[4] = {0, 0, 0, 0}, mu[4] = {0, 0, 0, 0}, iv[4] = {1, 1, 1, 1};
+        if (active && MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < a.C) { sc[j] = a.scale[c + j]; bi[j] = a.bias[c + j]; mu[j] = a.mean[c + j]; iv[j] = a.inv[c + j]; }
+        }
+        int flush = 0;
+        if (active) {
+            for (size_t r = (size_t)blockIdx.x * rows_per_pass + rlane; r < a.rows; r += (size_t)gridDim.x * rows_per_pass) {
+                float zv[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};
+                if (MODE != 2) {
+                    if (c + 3 < a.C) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.C + c));
+                        zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
+                    } else {
+                        for (int j = 0; j < 4; ++j) if (c + j < a.C) zv[j] = __ldg(a.z + r * a.C + c + j);
+                    }
+                }
+                if (MODE != 0) {
+                    if (c + 3 < a.C && (a.ldg & 3) == 0) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(a.g + r * a.ldg + c));
+                        gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w;
+                    } else {
+                        for (int j = 0; j < 4; ++j) if (c + j < a.C) gv[j] = __ldg(a.g + r * a.ldg + c + j);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (MODE == 0) { s1[j] += zv[j]; s2[j] += zv[j] * zv[j]; }
+                    if (MODE == 1) {
+                        const float zb = zv[j] * sc[j] + bi[j];
+                        const float dz = gv[j] * (zb >= 0.f ? 1.0f : 0.1f);
+                        s1[j] += dz; s2[j] += dz * ((zv[j] - mu[j]) * iv[j]);
+                    }
+                    if (MODE == 2) s1[j] += gv[j];
+                }
+                if (++flush == 64) {                  // bound fp32 accumulation length, then widen
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+                    flush = 0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
+        }
+        // combine the row lanes of this block that share a channel group
+        __shared__ double sm1[RED_THREADS][4], sm2[RED_THREADS][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sm1[threadIdx.x][j] = active ? d1[j] : 0.0; sm2[threadIdx.x][j] = active ? d2[j] : 0.0; }
+        __syncthreads();
+        if (threadIdx.x < groups_per_pass && cg0 + (int)threadIdx.x < c4) {
+            double t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+            for (int rl = 0; rl < rows_per_pass; ++rl)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { t1[j] += sm1[rl * groups_per_pass + threadIdx.x][j]; t2[j] += sm2[rl * groups_per_pass + threadIdx.x][j]; }
+            const int cc = (cg0 + threadIdx.x) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (cc + j < a.C) {
+                    a.partial[((size_t)blockIdx.x * 2 + 0) * a.C + cc + j] = t1[j];
+                    a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + cc + j] = t2[j];
+                }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- finish kernels (one thread per channel, fixed summation order) ----
+// forward: mean/var -> inv, scale, bias; moving averages updated as slim does
+// (assign_moving_average: v -= (v - value) * (1 - decay))
+__global__ void bn_stats_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, const float* gamma,
+                                       const float* beta, float eps, float decay, float* mean, float* inv, float* scale,
+                                       float* bias, float* moving_mean, float* moving_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int b = 0; b < nblocks; ++b) { s1 += partial[((size_t)b * 2) * C + c]; s2 += partial[((size_t)b * 2 + 1) * C + c]; }
+    const double m = s1 * inv_rows;
+    double v = s2 * inv_rows - m * m;
+    if (v < 0) v = 0;
+    const float mf = (float)m, vf = (float)v;
+    const float iv = rsqrtf(vf + eps);
+    const float sc = iv * gamma[c];
+    mean[c] = mf; inv[c] = iv; scale[c] = sc; bias[c] = beta[c] - mf * sc;
+    moving_mean[c] -= (moving_mean[c] - mf) * (1.0f - decay);
+    moving_var[c] -= (moving_var[c] - vf) * (1.0f - decay);
+}
+// backward: dbeta = s1, dgamma = s2 (written into the gradient bucket), and the per-channel means
+__global__ void bn_bwd_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, float* dgamma,
+                                     float* dbeta, float* m1, float* m2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int b = 0; b < nblocks; ++b) { s1 += partial[((size_t)b * 2) * C + c]; s2 += partial[((size_t)b * 2 + 1) * C + c]; }
+    dbeta[c] = (float)s1; dgamma[c] = (float)s2;
+    m1[c] = (float)(s1 * inv_rows); m2[c] = (float)(s2 * inv_rows);
+}
+__global__ void bias_grad_finish_kernel(const double* partial, int nblocks, int C, float* dbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0;
+    for (int b = 0; b < nblocks; ++b) s1 += partial[((size_t)b * 2) * C + c];
+    dbias[c] = (float)s1;
+}
+
+int bn_stats_launch(const float* z, size_t rows, int C, const float* gamma, const float* beta, float eps, float decay,
+                    float* mean, float* inv, float* scale, float* bias, float* moving_mean, float* moving_var,
+                    double* partial, cudaStream_t s) {
+    Y2_REQUIRE(C <= 3072, "bn_stats: too many channels");
+    RedArgs a = {};
+    a.z = z; a.rows = rows; a.C = C; a.partial = partial;
+    const int nb = red_blocks(rows, C);
+    col_reduce_kernel<0><<<nb, RED_THREADS, 0, s>>>(a);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, 1.0 / (double)rows, gamma, beta, eps, decay, mean,
+                                                          inv, scale, bias, moving_mean, moving_var);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int bn_bwd_reduce_launch(const float* z, const float* g, long long ldg, size_t rows, int C, const float* scale,
+                         const float* bias, const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1,
+                         float* m2, double* partial, cudaStream_t s) {
+    Y2_REQUIRE(C <= 3072, "bn_bwd: too many channels");
+    RedArgs a = {};
+    a.z = z; a.g = g; a.ldg = ldg; a.rows = rows; a.C = C; a.partial = partial;
+    a.scale = scale; a.bias = bias; a.mean = mean; a.inv = inv;
+    const int nb = red_blocks(rows, C);
+    col_reduce_kernel<1><<<nb, RED_THREADS, 0, s>>>(a);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, 1.0 / (double)rows, dgamma, dbeta, m1, m2);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* dbias, double* partial, cudaStream_t s) {
+    Y2_REQUIRE(C <= 3072, "bias_grad: too many channels");
+    RedArgs a = {};
+    a.g = g; a.ldg = ldg; a.rows = rows; a.C = C; a.partial = partial;
+    const int nb = red_blocks(rows, C);
+    col_reduce_kernel<2><<<nb, RED_THREADS, 0, s>>>(a);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, dbias);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bn apply (forward): y = leaky(z*scale + bias) -> planes.   4 channels per thread.
+__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
+                                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, size_t rows, int C, long long ldy) {
+    const int c4 = C / 4;
+    const size_t total = rows * (size_t)c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), bi = __ldg(reinterpret_cast<const float4*>(bias + c));
+        float f[4] = {t.x * sc.x + bi.x, t.y * sc.y + bi.y, t.z * sc.z + bi.z, t.w * sc.w + bi.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+        uint2 h, l;
+        split4(f, &h, &l);
+        *reinterpret_cast<uint2*>(y_hi + r * ldy + c) = h;
+        *reinterpret_cast<uint2*>(y_lo + r * ldy + c) = l;
+    }
+}
+static inline int ew_grid(size_t items) {
+    size_t b = (items + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+int bn_apply_launch(const float* z, const float* scale, const float* bias, bf16* y_hi, bf16* y_lo, size_t rows, int C,
+                    long long ldy, cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "bn_apply: C and pitch must be multiples of 4");
+    bn_apply_kernel<<<ew_grid(rows * (size_t)(C / 4)), 256, 0, s>>>(z, scale, bias, y_hi, y_lo, rows, C, ldy);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// bn backward apply: dx = scale * (dz - m1 - zhat * m2) -> planes (operand of dgrad / wgrad)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ g, long long ldg,
+                                    const float* __restrict__ scale, const float* __restrict__ bias,
+                                    const float* __restrict__ mean, const float* __restrict__ inv,
+                                    const float* __restrict__ m1, const float* __restrict__ m2, bf16* __restrict__ dx_hi,
+                                    bf16* __restrict__ dx_lo, size_t rows, int C) {
+    const int c4 = C / 4;
+    const size_t total = rows * (size_t)c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        const float4 zt = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+        float gv[4];
+        if ((ldg & 3) == 0) {
+            const float4 gt = __ldg(reinterpret_cast<const float4*>(g + r * ldg + c));
+            gv[0] = gt.x; gv[1] = gt.y; gv[2] = gt.z; gv[3] = gt.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[j] = __ldg(g + r * ldg + c + j);
+        }
+        const float zv[4] = {zt.x, zt.y, zt.z, zt.w};
+        float f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float sc = __ldg(scale + c + j);
+            const float zb = zv[j] * sc + __ldg(bias + c + j);
+            const float dz = gv[j] * (zb >= 0.f ? 1.0f : 0.1f);
+            const float zh = (zv[j] - __ldg(mean + c + j)) * __ldg(inv + c + j);
+            f[j] = sc * (dz - __ldg(m1 + c + j) - zh * __ldg(m2 + c + j));
+        }
+        uint2 h, l;
+        split4(f, &h, &l);
+        *reinterpret_cast<uint2*>(dx_hi + r * C + c) = h;
+        *reinterpret_cast<uint2*>(dx_lo + r * C + c) = l;
+    }
+}
+int bn_bwd_apply_launch(const float* z, const float* g, long long ldg, const float* scale, const float* bias,
+                        const float* mean, const float* inv, const float* m1, const float* m2, bf16* dx_hi, bf16* dx_lo,
+                        size_t rows, int C, cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0, "bn_bwd_apply: C must be a multiple of 4");
+    bn_bwd_apply_kernel<<<ew_grid(rows * (size_t)(C / 4)), 256, 0, s>>>(z, g, ldg, scale, bias, mean, inv, m1, m2, dx_hi, dx_lo,
+                                                                       rows, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// fp32 [rows][C] (pitch ld) -> planes [rows][Cpad] with zero padding (final layer: 425 -> 512)
+__global__ void split_planes_pad_kernel(const float* __restrict__ src, long long ld, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                        size_t rows, int C, int Cpad) {
+    const size_t total = rows * (size_t)Cpad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / Cpad;
+        const int c = (int)(i - r * Cpad);
+        const float v = c < C ? __ldg(src + r * ld + c) : 0.f;
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, size_t rows, int C, int Cpad, cudaStream_t s) {
+    split_planes_pad_kernel<<<ew_grid(rows * (size_t)Cpad), 256, 0, s>>>(src, ld, hi, lo, rows, C, Cpad);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// max-pool backward: the first maximum of each 2x2 window (row-major window order, strict >) gets the
+// gradient.  Values compared are the exact hi+lo activations.  One thread = 4 channels of one window.
+__global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp, const bf16* __restrict__ y_hi,
+                                   const bf16* __restrict__ y_lo, float* __restrict__ g, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, c4 = C / 4;
+    const size_t total = (size_t)B * Ho * Wo * c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % c4);
+        size_t t = i / c4;
+        const int xo = (int)(t % Wo);
+        t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const size_t prow = ((size_t)b * Ho + yo) * Wo + xo;
+        float gpv[4];
+        if ((ldgp & 3) == 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(gp + prow * ldgp + cv * 4));
+            gpv[0] = q.x; gpv[1] = q.y; gpv[2] = q.z; gpv[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gpv[j] = __ldg(gp + prow * ldgp + cv * 4 + j);
+        }
+        float v[4][4];
+        size_t off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            off[q] = (((size_t)b * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C + (size_t)cv * 4;
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>(y_hi + off[q]));
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(y_lo + off[q]));
+            v[q][0] = bf16lo(h.x) + bf16lo(l.x); v[q][1] = bf16hi(h.x) + bf16hi(l.x);
+            v[q][2] = bf16lo(h.y) + bf16lo(l.y); v[q][3] = bf16hi(h.y) + bf16hi(l.y);
+        }
+        float o[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int best = 0;
+#pragma unroll
+            for (int q = 1; q < 4; ++q)
+                if (v[q][j] > v[best][j]) best = q;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q][j] = (q == best) ? gpv[j] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(g + off[q]) = make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
+    }
+}
+int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
+                       int C, cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool_bwd: bad shape");
+    maxpool_bwd_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// reorg backward (accumulating): g[b, 2y+dy, 2x+dx, c] += gr[b, y, x, (dy*2+dx)*C + c], gr pitch ldr.
+__global__ void reorg_bwd_add_kernel(const float* __restrict__ gr, long long ldr, float* __restrict__ g, int B, int H, int W,
+                                     int C) {
+    const int Ho = H / 2, Wo = W / 2, c4 = C / 4;
+    const size_t total = (size_t)B * H * W * c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % c4);
+        size_t t = i / c4;
+        const int x = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        const int d = (y & 1) * 2 + (x & 1);
+        const size_t src = (((size_t)b * Ho + (y >> 1)) * Wo + (x >> 1)) * ldr + (size_t)d * C + cv * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(gr + src));
+        float4* dst = reinterpret_cast<float4*>(g + ((((size_t)b * H + y) * W + x) * C + cv * 4));
+        float4 o = *dst;
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        *dst = o;
+    }
+}
+int reorg_bwd_add_launch(const float* gr, long long ldr, float* g, int B, int H, int W, int C, cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0 && ldr % 4 == 0, "reorg_bwd: C and pitch must be multiples of 4");
+    reorg_bwd_add_kernel<<<ew_grid((size_t)B * H * W * (C / 4)), 256, 0, s>>>(gr, ldr, g, B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad weights: Wd[n = cin][tap' = 8 - tap][k = cout (padded)] from W HWIO [tap][cin][cout]  (180-degree
+// rotated taps, in/out channels swapped), split planes [2][cin_pad][taps*cout_pad].
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int taps, int cin, int cout,
+                                          int cin_pad, int cout_pad) {
+    const size_t K = (size_t)taps * cout_pad;
+    const size_t total = (size_t)cin_pad * K;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / K;                 // dgrad output channel = forward input channel
+        const size_t k = i - n * K;
+        const int tapd = (int)(k / cout_pad);   // dgrad tap
+        const int co = (int)(k - (size_t)tapd * cout_pad);
+        float v = 0.f;
+        if (n < (size_t)cin && co < cout) v = __ldg(w + ((size_t)(taps - 1 - tapd) * cin + n) * cout + co);
+        const bf16 h = __float2bfloat16_rn(v);
+        out[i] = h;
+        out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+int pack_dgrad_weights_launch(const float* w_hwio, bf16* out, int ksize, int cin, int cout, int cin_pad, int cout_pad,
+                              cudaStream_t s) {
+    const size_t total = (size_t)cin_pad * ksize * ksize * cout_pad;
+    pack_dgrad_weights_kernel<<<ew_grid(total), 256, 0, s>>>(w_hwio, out, ksize * ksize, cin, cout, cin_pad, cout_pad);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace y2

@@ -152,3 +152,15 @@ class Builder(object):
         # the reference registers hparam-weighted copies in tf.GraphKeys.LOSSES (:117-119)
         self.losses = {'weighted_' + k: self.objectives[k] * hparam[k] for k in self.objectives}
         return self.objectives
+
+    def backward(self, allreduce=True):
+        """Gradients of the total loss w.r.t. every variable -- the tf.gradients half of
+        slim.learning.create_train_op (train.py:127-129).  Returns (flat float32 bucket, {variable name: view}).
+        With torch.distributed initialised, the bucket is averaged over the data-parallel replicas with ONE
+        all-reduce (the reference has no multi-GPU support, README.md:99)."""
+        from ... import parallel
+        eng = inference._Engine.get(self.output.device, len(self.names), len(self.anchors))
+        flat, views = eng.backward(self.objectives.grad_inputs)
+        if allreduce:
+            parallel.allreduce_mean_(flat)
+        return flat, {"yolo2_darknet/" + k: v for k, v in views.items()}

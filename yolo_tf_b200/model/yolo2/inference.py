@@ -108,6 +108,56 @@ class _Engine(object):
                                         ctypes.c_void_p(self.ws.data_ptr() + off), need, precision, _lib.current_stream()))
         return out
 
+    # ---- training step (train.py:109-129) ----
+    def forward_train(self, x, scope, store):
+        """Forward with batch statistics; keeps activations for backward(); moving averages are updated in
+        the engine AND written back to the variable store (slim's UPDATE_OPS)."""
+        import ctypes
+        import torch
+        L = _lib.lib()
+        b, h, w, c = x.shape
+        need = L.y2_train_workspace_bytes(self.h, b, h, w)
+        if need == 0:
+            raise _lib.Y2Error(L.y2_last_error().decode())
+        if getattr(self, "tws", None) is None or self.tws.numel() < need + 1024:
+            self.tws = None
+            self.tws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+        off = (-self.tws.data_ptr()) % 1024
+        out = torch.empty((b, h // 32, w // 32, self.num_anchors * (5 + self.classes)), dtype=torch.float32, device=x.device)
+        _lib.check(L.y2_darknet_forward_train(self.h, _lib.ptr(x, torch.float32), b, h, w, _lib.ptr(out),
+                                              ctypes.c_void_p(self.tws.data_ptr() + off), need, _lib.current_stream()))
+        self._train_x = x                      # the backward reads the input again (conv0 weight gradient)
+        n = len(self.layers)
+        for i, (k, cin, cout, bn) in enumerate(self.layers):
+            if not bn:
+                continue
+            name = "%s/conv%d/BatchNorm/" % (scope, i)
+            mm = store.get(name + "moving_mean", (cout,), V.zeros, x.device)
+            mv = store.get(name + "moving_variance", (cout,), V.ones, x.device)
+            _lib.check(L.y2_get_bn_state(self.h, i, None, None, _lib.ptr(mm), _lib.ptr(mv), _lib.current_stream()))
+        return out
+
+    def backward(self, dnet):
+        """d(total_loss)/d(net) -> (flat float32 gradient bucket, {variable suffix -> view})."""
+        import ctypes
+        import torch
+        L = _lib.lib()
+        flat = torch.empty(L.y2_param_count(self.h), dtype=torch.float32, device=dnet.device)
+        _lib.check(L.y2_darknet_backward(self.h, _lib.ptr(dnet.contiguous(), torch.float32), _lib.ptr(flat), _lib.current_stream()))
+        views = {}
+        n = len(self.layers)
+        for i, (k, cin, cout, bn) in enumerate(self.layers):
+            w_off, g_off, b_off = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(L.y2_param_offsets(self.h, i, ctypes.byref(w_off), ctypes.byref(g_off), ctypes.byref(b_off)))
+            name = "conv%d" % i if i < n - 1 else "conv"
+            views[name + "/weights"] = flat[w_off.value:w_off.value + k * k * cin * cout].view(k, k, cin, cout)
+            if bn:
+                views[name + "/BatchNorm/gamma"] = flat[g_off.value:g_off.value + cout]
+                views[name + "/BatchNorm/beta"] = flat[b_off.value:b_off.value + cout]
+            else:
+                views[name + "/biases"] = flat[b_off.value:b_off.value + cout]
+        return flat, views
+
     def activation(self, layer, pooled, shape):
         import torch
         out = torch.empty(shape, dtype=torch.float32, device="cuda")
@@ -125,14 +175,12 @@ def darknet(net, classes, num_anchors, training=False, center=True, precision=No
     output [B, H/32, W/32, num_anchors*(5+classes)] and scope == 'yolo2_darknet' (inference.py:67).
     """
     scope = __name__.split('.')[-2] + '_' + inspect.stack()[0][3]
-    if training:
-        raise NotImplementedError(
-            "training-mode backbone (BN batch statistics + backward) is not built yet on this backend; "
-            "the head loss fwd+bwd (Objectives) is. No silent fallback is provided.")
     if not net.is_cuda:
         raise _lib.Y2Error("darknet: input must be a CUDA tensor (no CPU path exists)")
     eng = _Engine.get(net.device, classes, num_anchors)
     eng.sync_weights(scope, V.default_store(), net.device, center=center)
+    if training:
+        return scope, eng.forward_train(net.contiguous(), scope, V.default_store())
     out = eng.forward(net.contiguous(), precision=PRECISION if precision is None else precision)
     return scope, out
 
