@@ -24,6 +24,11 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err.c_str(); }
 
+int g_sched_override = 0;
+double g_sched_handoff_kb = 10.0;
+static float g_last_conv_ms = 0.f;
+static unsigned long long* g_dbg_host = nullptr;
+static int g_dbg_n = 0, g_dbg_sched[4] = {0, 0, 0, 0};
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -449,13 +454,45 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
         if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk)) break;
         T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
         T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
-        if (tc_conv_launch(T, s)) break;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        unsigned long long* dbg = nullptr;
+        if (g_dbg_host) { cudaMalloc(&dbg, (size_t)T.grid * 4 * sizeof(unsigned long long)); T.p.dbg = dbg; }
+        if (tc_conv_launch(T, s)) break;                       // warm-up / result
+        cudaEventRecord(e0, s);
+        if (tc_conv_launch(T, s)) break;                       // timed (same output)
+        cudaEventRecord(e1, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        cudaEventElapsedTime(&g_last_conv_ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (dbg) {
+            g_dbg_n = T.grid < 1024 ? T.grid : 1024;
+            cudaMemcpy(g_dbg_host, dbg, (size_t)g_dbg_n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            cudaFree(dbg);
+            g_dbg_sched[0] = T.p.dp_tiles; g_dbg_sched[1] = T.p.sk_ctas; g_dbg_sched[2] = T.grid; g_dbg_sched[3] = T.p.kblocks_total;
+        }
         if (tc_conv_check_watchdog()) break;
         rc = 0;
     } while (0);
     cudaFree(xp); cudaFree(wp); cudaFree(sk);
     return rc;
+}
+
+// Diagnostics: schedule override / timing of the last y2_conv2d kernel / per-CTA globaltimer stamps.
+int y2_debug_set(int key, double value) {
+    if (key == 0) g_sched_override = (int)value;
+    else if (key == 1) g_sched_handoff_kb = value;
+    else if (key == 2) { if (value != 0 && !g_dbg_host) g_dbg_host = new unsigned long long[1024 * 4]; if (value == 0) { delete[] g_dbg_host; g_dbg_host = nullptr; } }
+    else return -1;
+    return 0;
+}
+float y2_debug_last_conv_ms(void) { return g_last_conv_ms; }
+int y2_debug_cta_times(unsigned long long* out, int max_ctas, int* sched4) {
+    if (!g_dbg_host) return 0;
+    const int n = g_dbg_n < max_ctas ? g_dbg_n : max_ctas;
+    memcpy(out, g_dbg_host, (size_t)n * 4 * sizeof(unsigned long long));
+    if (sched4) memcpy(sched4, g_dbg_sched, sizeof(g_dbg_sched));
+    return n;
 }
 
 // Diagnostic twin of y2_conv2d for the weight-gradient GEMM: dw[k][k][cin][cout] from fp32 NHWC x and dy.

@@ -39,6 +39,11 @@ static constexpr int SMEM_LIMIT = 227 * 1024;
 static constexpr int SB_BYTES = 2 * 256 * 4;      // scale/bias staging for one tile
 static constexpr int BAR_BYTES = 256;
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // stream-K hand-off flags: one word per CTA, value = launch epoch (monotonic, never reset)
 __device__ __forceinline__ void flag_set(unsigned int* f, unsigned int epoch) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
@@ -207,7 +212,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         SegIter it;
         it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
         int tile, kb0, kb1;
+        if (p.dbg && et == 0) { p.dbg[blockIdx.x * 4 + 0] = gtime_ns(); p.dbg[blockIdx.x * 4 + 1] = 0; p.dbg[blockIdx.x * 4 + 2] = 0; }
         while (it.next(tile, kb0, kb1)) {
+            if (p.dbg && et == 0 && tile >= p.dp_tiles && p.dbg[blockIdx.x * 4 + 1] == 0) p.dbg[blockIdx.x * 4 + 1] = gtime_ns();
             const int nt = tile / p.m_tiles;
             const int mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
@@ -235,6 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
             tc_fence_after();
             // the other contributors ran at the START of their ranges: normally long done
+            if (p.dbg && et == 0 && last_contrib > (int)blockIdx.x) p.dbg[blockIdx.x * 4 + 2] = gtime_ns();   // own MMAs done, start waiting
             for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {
                 if (lane == 0) flag_wait(p.sk_flags + h, p.epoch, 0x500u);
                 __syncwarp();
@@ -312,6 +320,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if (p.dbg && et == 0) p.dbg[blockIdx.x * 4 + 3] = gtime_ns();
     }
 
     tc_fence_before();

@@ -59,6 +59,7 @@ struct ConvParams {
     float* sk_partial;       // stream-K: [grid][128][block_n] raw fp32 partial tiles
     unsigned int* sk_flags;  // stream-K: [grid] hand-off flags (value = launch epoch)
     unsigned int epoch;      // set per launch
+    unsigned long long* dbg; // optional [grid][4] globaltimer stamps: start, stream-K phase start, hand-off wait start, end
     long long ldc;           // output row pitch, elements
 };
 
@@ -66,9 +67,12 @@ struct ConvParams {
 // full waves of whole tiles run data-parallel; the last partial wave of r tiles is either one more
 // data-parallel wave (cost KB) or a stream-K split over all CTAs (cost r*KB/ctas + hand-off overhead),
 // whichever is cheaper.  max_ctas < 0 forces stream-K for everything (tests).
+extern int g_sched_override;          // 0 = cost model, 1 = data-parallel only, 2 = stream-K everything (diagnostics)
+extern double g_sched_handoff_kb;
 static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, int* dp_tiles, int* sk_ctas,
                                    int* grid) {
-    const double HANDOFF_KB = 10.0;          // partial write + flag + read, in k-block times
+    const double HANDOFF_KB = g_sched_handoff_kb;   // partial write + flag + read, in k-block times
+    if (g_sched_override == 2 && max_ctas == 0) max_ctas = -num_sms;
     long long G = num_sms;
     const bool force_sk = max_ctas < 0;
     if (max_ctas < 0) max_ctas = -max_ctas;
@@ -81,7 +85,7 @@ static inline void choose_schedule(long long tiles, int KB, int num_sms, int max
         if (sk > r * KB / 4) sk = r * KB / 4;          // never fewer than 4 k-blocks per CTA
         if (sk < 1) sk = 1;
         const double sk_cost = (double)r * KB / (double)sk + HANDOFF_KB;
-        if (!force_sk && (sk_cost >= (double)KB || sk <= r)) { full = tiles; r = 0; sk = 0; }   // plain extra wave
+        if (!force_sk && (sk_cost >= (double)KB || sk <= r || g_sched_override == 1)) { full = tiles; r = 0; sk = 0; }   // plain extra wave
     }
     *dp_tiles = (int)full;
     *sk_ctas = (int)sk;

@@ -25,6 +25,7 @@ class Model(object):
     _DETECTION = ("conf", "xy_min", "xy_max")
     _LAZY = ("iou", "prob", "wh", "areas", "xy", "offset_xy", "offset_xy_min", "offset_xy_max", "coords", "wh01")
     _SHAPE = {"conf": "C", "prob": "C", "iou": None, "areas": None, "coords": 4}
+    _ANCHOR_CACHE = {}
 
     def __init__(self, net, classes, anchors, training=False):
         import torch
@@ -38,7 +39,10 @@ class Model(object):
         self.training = training
         self._b, self._a = b, a
         self._cache = {}
-        self._anchors_dev = torch.as_tensor(self.anchors.astype(np.float32)).to(net.device).contiguous()
+        key = (str(net.device), self.anchors.astype(np.float32).tobytes())
+        if key not in Model._ANCHOR_CACHE:          # one upload per (device, anchor set): no per-step host sync
+            Model._ANCHOR_CACHE[key] = torch.as_tensor(self.anchors.astype(np.float32)).to(net.device).contiguous()
+        self._anchors_dev = Model._ANCHOR_CACHE[key]
         if not training:
             self._launch(self._DETECTION)
 
