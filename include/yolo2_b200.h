@@ -85,6 +85,12 @@ int y2_param_offsets(const y2_handle* h, int layer, size_t* w_off, size_t* gamma
 int y2_get_bn_state(y2_handle* h, int layer, float* gamma, float* beta, float* moving_mean, float* moving_variance,
                     void* stream);
 
+/* Test hooks of the training step (per-layer "teacher-forced" backward parity): y2_train_probe arms the next
+ * y2_darknet_backward to copy dL/dy of `layer` (dense [M][cout]) and dL/d(input of layer) (dense [M][cin]);
+ * y2_train_get_tensor reads saved forward state: kind 0 raw conv output, 1 activation, 2 pooled, 3 concat. */
+int y2_train_probe(y2_handle* h, int layer, float* gy_out, float* gin_out);
+int y2_train_get_tensor(y2_handle* h, int kind, int layer, float* dst, void* stream);
+
 /* Copy layer `layer`'s post-activation output of the LAST forward (pre-pool) as float32 NHWC into
  * `dst` -- the tensors `yolo2_darknet/conv{i}/...` that the reference exposes by name for summaries
  * (train.py:31-67); used by the per-layer parity tests.  pooled != 0 returns the max-pooled tensor. */

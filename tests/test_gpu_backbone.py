@@ -59,9 +59,11 @@ def test_conv_layer_shapes_vs_fp64(cuda, b, hw, cin, k, cout):
     assert _rel(got, ref) <= TOL
 
 
-@pytest.mark.parametrize("max_ctas,block_n", [(0, 0), (1, 0), (3, 0), (5, 128), (37, 64), (148, 32)])
+@pytest.mark.parametrize("max_ctas,block_n", [(0, 0), (1, 0), (2, 0), (-3, 0), (-5, 128), (-37, 64), (-148, 32), (37, 64)])
 def test_conv_streamk_and_tile_variants_vs_oracle(cuda, max_ctas, block_n):
-    """Stream-K hand-off: 3 m-tiles x K=72 k-blocks cut across 1..72 CTAs (up to ~24 contributors per tile)."""
+    """Hybrid schedule and stream-K hand-off: 3 m-tiles x K=72 k-blocks; max_ctas > 0 caps the grid (data-parallel
+    waves + cost-model remainder), max_ctas < 0 forces stream-K over |max_ctas| CTAs (up to ~24 partials per tile,
+    more than the 6 the cp.async staging holds, so the direct-load overflow path runs too)."""
     rs = np.random.RandomState(4)
     x = rs.normal(0, 1, size=(2, 13, 13, 512)).astype(np.float32)
     w = (rs.normal(0, 1, size=(3, 3, 512, 256)) * 0.02).astype(np.float32)

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "y2_param_count": (c_sz, [c_p]),
     "y2_param_offsets": (c_i, [c_p, c_i] + [ctypes.POINTER(c_sz)] * 3),
     "y2_get_bn_state": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "y2_train_probe": (c_i, [c_p, c_i, c_p, c_p]),
+    "y2_train_get_tensor": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "y2_set_profiling": (c_i, [c_p, c_i]),
     "y2_get_layer_ms": (c_i, [c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f)]),
     "y2_launch_count": (ctypes.c_ulonglong, []),

@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err.c_str(); }
 
 int g_sched_override = 0;
-double g_sched_handoff_kb = 10.0;
+double g_sched_handoff_kb = 13.0;
 static float g_last_conv_ms = 0.f;
 static unsigned long long* g_dbg_host = nullptr;
 static int g_dbg_n = 0, g_dbg_sched[4] = {0, 0, 0, 0};
@@ -129,6 +129,8 @@ struct y2_handle {
     std::vector<LayerState> layers;
     Plan plan;
     TrainPlan tplan;
+    int probe_layer = -1;              // test hooks (y2_train_probe)
+    float *probe_gy = nullptr, *probe_gin = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> ev;     // 2 per layer (start, stop) + 2 for the pool/reorg passes of that layer
 };

@@ -248,6 +248,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __syncwarp();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            // Partials of the other contributors are staged through the (now idle: a head segment with contributors
+            // is always this CTA's last segment) smem ring with cp.async, one 32-column chunk ahead, so the adds never
+            // wait on an L2 round trip per contributor.  Each thread copies and later reads only its own row slot
+            // (128 B, 16-byte pieces XOR-swizzled by row against bank conflicts): no cross-thread sync needed.
+            const int ncontrib = last_contrib - (int)blockIdx.x;
+            const int max_staged = (int)(((size_t)S * stage_bytes) / (2u * BLOCK_M * 128u));
+            const int nstaged = ncontrib < max_staged ? ncontrib : max_staged;
+            const int rr = q * 32 + lane;
+            auto stage_slot = [&](int buf, int hh) -> uint32_t {
+                return smem_u32(smem) + (uint32_t)(((buf * nstaged + hh) * BLOCK_M + rr) * 128);
+            };
+            auto stage_issue = [&](int c, int buf) {
+                for (int hh = 0; hh < nstaged; ++hh) {
+                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + hh) * BLOCK_M * p.block_n + (size_t)rr * p.block_n + c;
+                    const uint32_t dst = stage_slot(buf, hh);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((j ^ (rr & 7)) << 4)), "l"(src + 4 * j) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (nstaged > 0) stage_issue(0, 0);
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
@@ -263,7 +285,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {      // fixed order: deterministic sum
+                if (nstaged > 0) {
+                    const int buf = (c >> 5) & 1;
+                    if (c + 32 < p.block_n) {
+                        stage_issue(c + 32, buf ^ 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    for (int hh = 0; hh < nstaged; ++hh) {                  // ascending CTA order: deterministic sum
+                        const uint32_t src = stage_slot(buf, hh);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 t;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                         : "r"(src + (uint32_t)((j ^ (rr & 7)) << 4)));
+                            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                        }
+                    }
+                }
+                for (int h = blockIdx.x + 1 + nstaged; h <= last_contrib; ++h) {      // overflow (tiny-K corner): direct loads
                     const float4* src = reinterpret_cast<const float4*>(
                         p.sk_partial + (size_t)h * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n + c);
 #pragma unroll
@@ -429,7 +471,8 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
-    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, &p.dp_tiles, &p.sk_ctas, &L->grid);
+    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0), &p.dp_tiles,
+                    &p.sk_ctas, &L->grid);
     Y2_REQUIRE(L->grid <= 1024, "tc conv: grid too large for the flag page");
 
     // activation map: (C, W, H, N=2B) bf16, im2col mode, BLOCK_M pixels x BK channels per load

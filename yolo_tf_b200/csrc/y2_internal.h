@@ -69,9 +69,11 @@ struct ConvParams {
 // whichever is cheaper.  max_ctas < 0 forces stream-K for everything (tests).
 extern int g_sched_override;          // 0 = cost model, 1 = data-parallel only, 2 = stream-K everything (diagnostics)
 extern double g_sched_handoff_kb;
-static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, int* dp_tiles, int* sk_ctas,
-                                   int* grid) {
-    const double HANDOFF_KB = g_sched_handoff_kb;   // partial write + flag + read, in k-block times
+static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, double kb_weight, int* dp_tiles,
+                                   int* sk_ctas, int* grid) {
+    // hand-off (partial write, flag, staged read + finish) ~ 17 us measured = 13 k-block times of a 128x256x64 step;
+    // kb_weight = this kernel's k-block cost relative to that (block_n/256 * BK/64)
+    const double HANDOFF_KB = g_sched_handoff_kb / (kb_weight > 0.05 ? kb_weight : 0.05);
     if (g_sched_override == 2 && max_ctas == 0) max_ctas = -num_sms;
     long long G = num_sms;
     const bool force_sk = max_ctas < 0;

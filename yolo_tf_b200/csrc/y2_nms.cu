@@ -157,33 +157,95 @@ __global__ void __launch_bounds__(256) nms_order_kernel(NmsArgs a) {
     }
 }
 
+// apply: a CTA owns a [64 boxes][32 classes] tile of one image.  The tile is loaded with coalesced 128-byte rows into
+// shared memory; each warp then walks class COLUMNS (lanes = boxes), so the kept list of the class is uniform across
+// the warp and its boxes are broadcast from shared memory -- the IoU loop has no global loads and no divergence.
+// Only tiles of classes that kept something are touched; modified tiles are written back coalesced.
+static constexpr int AP_BOXES = 64, AP_CLASSES = 32;
 __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
-    const size_t per_img = (size_t)a.N * a.C;
-    const size_t total = (size_t)a.B * per_img;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(e / per_img);
-        const size_t r = e - (size_t)b * per_img;
-        const int n = (int)(r / a.C);
-        const int c = (int)(r - (size_t)n * a.C);
-        const int cnt = __ldg(a.kept_cnt + (size_t)b * a.C + c);
-        if (cnt == 0) continue;
-        const float v = a.conf[e];
-        const bool is_cand = v > a.thr;
-        const uint16_t* kept = a.cand + ((size_t)b * a.C + c) * a.N;
+    __shared__ float tile[AP_BOXES][AP_CLASSES + 1];
+    __shared__ float4 kbox[8][32];
+    __shared__ int tile_cnt[AP_CLASSES];
+    __shared__ int any_kept, dirty;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c_tiles = (a.C + AP_CLASSES - 1) / AP_CLASSES;
+    const int n_tiles = (a.N + AP_BOXES - 1) / AP_BOXES;
+    const long long total_tiles = (long long)a.B * n_tiles * c_tiles;
+    for (long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int ct = (int)(tix % c_tiles);
+        const long long r0 = tix / c_tiles;
+        const int ntile = (int)(r0 % n_tiles);
+        const int b = (int)(r0 / n_tiles);
+        const int c0 = ct * AP_CLASSES, n0 = ntile * AP_BOXES;
+        if (threadIdx.x == 0) { any_kept = 0; dirty = 0; }
+        __syncthreads();
+        if (threadIdx.x < AP_CLASSES) {
+            const int c = c0 + threadIdx.x;
+            const int k = (c < a.C) ? __ldg(a.kept_cnt + (size_t)b * a.C + c) : 0;
+            tile_cnt[threadIdx.x] = k;
+            if (k) any_kept = 1;
+        }
+        __syncthreads();
+        const int ak = any_kept;
+        __syncthreads();                                             // everyone has read it before the next tile resets it
+        if (!ak) continue;                                           // block-uniform
+        float* conf_img = a.conf + (size_t)b * a.N * a.C;
+        // load: row = box, 32 consecutive classes = one 128-byte segment per warp
+        for (int r = warp; r < AP_BOXES; r += 8) {
+            const int n = n0 + r, c = c0 + lane;
+            tile[r][lane] = (n < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
+        }
+        __syncthreads();
         const float* bmin = a.xy_min + (size_t)b * a.N * 2;
         const float* bmax = a.xy_max + (size_t)b * a.N * 2;
-        bool zero;
-        if (is_cand) {
-            bool found = false;
-            for (int t = 0; t < cnt; ++t) found |= (kept[t] == n);
-            zero = !found;
-        } else {
-            const float4 bn = load_box(bmin, bmax, n);
-            bool hit = false;
-            for (int t = 0; t < cnt && !hit; ++t) hit = iou_ref(load_box(bmin, bmax, kept[t]), bn) >= a.thr_iou;
-            zero = hit;
+        float4 bn[2];
+        bool n_ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = n0 + h * 32 + lane;
+            n_ok[h] = n < a.N;
+            bn[h] = n_ok[h] ? load_box(bmin, bmax, n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (zero) a.conf[e] = 0.0f;
+        bool wrote = false;
+        for (int cl = warp; cl < AP_CLASSES; cl += 8) {
+            const int cnt = tile_cnt[cl];
+            if (cnt == 0) continue;                                  // warp-uniform
+            const uint16_t* kept = a.cand + ((size_t)b * a.C + c0 + cl) * a.N;
+            float v[2];
+            bool cand[2], found[2] = {false, false}, hit[2] = {false, false};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { v[h] = tile[h * 32 + lane][cl]; cand[h] = v[h] > a.thr; }
+            for (int k0 = 0; k0 < cnt; k0 += 32) {
+                const int kc = min(32, cnt - k0);
+                int kidx = -1;
+                if (lane < kc) { kidx = kept[k0 + lane]; kbox[warp][lane] = load_box(bmin, bmax, kidx); }
+                __syncwarp();
+                for (int t = 0; t < kc; ++t) {
+                    const float4 kb = kbox[warp][t];
+                    const int ki = __shfl_sync(0xffffffffu, kidx, t);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        found[h] |= (ki == n0 + h * 32 + lane);
+                        if (!cand[h] && !hit[h]) hit[h] = iou_ref(kb, bn[h]) >= a.thr_iou;
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool zero = n_ok[h] && (cand[h] ? !found[h] : hit[h]);
+                if (zero) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
+            }
+        }
+        if (wrote) dirty = 1;
+        __syncthreads();
+        if (dirty) {
+            for (int r = warp; r < AP_BOXES; r += 8) {
+                const int n = n0 + r, c = c0 + lane;
+                if (n < a.N && c < a.C) conf_img[(size_t)n * a.C + c] = tile[r][lane];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -223,8 +285,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
         Y2_CUDA(cudaGetLastError());
     note_launch();
     }
-    const size_t total = (size_t)B * N * C;
-    size_t blocks = (total + 255) / 256;
+    long long blocks = (long long)B * ((N + AP_BOXES - 1) / AP_BOXES) * ((C + AP_CLASSES - 1) / AP_CLASSES);
     if (blocks > 148 * 8) blocks = 148 * 8;
     nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
