@@ -471,7 +471,8 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
-    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0), &p.dp_tiles,
+    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0),
+                    (size_t)planes * cout_pad * taps * Cin * sizeof(bf16), &p.dp_tiles,
                     &p.sk_ctas, &L->grid);
     Y2_REQUIRE(L->grid <= 1024, "tc conv: grid too large for the flag page");
 

@@ -69,12 +69,19 @@ struct ConvParams {
 // whichever is cheaper.  max_ctas < 0 forces stream-K for everything (tests).
 extern int g_sched_override;          // 0 = cost model, 1 = data-parallel only, 2 = stream-K everything (diagnostics)
 extern double g_sched_handoff_kb;
-static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, double kb_weight, int* dp_tiles,
-                                   int* sk_ctas, int* grid) {
+static inline void choose_schedule(long long tiles, int KB, int num_sms, int max_ctas, double kb_weight,
+                                   size_t shared_operand_bytes, int* dp_tiles, int* sk_ctas, int* grid) {
     // hand-off (partial write, flag, staged read + finish) ~ 17 us measured = 13 k-block times of a 128x256x64 step;
     // kb_weight = this kernel's k-block cost relative to that (block_n/256 * BK/64)
     const double HANDOFF_KB = g_sched_handoff_kb / (kb_weight > 0.05 ? kb_weight : 0.05);
     if (g_sched_override == 2 && max_ctas == 0) max_ctas = -num_sms;
+    // Measured (profiles/probe_sched_r1.json): when the operand every tile shares (the packed weights) stays
+    // L2-resident, stream-K over EVERYTHING beats the hybrid (its hand-offs hide behind the other CTAs' MMAs instead
+    // of forming a serial tail): conv8 0.120 vs 0.133 ms, conv13 0.118 vs 0.143, conv18 0.209 vs 0.249.  With the
+    // 113 MB weights of conv20 it loses (0.866 vs 0.647: every CTA streams a different K phase from DRAM).
+    if (g_sched_override == 0 && max_ctas == 0 && tiles < 4LL * num_sms && shared_operand_bytes > 0 &&
+        shared_operand_bytes <= ((size_t)48 << 20) && (double)tiles * KB / num_sms >= 2.0 * HANDOFF_KB)
+        max_ctas = -num_sms;
     long long G = num_sms;
     const bool force_sk = max_ctas < 0;
     if (max_ctas < 0) max_ctas = -max_ctas;

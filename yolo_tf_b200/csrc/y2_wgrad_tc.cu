@@ -332,7 +332,7 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     Y2_REQUIRE(stages >= 2, "wgrad: tile does not fit shared memory");
     p.num_stages = stages;
     L.smem_bytes = stages * stage_bytes + 1024 + 256;
-    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, bn / 256.0, &p.dp_tiles, &p.sk_ctas, &L.grid);
+    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, bn / 256.0, 0, &p.dp_tiles, &p.sk_ctas, &L.grid);
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
