@@ -72,7 +72,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int A_TILE = BLOCK_M * ROW_BYTES;
     constexpr int PLANES = SPLIT3 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int b_tile = p.block_n * ROW_BYTES;
     const int stage_bytes = PLANES * (A_TILE + b_tile);
@@ -206,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
         const int q = warp - EPI_WARP0;
         const int et = threadIdx.x - EPI_WARP0 * 32;       // 0..127
-        int acc = 0;
+        int acc = 0, sb_nt = -1;
         uint32_t acc_phase = 0;
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
         SegIter it;
@@ -228,16 +229,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 while (last_contrib + 1 < p.sk_ctas && sk_total * (last_contrib + 1) / p.sk_ctas < tile_end) ++last_contrib;
             }
 
-            // stage this tile's scale/bias (previous tile's readers are past the first barrier)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (is_head) {
+            // stage this tile's scale/bias -- only when the N-tile changes (consecutive tiles share it: m runs fastest),
+            // which keeps two barriers and a global-load round trip out of the per-tile critical path of the
+            // small-K layers.  The first barrier makes sure the previous tile's readers are done.
+            if (is_head && nt != sb_nt) {                   // uniform over the 128 epilogue threads
+                asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = et; i < p.block_n; i += 128) {
                     const int n = n0 + i;
                     sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
                     sb[256 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                sb_nt = nt;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
 
             mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
             tc_fence_after();

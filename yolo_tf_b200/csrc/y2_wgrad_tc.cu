@@ -80,7 +80,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int a_row = p.atom_ch * 2;                       // bytes per pixel row of an A atom (128 | 64)
     const int a_atom = WG_KPIX * a_row;                    // 8 KiB | 4 KiB
     const int a_plane = p.apt * a_atom;                    // 16 KiB
