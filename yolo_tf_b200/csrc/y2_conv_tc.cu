@@ -127,11 +127,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             while (it.next(tile, kb0, kb1)) {
                 const int nt = tile / p.m_tiles;
                 const int mt = tile - nt * p.m_tiles;
-                const int m0 = mt * BLOCK_M;
-                const int img = m0 / hw;
-                const int rem = m0 - img * hw;
-                const int y0 = rem / p.W;
-                const int x0 = rem - y0 * p.W;
+                int img, y0, x0;
+                if (p.tx) {                                  // spatial tile (tx x ty pixels x tb images): fused max-pool layers
+                    const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
+                    x0 = xt * p.tx; y0 = (r2 % p.tiles_y) * p.ty; img = (r2 / p.tiles_y) * p.tb;
+                } else {                                     // linear range of 128 pixels
+                    const int m0 = mt * BLOCK_M;
+                    img = m0 / hw;
+                    const int rem = m0 - img * hw;
+                    y0 = rem / p.W;
+                    x0 = rem - y0 * p.W;
+                }
                 const int n0 = nt * p.block_n;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int tap = kb / cblocks;
@@ -141,11 +147,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1u, 0x100u + stage);
                     uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                    tma_load_im2col_4d(st, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx,
-                                       (uint16_t)dy);
-                    if (SPLIT3)
-                        tma_load_im2col_4d(st + A_TILE, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
-                                           (uint16_t)dx, (uint16_t)dy);
+                    if (p.tx) {      // tile-mode box {BK, tx, ty, tb} shifted by the tap; out-of-image = zero fill = SAME padding
+                        tma_load_4d(st, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img);
+                        if (SPLIT3) tma_load_4d(st + A_TILE, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img + p.B);
+                    } else {
+                        tma_load_im2col_4d(st, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                        if (SPLIT3)
+                            tma_load_im2col_4d(st + A_TILE, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
+                                               (uint16_t)dx, (uint16_t)dy);
+                    }
                     uint8_t* sbt = st + PLANES * A_TILE;
                     const int kcoord = tap * p.Cin + c0;
                     tma_load_2d(sbt, &map_w, &full[stage], kcoord, n0);

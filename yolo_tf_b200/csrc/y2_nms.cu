@@ -68,31 +68,36 @@ struct NmsArgs {
 
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
     __shared__ uint32_t alive_sm[NMS_WARPS][NMS_MAX_N / 32];
+    __shared__ int cnt_sm[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * NMS_WARPS + warp;
+    const int c0 = blockIdx.x * 32;                     // this CTA: 32 classes of image b
     const int b = blockIdx.y;
-    if (c >= a.C) return;
     const float* conf_img = a.conf + (size_t)b * a.N * a.C;
     const float* bmin = a.xy_min + (size_t)b * a.N * 2;
     const float* bmax = a.xy_max + (size_t)b * a.N * 2;
-    uint16_t* cand = a.cand + ((size_t)b * a.C + c) * a.N;
-    uint16_t* sorted = a.sorted + ((size_t)b * a.C + c) * a.N;
     uint32_t* alive = alive_sm[warp];
 
-    // 1. compact candidates, index order
-    int K = 0;
-    for (int n0 = 0; n0 < a.N; n0 += 32) {
-        const int n = n0 + lane;
-        const bool is_c = (n < a.N) && (__ldg(conf_img + (size_t)n * a.C + c) > a.thr);
-        const uint32_t m = __ballot_sync(0xffffffffu, is_c);
-        if (is_c) cand[K + __popc(m & ((1u << lane) - 1u))] = (uint16_t)n;
-        K += __popc(m);
+    // 1. compact candidates with COALESCED reads: a warp reads 32 consecutive classes of one box (128 bytes);
+    //    lane = class.  List order is arbitrary (slots from a shared-memory counter); step 2 sorts with a total order.
+    if (threadIdx.x < 32) cnt_sm[threadIdx.x] = 0;
+    __syncthreads();
+    if (c0 + lane < a.C) {
+        uint16_t* my_cand = a.cand + ((size_t)b * a.C + c0 + lane) * a.N;
+        for (int n = warp; n < a.N; n += NMS_WARPS) {
+            if (__ldg(conf_img + (size_t)n * a.C + c0 + lane) > a.thr) my_cand[atomicAdd(&cnt_sm[lane], 1)] = (uint16_t)n;
+        }
     }
+    __syncthreads();
+    for (int cl = warp; cl < 32; cl += NMS_WARPS) {     // one warp per class from here on
+    const int c = c0 + cl;
+    if (c >= a.C) break;
+    uint16_t* cand = a.cand + ((size_t)b * a.C + c) * a.N;
+    uint16_t* sorted = a.sorted + ((size_t)b * a.C + c) * a.N;
+    const int K = cnt_sm[cl];
     if (K == 0) {
         if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = 0;
-        return;
+        continue;
     }
-    __syncwarp();
     // reference asserts fire as soon as one live box is compared with the rest: every box is checked
     if (a.status && a.N >= 2) {
         bool bad = false;
@@ -138,6 +143,8 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
         }
     }
     if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+    __syncwarp();
+    }   // class loop
 }
 
 // Final permutation: rank sort of all N boxes under the class-(C-1) visiting order. One CTA per image.
@@ -207,6 +214,7 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
             bn[h] = n_ok[h] ? load_box(bmin, bmax, n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         bool wrote = false;
+        const bool quick = a.thr_iou > 0.0f;
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
             const int cnt = tile_cnt[cl];
             if (cnt == 0) continue;                                  // warp-uniform
@@ -226,7 +234,9 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         found[h] |= (ki == n0 + h * 32 + lane);
-                        if (!cand[h] && !hit[h]) hit[h] = iou_ref(kb, bn[h]) >= a.thr_iou;
+                        // disjoint boxes have inter == 0 -> iou == 0 (or NaN) -> never >= a positive threshold: skip the divide
+                        if (!cand[h] && !hit[h] && (!quick || (kb.x < bn[h].z && bn[h].x < kb.z && kb.y < bn[h].w && bn[h].y < kb.w)))
+                            hit[h] = iou_ref(kb, bn[h]) >= a.thr_iou;
                     }
                 }
                 __syncwarp();
@@ -276,7 +286,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     a.kept_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + 2 * a16);
     a.status = status_out;
     a.order_out = order_out;
-    dim3 grid((C + NMS_WARPS - 1) / NMS_WARPS, B);
+    dim3 grid((C + 31) / 32, B);
     nms_select_kernel<<<grid, NMS_WARPS * 32, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();
