@@ -96,6 +96,11 @@ int y2_train_get_tensor(y2_handle* h, int kind, int layer, float* dst, void* str
  * (train.py:31-67); used by the per-layer parity tests.  pooled != 0 returns the max-pooled tensor. */
 int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* stream);
 
+/* Options.  "fuse_pool" (default 1): fuse the 2x2/2 max-pools (inference.py:74,83,96) into the conv epilogues when
+ * the batch and extent admit the spatial tiling (e.g. batch 32 at 416/608); 0 keeps the separate pool pass and
+ * materialises the un-pooled activations for y2_get_activation. */
+int y2_set_option(y2_handle* h, const char* key, int value);
+
 /* One conv (+scale/bias +leaky) on float32 NHWC tensors through the same tcgen05 kernel the
  * network uses (splits operands on the fly).  Diagnostic / test entry point.
  * block_n = 0 picks the tile width; max_ctas = 0 uses every SM (smaller values change how the

@@ -137,6 +137,39 @@ def test_darknet_forward_layer_by_layer_vs_oracle(cuda, classes, size, batch, an
     assert max(worst.values()) <= TOL, worst
 
 
+def test_fused_maxpool_epilogue_matches_separate_pool(cuda):
+    """Batch 32 admits the spatial tiling (16x8x1, 8x8x2, 4x4x8, 2x2x32 pixel blocks) that lets the 2x2 max-pool run
+    inside the conv epilogue (warp shuffles).  Fused and separate paths must agree bit for bit, and with the oracle."""
+    import torch
+    from yolo_tf_b200 import _lib
+    from yolo_tf_b200.model.yolo2 import inference
+    classes, size, batch = 20, 64, 32
+    params = init_params(classes, 5, seed=5)
+    _setup_store(params)
+    rs = np.random.RandomState(3)
+    x = rs.normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
+    xd = torch.from_numpy(x).to(cuda)
+    eng = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+    outs, pooled = {}, {}
+    for fuse in (1, 0):
+        _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", fuse))
+        _, out = inference.darknet(xd, classes, 5)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().y2_check_async_errors())
+        outs[fuse] = out.cpu().numpy()
+        pooled[fuse] = {i: eng.activation(i, True, (batch, size >> (k + 1), size >> (k + 1), c)).cpu().numpy()
+                        for k, (i, c) in enumerate([(0, 32), (1, 64), (4, 128), (7, 256), (12, 512)])}
+        if fuse:
+            with pytest.raises(_lib.Y2Error):
+                eng.activation(1, False, (batch, 32, 32, 64))       # un-pooled conv1 is never materialised when fused
+    _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", 1))
+    assert np.array_equal(outs[1].view(np.uint32), outs[0].view(np.uint32))
+    for i in pooled[1]:
+        assert np.array_equal(pooled[1][i].view(np.uint32), pooled[0][i].view(np.uint32)), i
+    ref = darknet_oracle(x, params, classes, 5)
+    assert _rel(outs[1], ref.astype(np.float64)) <= TOL
+
+
 def test_xavier_checkpoint_config1(cuda):
     """BASELINE config 1 weights: what slim creates (Xavier-uniform, BN gamma=1 beta=0 mean=0 var=1)."""
     import torch

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "y2_nms_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "y2_nms": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "y2_check_async_errors": (c_i, []),
+    "y2_set_option": (c_i, [c_p, ctypes.c_char_p, c_i]),
     "y2_conv2d_wgrad": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p]),
     "y2_train_workspace_bytes": (c_sz, [c_p, c_i, c_i, c_i]),
     "y2_darknet_forward_train": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),

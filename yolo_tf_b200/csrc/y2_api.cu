@@ -118,6 +118,7 @@ struct Plan {
     bf16* concat = nullptr;
     void* streamk = nullptr;
     std::vector<TcConvLaunch> launch;   // per layer (index 0 unused)
+    std::vector<char> fused;            // per layer: max-pool fused into the conv epilogue
 };
 
 }  // namespace y2
@@ -129,6 +130,7 @@ struct y2_handle {
     std::vector<LayerState> layers;
     Plan plan;
     TrainPlan tplan;
+    int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
     bool profiling = false;
@@ -299,6 +301,7 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
     P.B = B; P.H = H; P.W = W; P.ws = ws; P.ws_bytes = ws_bytes; P.precision = precision;
     P.act.assign(nl, nullptr); P.pooled.assign(nl, nullptr); P.oh = l.oh; P.ow = l.ow;
     P.launch.resize(nl);
+    P.fused.assign(nl, 0);
     P.concat = reinterpret_cast<bf16*>(base + l.concat_off);
     P.streamk = base + l.streamk_off;
     Y2_CUDA(cudaMemsetAsync(P.streamk, 0, 4096, s));          // hand-off flags start at 0 (epochs are >= 1)
@@ -314,10 +317,18 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
         const size_t M = (size_t)B * oh * ow;
         if (i == nl - 2) input = P.concat;         // conv20 reads concat([reorg, conv19])
         TcConvLaunch& T = P.launch[i];
+        // max-pool layers: fuse the 2x2/2 pool into the conv epilogue when the batch / extent admit the spatial tiling
+        const bool fuse = L.d.pool && h->fuse_pool && tc_conv_can_fuse_pool(B, oh, ow);
+        P.fused[i] = fuse;
         if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin, L.d.ksize, L.wpack, L.d.cout, L.cout_pad, L.block_n,
-                         0, precision == 0, h->num_sms, P.streamk))
+                         0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0))
             return -1;
         ConvParams& p = T.p;
+        if (fuse) {
+            p.pool_hi = P.pooled[i];
+            p.pool_lo = P.pooled[i] + (M / 4) * L.d.cout;
+            p.ldp = L.d.cout;
+        }
         p.scale = L.d.has_bn ? L.scale : nullptr;
         p.bias = L.bias;
         p.leaky = L.d.has_bn ? 1 : 0;
@@ -331,6 +342,7 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
             p.mode = EPI_PLANES; p.ldc = L.d.cout;
             p.out_hi = P.act[i];
             p.out_lo = P.act[i] + M * L.d.cout;
+            if (fuse && !L.d.passthrough) p.out_hi = p.out_lo = nullptr;   // the un-pooled tensor is never materialised
         }
         input = L.d.pool ? P.pooled[i] : P.act[i];
     }
@@ -370,7 +382,7 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
             // reorg(passthrough) -> concat channels [0, 2048); both planes in one launch (batch 2B)
             if (reorg_launch(P.act[i], P.concat, 2 * B, oh, ow, L.d.cout, 2, 2, 4 * L.d.cout + 1024, s)) return -1;
         }
-        if (L.d.pool) {
+        if (L.d.pool && !P.fused[i]) {
             if (maxpool_planes_launch(P.act[i], P.act[i] + M * L.d.cout, P.pooled[i],
                                       P.pooled[i] + (M / 4) * L.d.cout, B, oh, ow, L.d.cout, s))
                 return -1;
@@ -428,7 +440,18 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
         const int cat_c = 4 * 512 + 1024;
         return merge_planes_launch(P.concat + 2048, P.concat + M * cat_c + 2048, dst, M, d.cout, cat_c, s);
     }
+    Y2_REQUIRE(!(P.fused[layer] && !d.passthrough),
+               "y2_get_activation: layer %d's max-pool is fused into its conv epilogue; the un-pooled tensor is not "
+               "materialised (y2_set_option(h, \"fuse_pool\", 0) keeps it)", layer);
     return merge_planes_launch(P.act[layer], P.act[layer] + M * d.cout, dst, M, d.cout, d.cout, s);
+}
+
+/* Options: "fuse_pool" (default 1) -- fuse the 2x2 max-pools into the conv epilogues when the shape allows it. */
+int y2_set_option(y2_handle* h, const char* key, int value) {
+    Y2_REQUIRE(h && key, "y2_set_option: null argument");
+    if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }
+    set_error("y2_set_option: unknown option '%s'", key);
+    return -1;
 }
 
 int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,

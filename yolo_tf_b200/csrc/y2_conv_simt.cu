@@ -179,32 +179,48 @@ conv0_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dx_hi, 
     for (int k = 0; k < 27; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
-    for (size_t idx = (size_t)blockIdx.x * 32 + lane; idx < total; idx += (size_t)gridDim.x * 32) {
-        const int xx0 = (int)(idx % W);
-        size_t t = idx / W;
+    // a block walks strips of 32 consecutive pixels of one image row; the 3 x 34 x 3 input halo of the strip is staged
+    // once in shared memory (coalesced) and shared by the 8 channel-group warps
+    __shared__ float sin_[3][34 * 3 + 2];
+    const int strips_x = (W + 31) / 32;
+    const size_t strips = (size_t)B * H * strips_x;
+    (void)total;
+    for (size_t sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
+        const int xs = (int)(sidx % strips_x);
+        size_t t = sidx / strips_x;
         const int yy0 = (int)(t % H);
         const int b = (int)(t / H);
-        const uint2 h = __ldg(reinterpret_cast<const uint2*>(dx_hi + idx * 32 + warp * 4));
-        const uint2 l = __ldg(reinterpret_cast<const uint2*>(dx_lo + idx * 32 + warp * 4));
-        float d[4];
-        d[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-        d[1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
-        d[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-        d[3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+        const int x0 = xs * 32;
+        __syncthreads();                                   // previous strip's readers are done
+        for (int e = threadIdx.x; e < 3 * 102; e += blockDim.x) {
+            const int r = e / 102, rem = e - r * 102;
+            const int px = rem / 3, ch = rem - px * 3;
+            const int yy = yy0 - 1 + r, xx = x0 - 1 + px;
+            const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+            sin_[r][rem] = ok ? __ldg(x + (((size_t)b * H + yy) * W + xx) * 3 + ch) : 0.f;
+        }
+        __syncthreads();
+        const int xx0 = x0 + lane;
+        if (xx0 < W) {
+            const size_t idx = ((size_t)b * H + yy0) * W + xx0;
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>(dx_hi + idx * 32 + warp * 4));
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(dx_lo + idx * 32 + warp * 4));
+            float d[4];
+            d[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+            d[1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+            d[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+            d[3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int yy = yy0 - 1 + r, xx = xx0 - 1 + c;
-                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-                const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float v = ok ? __ldg(src + ch) : 0.f;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float v = sin_[r][(lane + c) * 3 + ch];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[(r * 3 + c) * 3 + ch][j] = fmaf(v, d[j], acc[(r * 3 + c) * 3 + ch][j]);
-                }
-            }
+                        for (int j = 0; j < 4; ++j) acc[(r * 3 + c) * 3 + ch][j] = fmaf(v, d[j], acc[(r * 3 + c) * 3 + ch][j]);
+                    }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 27; ++k)

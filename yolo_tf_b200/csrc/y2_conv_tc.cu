@@ -229,7 +229,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int nt = tile / p.m_tiles;
             const int mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
-            const long long row = (long long)mt * BLOCK_M + q * 32 + lane;
+            long long row = (long long)mt * BLOCK_M + q * 32 + lane;
+            bool pool_writer = false;
+            size_t pool_row = 0;
+            if (p.tx) {                                      // spatial tile: row r = (image bb, yy, xx) inside the block
+                const int r = q * 32 + lane;
+                const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
+                const int xx = r % p.tx, yy = (r / p.tx) % p.ty, bb = r / (p.tx * p.ty);
+                const int px = xt * p.tx + xx, py = (r2 % p.tiles_y) * p.ty + yy, pb = (r2 / p.tiles_y) * p.tb + bb;
+                row = ((long long)pb * p.H + py) * p.W + px;
+                pool_writer = ((xx | yy) & 1) == 0;
+                pool_row = ((size_t)pb * (p.H / 2) + py / 2) * (p.W / 2) + px / 2;
+            }
             const bool row_ok = row < p.M;
             const bool is_head = (kb0 == 0);                 // owns the tile's output
             // stream-K CTAs blockIdx.x+1 .. last_contrib start inside this tile and hold its other k-ranges
@@ -335,22 +346,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (!row_ok) continue;
                 if (p.mode == EPI_PLANES) {
-                    uint32_t hi[16], lo[16];
+                    auto store_planes = [&](bf16* dst_hi, bf16* dst_lo, size_t off) {
+                        uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]);
-                        const __nv_bfloat16 h1 = __float2bfloat16_rn(f[2 * j + 1]);
-                        const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
-                        const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
-                        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                    }
-                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldc + n0 + c);
-                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldc + n0 + c);
+                        for (int j = 0; j < 16; ++j) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]);
+                            const __nv_bfloat16 h1 = __float2bfloat16_rn(f[2 * j + 1]);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(dst_hi + off);
+                        uint4* dl = reinterpret_cast<uint4*>(dst_lo + off);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) {
+                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    };
+                    if (p.out_hi) store_planes(p.out_hi, p.out_lo, (size_t)row * p.ldc + n0 + c);
+                    if (p.tx) {
+                        // fused 2x2/2 max-pool: the tile is a tx x ty spatial block, so the window partners of row r are
+                        // rows r^1 (x) and r^tx (y) = lanes of the same warp.  Max on the exact fp32 values, then split.
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float m = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.tx));
+                        }
+                        if (pool_writer) store_planes(p.pool_hi, p.pool_lo, pool_row * (size_t)p.ldp + n0 + c);
                     }
                 } else {  // EPI_F32: 128-bit stores when aligned, else masked scalar stores (N = 425, 125)
                     float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c;
@@ -452,8 +476,28 @@ int tc_conv_check_watchdog() {
     return -3;
 }
 
+// Spatial tiling for the fused max-pool epilogue: tx x ty pixels x tb images = 128 rows, tx a power of two in [2,16]
+// (the window partners must be lanes r^1 and r^tx of one warp), exact cover of (W, H, B).
+static bool pool_tiling(int B, int H, int W, int* tx, int* ty, int* tb) {
+    if ((H & 1) || (W & 1)) return false;
+    for (int x = 16; x >= 2; x >>= 1) {
+        if (W % x) continue;
+        for (int y = 128 / x; y >= 2; y >>= 1) {
+            const int b = 128 / (x * y);
+            if (x * y * b != 128 || x * y < 4) continue;
+            if ((x * y) % 32 != 0 && 32 % (x * y) != 0) continue;     // a warp = whole rows of the block
+            if (H % y == 0 && B % b == 0 && (y & 1) == 0) { *tx = x; *ty = y; *tb = b; return true; }
+        }
+    }
+    return false;
+}
+bool tc_conv_can_fuse_pool(int B, int H, int W) {
+    int a, b, c;
+    return pool_tiling(B, H, W, &a, &b, &c);
+}
+
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize, const bf16* wpack,
-                 int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws) {
+                 int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws, int fuse_pool) {
     if (load_driver_entry_points()) return -1;
     Y2_REQUIRE(ksize == 1 || ksize == 3, "tc conv: ksize must be 1 or 3 (got %d)", ksize);
     Y2_REQUIRE(Cin % 32 == 0, "tc conv: Cin must be a multiple of 32 (got %d)", Cin);
@@ -470,6 +514,11 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     p.M = (int)M; p.N = cout; p.Cin = Cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
     p.block_n = block_n;
     p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    if (fuse_pool) {
+        Y2_REQUIRE(pool_tiling(B, H, W, &p.tx, &p.ty, &p.tb), "tc conv: no spatial tiling for the fused max-pool at B=%d H=%d W=%d", B, H, W);
+        p.tiles_x = W / p.tx; p.tiles_y = H / p.ty;
+        p.m_tiles = p.tiles_x * p.tiles_y * (B / p.tb);          // exact cover: same count, different pixel order
+    }
     p.n_tiles = cout_pad / block_n;
     p.kblocks_total = taps * (Cin / BK);
     p.cout_pad = cout_pad;
@@ -490,6 +539,19 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
                     &p.sk_ctas, &L->grid);
     Y2_REQUIRE(L->grid <= 1024, "tc conv: grid too large for the flag page");
 
+    if (fuse_pool) {
+        // activation map for the fused max-pool layers: (C, W, H, N=2B) bf16, TILE mode, box {BK, tx, ty, tb}
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.tx, (cuuint32_t)p.ty, (cuuint32_t)p.tb};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encodeTiled(&L->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in_planes), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D activation) failed (%d) B=%d H=%d W=%d Cin=%d box=%dx%dx%d",
+                   (int)r, B, H, W, Cin, p.tx, p.ty, p.tb);
+    } else
     // activation map: (C, W, H, N=2B) bf16, im2col mode, BLOCK_M pixels x BK channels per load
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};

@@ -47,6 +47,9 @@ struct ConvParams {
     int M, N, Cin, ksize, B, H, W;
     int block_n, m_tiles, n_tiles, kblocks_total;
     int dp_tiles, sk_ctas;   // schedule (choose_schedule)
+    int tx, ty, tb, tiles_x, tiles_y;   // tx != 0: M-tiles are tx x ty pixel blocks of tb images (fused max-pool layers)
+    bf16 *pool_hi, *pool_lo; // fused 2x2/2 max-pool output planes [B][H/2][W/2][N], row pitch ldp
+    long long ldp;
     int cout_pad;            // rows per weight plane in the packed weight matrix
     int num_stages;
     int mode;                // EpilogueMode
@@ -115,7 +118,9 @@ struct TcConvLaunch {
 // wpack: bf16 [2][cout_pad][ksize*ksize*Cin] (k = tap*Cin + c).  Returns 0 or <0 (error set).
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
                  const bf16* wpack, int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms,
-                 void* streamk_ws);
+                 void* streamk_ws, int fuse_pool = 0);
+// true when (B, H, W) admits the spatial tiling the fused max-pool epilogue needs
+bool tc_conv_can_fuse_pool(int B, int H, int W);
 // bytes of the stream-K scratch (flags page + one partial tile per SM); must be zeroed once before first use
 size_t tc_conv_streamk_bytes(int num_sms);
 int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);

@@ -10,14 +10,17 @@
 //   * IoU uses the float32 operation order of iou() with no FMA contraction (explicit _rn intrinsics).
 //
 // Three kernels, no host round trip:
-//   select : one warp per (image, class).  Compacts the candidates (> threshold) in index order,
-//            rank-sorts them with the lexicographic comparator (ties descend into earlier class
-//            columns, which are still unmodified because nothing is written here), then runs the
+//   select : a CTA owns 32 classes of one image.  Candidates (> threshold) are compacted with coalesced reads
+//            (a warp reads 32 consecutive classes of one box = 128 bytes; lane = class; slots from a shared-memory
+//            counter).  Then one warp per class rank-sorts its candidates with the lexicographic comparator (ties
+//            descend into earlier class columns, still unmodified because nothing is written here) and runs the
 //            sequential greedy sweep with a shared-memory alive bitmask -> list of KEPT boxes.
 //   order  : (optional) final permutation of the N boxes = the order of the list the reference returns.
-//   apply  : one thread per score.  A candidate is zeroed iff it is not kept; a non-candidate (it
-//            sorts after every candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
-// Scores are read once by select (class-strided, L2-resident) and once by apply (coalesced).
+//   apply  : a CTA owns a [64 boxes][32 classes] tile (coalesced 128-byte rows through shared memory); warps walk
+//            class columns with lanes = boxes, the class's kept boxes broadcast from shared memory.  A candidate is
+//            zeroed iff it is not kept; a non-candidate (it sorts after every candidate) is zeroed iff any kept box
+//            overlaps it >= threshold_iou (disjoint pairs are rejected before the divide when threshold_iou > 0).
+// Scores are read once by select and once by apply, both coalesced; only tiles that change are written back.
 #include "y2_internal.h"
 
 namespace y2 {

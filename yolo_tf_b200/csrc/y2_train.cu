@@ -130,16 +130,34 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(RedArgs a) {
     }
 }
 
-// ---- finish kernels (one thread per channel, fixed summation order) ----
+// ---- finish kernels: a block owns 32 channels (lane = channel: coalesced 256-byte rows of the partial matrix); its
+// 8 warps sum interleaved subsets of the per-block partials, then warp 0 combines them in fixed order (deterministic).
+static constexpr int FIN_THREADS = 256;
+__device__ __forceinline__ bool finish_sums(const double* __restrict__ partial, int nblocks, int C, double* s1, double* s2) {
+    __shared__ double sm[2][8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    double a1 = 0, a2 = 0;
+    if (c < C)
+        for (int b = warp; b < nblocks; b += 8) { a1 += partial[((size_t)b * 2) * C + c]; a2 += partial[((size_t)b * 2 + 1) * C + c]; }
+    sm[0][warp][lane] = a1; sm[1][warp][lane] = a2;
+    __syncthreads();
+    if (warp != 0 || c >= C) return false;
+    double t1 = 0, t2 = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t1 += sm[0][w][lane]; t2 += sm[1][w][lane]; }
+    *s1 = t1; *s2 = t2;
+    return true;
+}
 // forward: mean/var -> inv, scale, bias; moving averages updated as slim does
 // (assign_moving_average: v -= (v - value) * (1 - decay))
-__global__ void bn_stats_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, const float* gamma,
-                                       const float* beta, float eps, float decay, float* mean, float* inv, float* scale,
-                                       float* bias, float* moving_mean, float* moving_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0, s2 = 0;
-    for (int b = 0; b < nblocks; ++b) { s1 += partial[((size_t)b * 2) * C + c]; s2 += partial[((size_t)b * 2 + 1) * C + c]; }
+__global__ void __launch_bounds__(FIN_THREADS)
+bn_stats_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, const float* gamma,
+                       const float* beta, float eps, float decay, float* mean, float* inv, float* scale,
+                       float* bias, float* moving_mean, float* moving_var) {
+    double s1, s2;
+    if (!finish_sums(partial, nblocks, C, &s1, &s2)) return;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const double m = s1 * inv_rows;
     double v = s2 * inv_rows - m * m;
     if (v < 0) v = 0;
@@ -151,21 +169,19 @@ __global__ void bn_stats_finish_kernel(const double* partial, int nblocks, int C
     moving_var[c] -= (moving_var[c] - vf) * (1.0f - decay);
 }
 // backward: dbeta = s1, dgamma = s2 (written into the gradient bucket), and the per-channel means
-__global__ void bn_bwd_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, float* dgamma,
-                                     float* dbeta, float* m1, float* m2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0, s2 = 0;
-    for (int b = 0; b < nblocks; ++b) { s1 += partial[((size_t)b * 2) * C + c]; s2 += partial[((size_t)b * 2 + 1) * C + c]; }
+__global__ void __launch_bounds__(FIN_THREADS)
+bn_bwd_finish_kernel(const double* partial, int nblocks, int C, double inv_rows, float* dgamma, float* dbeta, float* m1, float* m2) {
+    double s1, s2;
+    if (!finish_sums(partial, nblocks, C, &s1, &s2)) return;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     dbeta[c] = (float)s1; dgamma[c] = (float)s2;
     m1[c] = (float)(s1 * inv_rows); m2[c] = (float)(s2 * inv_rows);
 }
-__global__ void bias_grad_finish_kernel(const double* partial, int nblocks, int C, float* dbias) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0;
-    for (int b = 0; b < nblocks; ++b) s1 += partial[((size_t)b * 2) * C + c];
-    dbias[c] = (float)s1;
+__global__ void __launch_bounds__(FIN_THREADS)
+bias_grad_finish_kernel(const double* partial, int nblocks, int C, float* dbias) {
+    double s1, s2;
+    if (!finish_sums(partial, nblocks, C, &s1, &s2)) return;
+    dbias[blockIdx.x * 32 + (threadIdx.x & 31)] = (float)s1;
 }
 
 int bn_stats_launch(const float* z, size_t rows, int C, const float* gamma, const float* beta, float eps, float decay,
@@ -178,7 +194,7 @@ int bn_stats_launch(const float* z, size_t rows, int C, const float* gamma, cons
     col_reduce_kernel<0><<<nb, RED_THREADS, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();
-    bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, 1.0 / (double)rows, gamma, beta, eps, decay, mean,
+    bn_stats_finish_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(partial, nb, C, 1.0 / (double)rows, gamma, beta, eps, decay, mean,
                                                           inv, scale, bias, moving_mean, moving_var);
     Y2_CUDA(cudaGetLastError());
     note_launch();
@@ -196,7 +212,7 @@ int bn_bwd_reduce_launch(const float* z, const float* g, long long ldg, size_t r
     col_reduce_kernel<1><<<nb, RED_THREADS, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();
-    bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, 1.0 / (double)rows, dgamma, dbeta, m1, m2);
+    bn_bwd_finish_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(partial, nb, C, 1.0 / (double)rows, dgamma, dbeta, m1, m2);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -210,7 +226,7 @@ int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* d
     col_reduce_kernel<2><<<nb, RED_THREADS, 0, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();
-    bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nb, C, dbias);
+    bias_grad_finish_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(partial, nb, C, dbias);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
