@@ -116,23 +116,31 @@ def test_darknet_forward_layer_by_layer_vs_oracle(cuda, classes, size, batch, an
     x = rs.normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
     taps = {}
     ref = darknet_oracle(x, params, classes, 5, taps=taps)
-    scope, out = inference.darknet(torch.from_numpy(x).to(cuda), classes, 5)
-    torch.cuda.synchronize()
-    _lib.check(_lib.lib().y2_check_async_errors())
-    assert scope == "yolo2_darknet"
     eng = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+    xd = torch.from_numpy(x).to(cuda)
     worst = {}
-    for i, (name, k, cin, cout, then) in enumerate(layer_table(classes, 5)[:-1]):
-        if i == 0:
-            got = eng.activation(0, True, taps["conv0/pool"].shape).cpu().numpy()
-            worst["conv0/pool"] = _rel(got, taps["conv0/pool"].astype(np.float64))
-            continue
-        got = eng.activation(i, False, taps[name].shape).cpu().numpy()
-        worst[name] = _rel(got, taps[name].astype(np.float64))
-        if then in ("pool", "passthrough+pool"):
-            gp = eng.activation(i, True, taps[name + "/pool"].shape).cpu().numpy()
-            worst[name + "/pool"] = _rel(gp, taps[name + "/pool"].astype(np.float64))
-    worst["output"] = _rel(out.cpu().numpy(), ref.astype(np.float64))
+    # Pass 1 keeps every un-pooled tensor (separate pool kernels); pass 2 is the default plan, where the pool of a
+    # layer may live in the conv epilogue and only the pooled tensor exists.
+    for fuse in (0, 1):
+        _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", fuse))
+        scope, out = inference.darknet(xd, classes, 5)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().y2_check_async_errors())
+        assert scope == "yolo2_darknet"
+        tag = "" if fuse == 0 else "[fused]"
+        for i, (name, k, cin, cout, then) in enumerate(layer_table(classes, 5)[:-1]):
+            if i == 0:
+                got = eng.activation(0, True, taps["conv0/pool"].shape).cpu().numpy()
+                worst["conv0/pool" + tag] = _rel(got, taps["conv0/pool"].astype(np.float64))
+                continue
+            has_pool = then in ("pool", "passthrough+pool")
+            if fuse == 0:
+                got = eng.activation(i, False, taps[name].shape).cpu().numpy()
+                worst[name] = _rel(got, taps[name].astype(np.float64))
+            if has_pool:
+                gp = eng.activation(i, True, taps[name + "/pool"].shape).cpu().numpy()
+                worst[name + "/pool" + tag] = _rel(gp, taps[name + "/pool"].astype(np.float64))
+        worst["output" + tag] = _rel(out.cpu().numpy(), ref.astype(np.float64))
     print("per-layer rel err:", {k: "%.1e" % v for k, v in worst.items()})
     assert max(worst.values()) <= TOL, worst
 

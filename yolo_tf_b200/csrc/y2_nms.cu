@@ -175,6 +175,7 @@ static constexpr int AP_BOXES = 64, AP_CLASSES = 32;
 __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
     __shared__ float tile[AP_BOXES][AP_CLASSES + 1];
     __shared__ float4 kbox[8][32];
+    __shared__ float karea[8][32];
     __shared__ int tile_cnt[AP_CLASSES];
     __shared__ int any_kept, dirty;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,8 +217,11 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
             n_ok[h] = n < a.N;
             bn[h] = n_ok[h] ? load_box(bmin, bmax, n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        const float barea[2] = {__fmul_rn(__fsub_rn(bn[0].z, bn[0].x), __fsub_rn(bn[0].w, bn[0].y)),
+                                __fmul_rn(__fsub_rn(bn[1].z, bn[1].x), __fsub_rn(bn[1].w, bn[1].y))};
         bool wrote = false;
         const bool quick = a.thr_iou > 0.0f;
+        const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
             const int cnt = tile_cnt[cl];
             if (cnt == 0) continue;                                  // warp-uniform
@@ -229,17 +233,35 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
             for (int k0 = 0; k0 < cnt; k0 += 32) {
                 const int kc = min(32, cnt - k0);
                 int kidx = -1;
-                if (lane < kc) { kidx = kept[k0 + lane]; kbox[warp][lane] = load_box(bmin, bmax, kidx); }
+                if (lane < kc) {
+                    kidx = kept[k0 + lane];
+                    const float4 kq = load_box(bmin, bmax, kidx);
+                    kbox[warp][lane] = kq;
+                    karea[warp][lane] = __fmul_rn(__fsub_rn(kq.z, kq.x), __fsub_rn(kq.w, kq.y));
+                }
                 __syncwarp();
                 for (int t = 0; t < kc; ++t) {
                     const float4 kb = kbox[warp][t];
+                    const float ka = karea[warp][t];
                     const int ki = __shfl_sync(0xffffffffu, kidx, t);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         found[h] |= (ki == n0 + h * 32 + lane);
-                        // disjoint boxes have inter == 0 -> iou == 0 (or NaN) -> never >= a positive threshold: skip the divide
-                        if (!cand[h] && !hit[h] && (!quick || (kb.x < bn[h].z && bn[h].x < kb.z && kb.y < bn[h].w && bn[h].y < kb.w)))
+                        if (cand[h] || hit[h]) continue;
+                        if (quick) {
+                            // Same float32 operations as iou_ref up to the divide (bit-identical inter and den), then a
+                            // conservative filter: rn(inter/den) >= thr needs inter >= thr*(1-2^-24)*den, so anything
+                            // below 0.999*thr*den is certainly no hit and skips the IEEE division.  Disjoint pairs
+                            // (inter == 0) fall out here too.  NaNs fail the '<' and take the exact path.
+                            const float iw = fmaxf(__fsub_rn(fminf(kb.z, bn[h].z), fmaxf(kb.x, bn[h].x)), 0.0f);
+                            const float ih = fmaxf(__fsub_rn(fminf(kb.w, bn[h].w), fmaxf(kb.y, bn[h].y)), 0.0f);
+                            const float inter = __fmul_rn(iw, ih);
+                            const float den = fmaxf(__fsub_rn(__fadd_rn(ka, barea[h]), inter), 1e-10f);
+                            if (inter < __fmul_rn(thr_lo, den)) continue;
+                            hit[h] = __fdiv_rn(inter, den) >= a.thr_iou;
+                        } else {
                             hit[h] = iou_ref(kb, bn[h]) >= a.thr_iou;
+                        }
                     }
                 }
                 __syncwarp();

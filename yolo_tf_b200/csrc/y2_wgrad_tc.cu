@@ -219,6 +219,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 __syncwarp();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
+            // other contributors' partials: staged through the idle smem ring with cp.async, one chunk ahead
+            // (same scheme as the forward kernel: per-thread row slots, 16-byte pieces XOR-swizzled by row)
+            const int ncontrib = last_contrib - (int)blockIdx.x;
+            const int max_staged = (int)(((size_t)S * stage_bytes) / (2u * WG_M * 128u));
+            const int nstaged = ncontrib < max_staged ? ncontrib : max_staged;
+            auto stage_slot = [&](int buf, int hh) -> uint32_t {
+                return smem_u32(smem) + (uint32_t)(((buf * nstaged + hh) * WG_M + r) * 128);
+            };
+            auto stage_issue = [&](int c, int buf) {
+                for (int hh = 0; hh < nstaged; ++hh) {
+                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + hh) * WG_M * p.block_n + (size_t)r * p.block_n + c;
+                    const uint32_t dst = stage_slot(buf, hh);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((j ^ (r & 7)) << 4)), "l"(src + 4 * j) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (is_head && nstaged > 0) stage_issue(0, 0);
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
@@ -234,7 +253,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {
+                if (nstaged > 0) {
+                    const int buf = (c >> 5) & 1;
+                    if (c + 32 < p.block_n) {
+                        stage_issue(c + 32, buf ^ 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    for (int hh = 0; hh < nstaged; ++hh) {
+                        const uint32_t src = stage_slot(buf, hh);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 t;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                         : "r"(src + (uint32_t)((j ^ (r & 7)) << 4)));
+                            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                        }
+                    }
+                }
+                for (int h = blockIdx.x + 1 + nstaged; h <= last_contrib; ++h) {
                     const float4* src = reinterpret_cast<const float4*>(p.sk_partial + (size_t)h * WG_M * p.block_n + (size_t)r * p.block_n + c);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
