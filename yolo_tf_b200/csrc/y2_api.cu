@@ -131,6 +131,7 @@ struct y2_handle {
     Plan plan;
     TrainPlan tplan;
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
+    int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
     bool profiling = false;
@@ -318,10 +319,11 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
         if (i == nl - 2) input = P.concat;         // conv20 reads concat([reorg, conv19])
         TcConvLaunch& T = P.launch[i];
         // max-pool layers: fuse the 2x2/2 pool into the conv epilogue when the batch / extent admit the spatial tiling
-        const bool fuse = L.d.pool && h->fuse_pool && tc_conv_can_fuse_pool(B, oh, ow);
+        const int halo = (h->halo && tc_conv_can_halo(B, oh, ow, L.d.cin, L.d.ksize, L.cout_pad, L.block_n, precision == 0)) ? h->halo : 0;
+        const bool fuse = L.d.pool && h->fuse_pool && (halo || tc_conv_can_fuse_pool(B, oh, ow));
         P.fused[i] = fuse;
         if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin, L.d.ksize, L.wpack, L.d.cout, L.cout_pad, L.block_n,
-                         0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0))
+                         0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0, halo))
             return -1;
         ConvParams& p = T.p;
         if (fuse) {
@@ -450,6 +452,7 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
 int y2_set_option(y2_handle* h, const char* key, int value) {
     Y2_REQUIRE(h && key, "y2_set_option: null argument");
     if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }
+    if (strcmp(key, "halo") == 0) { h->halo = value; h->plan.valid = false; return 0; }
     set_error("y2_set_option: unknown option '%s'", key);
     return -1;
 }
@@ -476,7 +479,8 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
         if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
         if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s)) break;
         TcConvLaunch T;
-        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk)) break;
+        const int halo = (g_conv_force_halo && tc_conv_can_halo(B, H, W, cin, ksize, cpad, bn, precision == 0)) ? g_conv_force_halo : 0;
+        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk, 0, halo)) break;
         T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
         T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
         cudaEvent_t e0, e1;
@@ -507,6 +511,8 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
 int y2_debug_set(int key, double value) {
     if (key == 0) g_sched_override = (int)value;
     else if (key == 1) g_sched_handoff_kb = value;
+    else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
+    else if (key == 4) g_conv_force_halo = (int)value;      // y2_conv2d: halo mode (1|2) where applicable
     else if (key == 2) { if (value != 0 && !g_dbg_host) g_dbg_host = new unsigned long long[1024 * 4]; if (value == 0) { delete[] g_dbg_host; g_dbg_host = nullptr; } }
     else return -1;
     return 0;

@@ -165,72 +165,80 @@ int conv0_raw_launch(const float* x, const float* w_hwio, float* z, int B, int H
     return 0;
 }
 
-// conv0 weight gradient: dW[27][32] = sum_p patch(p)[27] * dx(p)[32].  Warp w of a block owns output channels
-// [4w, 4w+4); lane = pixel lane; each thread keeps 27x4 partial sums; shuffle-reduce per warp, per-block
-// partials in fp64, fixed-order finish (deterministic).
+// conv0 weight gradient: dW[tap][cin][cout] = sum over pixels of x[p + tap][cin] * dx[p][cout]  (27 x 32 outputs, 11 M
+// pixels at batch 64: a skinny reduction, CUDA cores).  lane = output channel, every lane of a warp walks the SAME
+// pixels: the 27 input values of a pixel are warp-broadcast shared-memory reads (128-bit, 4 pixels = 18 consecutive floats
+// per image row), dx is one coalesced 64-byte row per plane.  A block stages the three input rows of one image row
+// (halo included), its 8 warps split the row's 4-pixel groups.  fp32 partial sums per lane, fp64 per-block partials,
+// fixed-order finish (deterministic).
 static constexpr int C0W_BLOCKS = 148 * 4;
+static constexpr int C0W_MAXW = 1024;
 __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dx_hi, const bf16* __restrict__ dx_lo,
                    double* __restrict__ partial, int B, int H, int W) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t total = (size_t)B * H * W;
-    float acc[27][4];
+    extern __shared__ __align__(16) float c0w_smem[];
+    const int pitch = ((W + 2) * 3 + 2 + 3) & ~3;           // floats per staged row (+2: the last 128-bit read overshoots)
+    float* sin_ = c0w_smem;                                  // [3][pitch]
+    float acc[27];
 #pragma unroll
-    for (int k = 0; k < 27; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
-    // a block walks strips of 32 consecutive pixels of one image row; the 3 x 34 x 3 input halo of the strip is staged
-    // once in shared memory (coalesced) and shared by the 8 channel-group warps
-    __shared__ float sin_[3][34 * 3 + 2];
-    const int strips_x = (W + 31) / 32;
-    const size_t strips = (size_t)B * H * strips_x;
-    (void)total;
-    for (size_t sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
-        const int xs = (int)(sidx % strips_x);
-        size_t t = sidx / strips_x;
-        const int yy0 = (int)(t % H);
-        const int b = (int)(t / H);
-        const int x0 = xs * 32;
-        __syncthreads();                                   // previous strip's readers are done
-        for (int e = threadIdx.x; e < 3 * 102; e += blockDim.x) {
-            const int r = e / 102, rem = e - r * 102;
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    const int groups = W / 4;
+    const long long rows = (long long)B * H;
+    for (long long ridx = blockIdx.x; ridx < rows; ridx += gridDim.x) {
+        const int yy0 = (int)(ridx % H);
+        const int b = (int)(ridx / H);
+        __syncthreads();                                     // previous row's readers are done
+        for (int e = threadIdx.x; e < 3 * pitch; e += blockDim.x) {
+            const int r = e / pitch, rem = e - r * pitch;
             const int px = rem / 3, ch = rem - px * 3;
-            const int yy = yy0 - 1 + r, xx = x0 - 1 + px;
+            const int yy = yy0 - 1 + r, xx = px - 1;
             const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-            sin_[r][rem] = ok ? __ldg(x + (((size_t)b * H + yy) * W + xx) * 3 + ch) : 0.f;
+            sin_[e] = ok ? __ldg(x + (((size_t)b * H + yy) * W + xx) * 3 + ch) : 0.f;
         }
         __syncthreads();
-        const int xx0 = x0 + lane;
-        if (xx0 < W) {
-            const size_t idx = ((size_t)b * H + yy0) * W + xx0;
-            const uint2 h = __ldg(reinterpret_cast<const uint2*>(dx_hi + idx * 32 + warp * 4));
-            const uint2 l = __ldg(reinterpret_cast<const uint2*>(dx_lo + idx * 32 + warp * 4));
+        const size_t row_base = ((size_t)b * H + yy0) * W;
+        for (int g = warp; g < groups; g += 8) {
+            // dx of the 4 pixels, this lane's channel: hi + lo
             float d[4];
-            d[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-            d[1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
-            d[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-            d[3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int i = 0; i < 4; ++i) {
+                const size_t idx = (row_base + 4 * g + i) * 32 + lane;
+                const unsigned short h = __ldg(reinterpret_cast<const unsigned short*>(dx_hi) + idx);
+                const unsigned short l = __ldg(reinterpret_cast<const unsigned short*>(dx_lo) + idx);
+                d[i] = __uint_as_float((uint32_t)h << 16) + __uint_as_float((uint32_t)l << 16);
+            }
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) {
+                float v[20];                                 // pixels 4g-1 .. 4g+4 of input row r: 18 floats (+2 unused)
+                const float4* src = reinterpret_cast<const float4*>(sin_ + r * pitch + 12 * g);
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float v = sin_[r][(lane + c) * 3 + ch];
+                for (int q = 0; q < 5; ++q) {
+                    const float4 t = src[q];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[(r * 3 + c) * 3 + ch][j] = fmaf(v, d[j], acc[(r * 3 + c) * 3 + ch][j]);
-                    }
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            acc[(r * 3 + c) * 3 + ch] = fmaf(v[(i + c) * 3 + ch], d[i], acc[(r * 3 + c) * 3 + ch]);
+            }
         }
     }
+    // block reduction over the 8 warps (same channel = same lane), then one fp64 partial per block
+    __syncthreads();
+    float* red = c0w_smem;                                   // [8][27][32] floats = 27.6 KB (reuses the staging area)
 #pragma unroll
-    for (int k = 0; k < 27; ++k)
+    for (int k = 0; k < 27; ++k) red[(warp * 27 + k) * 32 + lane] = acc[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
+        double sacc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v = acc[k][j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) partial[((size_t)blockIdx.x * 27 + k) * 32 + warp * 4 + j] = (double)v;
-        }
+        for (int w = 0; w < 8; ++w) sacc += (double)red[w * 27 * 32 + i];
+        partial[(size_t)blockIdx.x * 27 * 32 + i] = sacc;
+    }
 }
 __global__ void conv0_wgrad_finish_kernel(const double* partial, int nblocks, float* dw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +249,11 @@ __global__ void conv0_wgrad_finish_kernel(const double* partial, int nblocks, fl
 }
 int conv0_wgrad_launch(const float* x, const bf16* dx_hi, const bf16* dx_lo, float* dw, double* partial, int B, int H, int W,
                        cudaStream_t s) {
-    conv0_wgrad_kernel<<<C0W_BLOCKS, 256, 0, s>>>(x, dx_hi, dx_lo, partial, B, H, W);
+    Y2_REQUIRE(W % 4 == 0 && W <= C0W_MAXW, "conv0 wgrad: W must be a multiple of 4 and <= %d (got %d)", C0W_MAXW, W);
+    const int pitch = ((W + 2) * 3 + 2 + 3) & ~3;
+    size_t smem = (size_t)3 * pitch * sizeof(float);
+    if (smem < (size_t)8 * 27 * 32 * sizeof(float)) smem = (size_t)8 * 27 * 32 * sizeof(float);
+    conv0_wgrad_kernel<<<C0W_BLOCKS, 256, smem, s>>>(x, dx_hi, dx_lo, partial, B, H, W);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     conv0_wgrad_finish_kernel<<<(27 * 32 + 127) / 128, 128, 0, s>>>(partial, C0W_BLOCKS, dw);

@@ -64,6 +64,15 @@ __device__ __forceinline__ void flag_wait(const unsigned int* f, unsigned int ep
     }
 }
 
+// (x0, x1) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi); one packed convert per pair of values.
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);              // .x (low half) = x0
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 template <int BK, bool SPLIT3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -76,17 +85,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int b_tile = p.block_n * ROW_BYTES;
-    const int stage_bytes = PLANES * (A_TILE + b_tile);
+    const int stage_bytes = p.halo ? PLANES * p.halo_plane_bytes : PLANES * (A_TILE + b_tile);
     const int S = p.num_stages;
-    float* sb = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);       // [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + SB_BYTES);
+    uint8_t* ring = smem + p.bres_bytes;                    // halo mode keeps the weights of all taps below the ring
+    float* sb = reinterpret_cast<float*>(ring + (size_t)S * stage_bytes);       // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_bytes + SB_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + S;
     uint64_t* tfull = bars + 2 * S;
     uint64_t* tempty = bars + 2 * S + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    uint64_t* bres = bars + 2 * S + 5;                      // halo mode: resident weights landed
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform (also for the compiler)
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -102,6 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4);
         }
+        mbar_init(bres, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -117,101 +129,162 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int hw = p.H * p.W;
 
     if (warp == 0) {
-        // ===================== TMA producer (one lane) =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            SegIter it;
-            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-            int tile, kb0, kb1;
-            while (it.next(tile, kb0, kb1)) {
-                const int nt = tile / p.m_tiles;
-                const int mt = tile - nt * p.m_tiles;
-                int img, y0, x0;
-                if (p.tx) {                                  // spatial tile (tx x ty pixels x tb images): fused max-pool layers
-                    const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
-                    x0 = xt * p.tx; y0 = (r2 % p.tiles_y) * p.ty; img = (r2 / p.tiles_y) * p.tb;
-                } else {                                     // linear range of 128 pixels
-                    const int m0 = mt * BLOCK_M;
-                    img = m0 / hw;
-                    const int rem = m0 - img * hw;
-                    y0 = rem / p.W;
-                    x0 = rem - y0 * p.W;
-                }
-                const int n0 = nt * p.block_n;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const int tap = kb / cblocks;
-                    const int c0 = (kb - tap * cblocks) * BK;
+        // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        SegIter it;
+        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        int tile, kb0, kb1;
+        if (BK == 32 && p.halo && !(p.dbg_flags & 1)) {      // all 9 taps of the packed weights: once per CTA
+            mbar_expect_tx_e(leader, bres, (uint32_t)(9 * PLANES * b_tile));
+            for (int tap = 0; tap < 9; ++tap) {
+                tma_load_2d_e(leader, smem + (size_t)(tap * PLANES) * b_tile, &map_w, bres, tap * BK, 0);
+                if (SPLIT3) tma_load_2d_e(leader, smem + (size_t)(tap * PLANES + 1) * b_tile, &map_w, bres, tap * BK, p.cout_pad);
+            }
+        }
+        while (it.next(tile, kb0, kb1)) {
+            const int nt = tile / p.m_tiles;
+            const int mt = tile - nt * p.m_tiles;
+            int img, y0, x0;
+            if (p.tx) {                                      // spatial tile (tx x ty pixels x tb images)
+                const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
+                x0 = xt * p.tx; y0 = (r2 % p.tiles_y) * p.ty; img = (r2 / p.tiles_y) * p.tb;
+            } else {                                         // linear range of 128 pixels
+                const int m0 = mt * BLOCK_M;
+                img = m0 / hw;
+                const int rem = m0 - img * hw;
+                y0 = rem / p.W;
+                x0 = rem - y0 * p.W;
+            }
+            // __shfl_sync(.., 0) marks a value warp-uniform for ptxas, so the TMA operands stay in uniform registers
+            x0 = __shfl_sync(0xffffffffu, x0, 0); y0 = __shfl_sync(0xffffffffu, y0, 0); img = __shfl_sync(0xffffffffu, img, 0);
+            const int n0 = __shfl_sync(0xffffffffu, nt * p.block_n, 0);
+            int tap = kb0 / cblocks;
+            int cb = kb0 - tap * cblocks;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1u, 0x100u + stage);
+                __syncwarp();
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                tap = __shfl_sync(0xffffffffu, tap, 0); cb = __shfl_sync(0xffffffffu, cb, 0);
+                uint8_t* st = ring + (size_t)stage * stage_bytes;
+                if (p.dbg_flags & 1) {                       // diagnostics: no loads, the MMAs read whatever is there
+                    mbar_arrive_e(leader, &full[stage]);
+                } else if (BK == 32 && p.halo) {             // one halo fetch serves all 9 taps of this tile
+                    mbar_expect_tx_e(leader, &full[stage], (uint32_t)(PLANES * p.halo_tx_bytes));
+                    tma_load_4d_e(leader, st, &map_a, &full[stage], 0, x0 - 1, y0 - 1, img);
+                    if (SPLIT3) tma_load_4d_e(leader, st + p.halo_plane_bytes, &map_a, &full[stage], 0, x0 - 1, y0 - 1, img + p.B);
+                } else {
+                    const int c0 = cb * BK;
                     const int dy = (p.ksize == 3) ? tap / 3 : 0;
                     const int dx = (p.ksize == 3) ? tap - dy * 3 : 0;
-                    mbar_wait(&empty[stage], phase ^ 1u, 0x100u + stage);
-                    uint8_t* st = smem + (size_t)stage * stage_bytes;
-                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    mbar_expect_tx_e(leader, &full[stage], (uint32_t)stage_bytes);
                     if (p.tx) {      // tile-mode box {BK, tx, ty, tb} shifted by the tap; out-of-image = zero fill = SAME padding
-                        tma_load_4d(st, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img);
-                        if (SPLIT3) tma_load_4d(st + A_TILE, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img + p.B);
+                        tma_load_4d_e(leader, st, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img);
+                        if (SPLIT3) tma_load_4d_e(leader, st + A_TILE, &map_a, &full[stage], c0, x0 + dx - pad, y0 + dy - pad, img + p.B);
                     } else {
-                        tma_load_im2col_4d(st, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                        tma_load_im2col_4d_e(leader, st, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
                         if (SPLIT3)
-                            tma_load_im2col_4d(st + A_TILE, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
-                                               (uint16_t)dx, (uint16_t)dy);
+                            tma_load_im2col_4d_e(leader, st + A_TILE, &map_a, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
+                                                 (uint16_t)dx, (uint16_t)dy);
                     }
                     uint8_t* sbt = st + PLANES * A_TILE;
                     const int kcoord = tap * p.Cin + c0;
-                    tma_load_2d(sbt, &map_w, &full[stage], kcoord, n0);
-                    if (SPLIT3) tma_load_2d(sbt + b_tile, &map_w, &full[stage], kcoord, p.cout_pad + n0);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    tma_load_2d_e(leader, sbt, &map_w, &full[stage], kcoord, n0);
+                    if (SPLIT3) tma_load_2d_e(leader, sbt + b_tile, &map_w, &full[stage], kcoord, p.cout_pad + n0);
+                }
+                if (++cb == cblocks) { cb = 0; ++tap; }
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one lane) =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            SegIter it;
-            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-            int tile, kb0, kb1;
-            while (it.next(tile, kb0, kb1)) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        bool bres_ready = false;
+        const uint32_t ring_u32 = smem_u32(ring);
+        const uint32_t bres_u32 = smem_u32(smem);
+        SegIter it;
+        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        int tile, kb0, kb1;
+        while (it.next(tile, kb0, kb1)) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
+            __syncwarp();
+            tc_fence_after();
+            // __shfl_sync(.., 0) marks a value warp-uniform for ptxas: descriptors are then built in uniform registers
+            const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(acc * ACC_COLS), 0);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase, 0x300u + stage);
+                __syncwarp();
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[stage], phase, 0x300u + stage);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + A_TILE;
-                    const uint32_t b_hi = a_hi + PLANES * A_TILE;
-                    const uint32_t b_lo = b_hi + b_tile;
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                const uint32_t st = ring_u32 + (uint32_t)(stage * stage_bytes);
+                if (BK == 32 && p.halo) {
+                    if (!bres_ready) {
+                        if (!(p.dbg_flags & 1)) mbar_wait(bres, 0u, 0x310u);
+                        __syncwarp();
+                        tc_fence_after();
+                        bres_ready = true;
+                    }
+                    // A operand of tap (dy, dx) = the 8 x 16 window of the 10 x 18 halo tile starting at (dx, dy):
+                    // descriptor start shifted by whole 64-byte rows, 8-row groups one halo row (10 rows) apart.  The
+                    // swizzle is a function of the absolute shared-memory address (what TMA wrote), so no base offset.
+                    const uint32_t dh_hi = (uint32_t)make_kmajor_desc_ex(st, 64, 640, 0);
+                    const uint32_t dh_lo = (uint32_t)make_kmajor_desc_ex(st + (uint32_t)p.halo_plane_bytes, 64, 640, 0);
+                    const uint32_t dw_hi = (uint32_t)make_kmajor_desc(bres_u32, 64);
+                    const uint32_t dw_lo = (uint32_t)make_kmajor_desc(bres_u32 + (uint32_t)b_tile, 64);
+                    const uint32_t ha = (uint32_t)(make_kmajor_desc_ex(0, 64, 640, 0) >> 32);   // high words: constants
+                    const uint32_t hb = (uint32_t)(make_kmajor_desc(0, 64) >> 32);
+                    const uint32_t wstep = (uint32_t)(PLANES * b_tile) >> 4;
+                    if (!(p.dbg_flags & 2)) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t koff = k * 32;      // 16 bf16 = 32 bytes along K inside the swizzle row
-                        const uint64_t da_hi = make_kmajor_desc(a_hi + koff, ROW_BYTES);
-                        const uint64_t db_hi = make_kmajor_desc(b_hi + koff, ROW_BYTES);
-                        tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        if (SPLIT3) {
-                            const uint64_t da_lo = make_kmajor_desc(a_lo + koff, ROW_BYTES);
-                            const uint64_t db_lo = make_kmajor_desc(b_lo + koff, ROW_BYTES);
-                            tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-                            tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t a_off = (uint32_t)(((tap / 3) * 10 + (tap % 3)) * 64 + k * 32) >> 4;
+                                const uint32_t w_off = (uint32_t)tap * wstep + (uint32_t)(k * 2);
+                                tc_mma_f16_e(leader, d_tmem, dh_hi + a_off, ha, dw_hi + w_off, hb, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+                                if (SPLIT3) {
+                                    tc_mma_f16_e(leader, d_tmem, dh_hi + a_off, ha, dw_lo + w_off, hb, idesc, 1u);
+                                    tc_mma_f16_e(leader, d_tmem, dh_lo + a_off, ha, dw_hi + w_off, hb, idesc, 1u);
+                                }
+                            }
                         }
                     }
-                    tc_commit(&empty[stage]);              // smem slot reusable once these MMAs retire
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1u;
+                } else {
+                    const uint32_t da_hi = (uint32_t)make_kmajor_desc(st, ROW_BYTES);
+                    const uint32_t da_lo = (uint32_t)make_kmajor_desc(st + A_TILE, ROW_BYTES);
+                    const uint32_t db_hi = (uint32_t)make_kmajor_desc(st + PLANES * A_TILE, ROW_BYTES);
+                    const uint32_t db_lo = (uint32_t)make_kmajor_desc(st + PLANES * A_TILE + (uint32_t)b_tile, ROW_BYTES);
+                    const uint32_t hd = (uint32_t)(make_kmajor_desc(0, ROW_BYTES) >> 32);       // high word: constant
+                    if (!(p.dbg_flags & 2)) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t koff = (uint32_t)(k * 2);   // 16 bf16 = 32 bytes along K inside the swizzle row (>> 4)
+                            tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_hi + koff, hd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            if (SPLIT3) {
+                                tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc, 1u);
+                                tc_mma_f16_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc, 1u);
+                            }
+                        }
                     }
                 }
-                tc_commit(&tfull[acc]);                    // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                tc_commit_e(leader, &empty[stage]);                  // smem slot reusable once these MMAs retire
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
+            tc_commit_e(leader, &tfull[acc]);                        // accumulator complete -> epilogue
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
@@ -230,7 +303,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
             long long row = (long long)mt * BLOCK_M + q * 32 + lane;
-            bool pool_writer = false;
             size_t pool_row = 0;
             if (p.tx) {                                      // spatial tile: row r = (image bb, yy, xx) inside the block
                 const int r = q * 32 + lane;
@@ -238,7 +310,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int xx = r % p.tx, yy = (r / p.tx) % p.ty, bb = r / (p.tx * p.ty);
                 const int px = xt * p.tx + xx, py = (r2 % p.tiles_y) * p.ty + yy, pb = (r2 / p.tiles_y) * p.tb + bb;
                 row = ((long long)pb * p.H + py) * p.W + px;
-                pool_writer = ((xx | yy) & 1) == 0;
                 pool_row = ((size_t)pb * (p.H / 2) + py / 2) * (p.W / 2) + px / 2;
             }
             const bool row_ok = row < p.M;
@@ -282,7 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int nstaged = ncontrib < max_staged ? ncontrib : max_staged;
             const int rr = q * 32 + lane;
             auto stage_slot = [&](int buf, int hh) -> uint32_t {
-                return smem_u32(smem) + (uint32_t)(((buf * nstaged + hh) * BLOCK_M + rr) * 128);
+                return smem_u32(ring) + (uint32_t)(((buf * nstaged + hh) * BLOCK_M + rr) * 128);
             };
             auto stage_issue = [&](int c, int buf) {
                 for (int hh = 0; hh < nstaged; ++hh) {
@@ -295,21 +366,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
             if (nstaged > 0) stage_issue(0, 0);
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row, v);                    // chunk 0 in flight
             for (int c = 0; c < p.block_n; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
-                tmem_ld_wait();
-                if (!is_head) {                              // raw partial -> this CTA's slot
-                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                    continue;
-                }
+                tmem_ld_wait_dep(v);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (c + 32 < p.block_n) tmem_ld_32x32b_x32(t_row + (uint32_t)(c + 32), v);   // next chunk streams in behind the math
+                if (!is_head) {                              // raw partial -> this CTA's slot
+                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    continue;
+                }
                 if (nstaged > 0) {
                     const int buf = (c >> 5) & 1;
                     if (c + 32 < p.block_n) {
@@ -340,43 +410,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = f[j] * sb[c + j] + sb[256 + c + j];
-                    f[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
-                }
+                for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], sb[c + j], sb[256 + c + j]);   // folded BN (1, 0 when absent)
                 if (!row_ok) continue;
                 if (p.mode == EPI_PLANES) {
-                    auto store_planes = [&](bf16* dst_hi, bf16* dst_lo, size_t off) {
+                    if (p.out_hi) {                          // un-pooled tensor: leaky, hi/lo split, 64 B per plane
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]);
-                            const __nv_bfloat16 h1 = __float2bfloat16_rn(f[2 * j + 1]);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
-                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            const float t0 = f[2 * j], t1 = f[2 * j + 1];
+                            split_pack2(p.leaky ? fmaxf(t0, 0.1f * t0) : t0, p.leaky ? fmaxf(t1, 0.1f * t1) : t1, hi[j], lo[j]);
                         }
-                        uint4* dh = reinterpret_cast<uint4*>(dst_hi + off);
-                        uint4* dl = reinterpret_cast<uint4*>(dst_lo + off);
+                        const size_t off = (size_t)row * p.ldc + n0 + c;
+                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                             dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                         }
-                    };
-                    if (p.out_hi) store_planes(p.out_hi, p.out_lo, (size_t)row * p.ldc + n0 + c);
-                    if (p.tx) {
+                    }
+                    if (p.pool_hi) {
                         // fused 2x2/2 max-pool: the tile is a tx x ty spatial block, so the window partners of row r are
-                        // rows r^1 (x) and r^tx (y) = lanes of the same warp.  Max on the exact fp32 values, then split.
+                        // rows r^1 (x) and r^tx (y) = lanes of the same warp.  Exchange-and-halve: after the x step each
+                        // lane of a pair keeps 16 of the 32 columns, after the y step 8 -- the four lanes of a window end
+                        // with disjoint quarters and each writes 16 B per plane (no idle lanes, 24 shuffles instead of 64).
+                        // max runs on the exact fp32 BN outputs; leaky (monotone) is applied to the 8 survivors.
+                        const bool odd_x = (lane & 1) != 0, odd_y = (lane & p.tx) != 0;
+                        float a[16], m[8];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float m = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.tx));
+                        for (int j = 0; j < 16; ++j) {
+                            const float send = odd_x ? f[j] : f[j + 16];
+                            const float keep = odd_x ? f[j + 16] : f[j];
+                            a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
                         }
-                        if (pool_writer) store_planes(p.pool_hi, p.pool_lo, pool_row * (size_t)p.ldp + n0 + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float send = odd_y ? a[j] : a[j + 8];
+                            const float keep = odd_y ? a[j + 8] : a[j];
+                            const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tx));
+                            m[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) split_pack2(m[2 * j], m[2 * j + 1], hi[j], lo[j]);
+                        const size_t off = pool_row * (size_t)p.ldp + n0 + c + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+                        *reinterpret_cast<uint4*>(p.pool_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(p.pool_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 } else {  // EPI_F32: 128-bit stores when aligned, else masked scalar stores (N = 425, 125)
+                    if (p.leaky) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
+                    }
                     float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c;
                     if ((p.ldc & 3) == 0 && n0 + c + 32 <= p.N) {
                         float4* d4 = reinterpret_cast<float4*>(dst);
@@ -496,8 +581,19 @@ bool tc_conv_can_fuse_pool(int B, int H, int W) {
     return pool_tiling(B, H, W, &a, &b, &c);
 }
 
+int g_conv_dbg_flags = 0, g_conv_force_halo = 0;
+
+// Halo mode: 3x3, 32 input channels, a single N tile whose 9 weight taps fit next to the halo ring.
+bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int block_n, int split3) {
+    (void)B;
+    const int planes = split3 ? 2 : 1;
+    return ksize == 3 && Cin == 32 && cout_pad == block_n && (W % 8) == 0 && (H % 16) == 0 &&
+           9 * planes * block_n * 64 + 2 * planes * 12288 + 1024 + SB_BYTES + BAR_BYTES <= SMEM_LIMIT;
+}
+
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize, const bf16* wpack,
-                 int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws, int fuse_pool) {
+                 int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws, int fuse_pool,
+                 int halo) {
     if (load_driver_entry_points()) return -1;
     Y2_REQUIRE(ksize == 1 || ksize == 3, "tc conv: ksize must be 1 or 3 (got %d)", ksize);
     Y2_REQUIRE(Cin % 32 == 0, "tc conv: Cin must be a multiple of 32 (got %d)", Cin);
@@ -514,32 +610,59 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     p.M = (int)M; p.N = cout; p.Cin = Cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
     p.block_n = block_n;
     p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-    if (fuse_pool) {
+    if (fuse_pool && !halo) {
         Y2_REQUIRE(pool_tiling(B, H, W, &p.tx, &p.ty, &p.tb), "tc conv: no spatial tiling for the fused max-pool at B=%d H=%d W=%d", B, H, W);
         p.tiles_x = W / p.tx; p.tiles_y = H / p.ty;
         p.m_tiles = p.tiles_x * p.tiles_y * (B / p.tb);          // exact cover: same count, different pixel order
     }
+    if (halo) {
+        Y2_REQUIRE(halo == 1, "tc conv: halo mode %d invalid", halo);
+        Y2_REQUIRE(tc_conv_can_halo(B, H, W, Cin, ksize, cout_pad, block_n, split3), "tc conv: halo mode not applicable (B=%d H=%d W=%d Cin=%d k=%d N=%d)", B, H, W, Cin, ksize, block_n);
+        p.tx = 8; p.ty = 16; p.tb = 1;                           // 8 x 16 pixel blocks: one 8-row MMA group per pixel row
+        p.tiles_x = W / 8; p.tiles_y = H / 16;
+        p.m_tiles = p.tiles_x * p.tiles_y * B;
+        p.halo = halo;
+        p.halo_tx_bytes = 10 * 18 * 64;
+        p.halo_plane_bytes = 12288;                              // 1 KiB multiple: swizzle phase identical per plane
+        p.bres_bytes = 9 * (split3 ? 2 : 1) * block_n * 64;
+    }
+    p.dbg_flags = g_conv_dbg_flags;
     p.n_tiles = cout_pad / block_n;
-    p.kblocks_total = taps * (Cin / BK);
+    p.kblocks_total = halo ? 1 : taps * (Cin / BK);
     p.cout_pad = cout_pad;
     Y2_REQUIRE(sk_ws && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0, "tc conv: stream-K workspace missing/unaligned");
     p.sk_flags = static_cast<unsigned int*>(sk_ws);                         // [num_sms] (first 4 KiB)
     p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
     const int planes = split3 ? 2 : 1;
-    const int stage_bytes = planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
-    int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES) / stage_bytes;
+    const int stage_bytes = halo ? planes * p.halo_plane_bytes : planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
+    int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES - p.bres_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     Y2_REQUIRE(stages >= 2, "tc conv: tile does not fit shared memory");
     p.num_stages = stages;
-    L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES;
+    L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES + p.bres_bytes;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
     choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0),
                     (size_t)planes * cout_pad * taps * Cin * sizeof(bf16), &p.dp_tiles,
                     &p.sk_ctas, &L->grid);
+    if (halo) {                                                  // one k-block per tile: plain data-parallel waves
+        p.dp_tiles = p.m_tiles; p.sk_ctas = 0;
+        L->grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+        if (max_ctas > 0 && L->grid > max_ctas) L->grid = max_ctas;
+    }
     Y2_REQUIRE(L->grid <= 1024, "tc conv: grid too large for the flag page");
 
-    if (fuse_pool) {
+    if (halo) {
+        // halo map: (C, W, H, N=2B) bf16, TILE mode, box {32, 10, 18, 1}; out-of-image = zero fill = SAME padding
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {32u, 10u, 18u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encodeTiled(&L->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in_planes), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (halo activation) failed (%d) B=%d H=%d W=%d", (int)r, B, H, W);
+    } else if (fuse_pool) {
         // activation map for the fused max-pool layers: (C, W, H, N=2B) bf16, TILE mode, box {BK, tx, ty, tb}
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};

@@ -64,7 +64,13 @@ struct ConvParams {
     unsigned int epoch;      // set per launch
     unsigned long long* dbg; // optional [grid][4] globaltimer stamps: start, stream-K phase start, hand-off wait start, end
     long long ldc;           // output row pitch, elements
+    // halo mode (3x3, Cin = 32, one N tile): the M-tile is an 8 x 16 pixel block whose (8+2) x (16+2) input halo is
+    // fetched ONCE per tile (tile-mode TMA) and every tap's A operand is a shifted window of it; the packed weights of
+    // all 9 taps stay resident in shared memory (descriptor starts are whole-row shifts, 8-row group pitch = 10 rows).
+    int halo, halo_plane_bytes, halo_tx_bytes, bres_bytes;
+    int dbg_flags;           // diagnostics: 1 = skip TMA loads, 2 = skip MMAs
 };
+extern int g_conv_dbg_flags, g_conv_force_halo;
 
 // Hybrid schedule for `tiles` output tiles of `KB` k-blocks on `ctas` persistent CTAs (max_ctas > 0 caps it):
 // full waves of whole tiles run data-parallel; the last partial wave of r tiles is either one more
@@ -118,7 +124,9 @@ struct TcConvLaunch {
 // wpack: bf16 [2][cout_pad][ksize*ksize*Cin] (k = tap*Cin + c).  Returns 0 or <0 (error set).
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
                  const bf16* wpack, int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms,
-                 void* streamk_ws, int fuse_pool = 0);
+                 void* streamk_ws, int fuse_pool = 0, int halo = 0);
+// true when the layer can run in halo mode (see ConvParams::halo)
+bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int block_n, int split3);
 // true when (B, H, W) admits the spatial tiling the fused max-pool epilogue needs
 bool tc_conv_can_fuse_pool(int B, int H, int W);
 // bytes of the stream-K scratch (flags page + one partial tile per SM); must be zeroed once before first use

@@ -110,6 +110,44 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
         : "memory");
 }
 
+// ---- warp-converged variants: every lane of the warp executes the call, the lane with `leader` != 0 (= elect_one(),
+// evaluated once by the role) issues the operation.  Keeping the role loops converged lets the compiler hold addresses /
+// descriptors / coordinates in UNIFORM registers, which is what UTMALDG / UTCHMMA take; issuing from an `if (lane == 0)`
+// region instead costs a convergence "waterfall" (ELECT + 5 R2UR + branch) per instruction -- more than a
+// 128x64x16 MMA lasts.
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %2, 0;\n\t"
+                 "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n"
+                 ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint32_t leader, uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %1, 0;\n\t"
+                 "@pe mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t leader, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_e(uint32_t leader, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                              int c2, int c3) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %7, 0;\n\t"
+        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_e(uint32_t leader, void* dst, const CUtensorMap* m, uint64_t* bar, int c,
+                                                     int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %9, 0;\n\t"
+        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+        "r"(n), "h"(off_w), "h"(off_h), "r"(leader)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM / tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -137,6 +175,22 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// Descriptors travel as (lo, hi) 32-bit halves: hi (SBO / version / swizzle mode) is constant per operand kind and all
+// address arithmetic happens on lo = (addr >> 4) | LBO << 16 with 32-bit adds (uniform-datapath friendly).
+__device__ __forceinline__ void tc_mma_f16_e(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred pe, p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t leader, uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %1, 0;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                 ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -149,6 +203,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+// Wait for the outstanding tcgen05.ld of this thread; `r` is listed as in/out so that no use of the loaded registers
+// can be scheduled above the wait (needed when the load is issued ahead of its consumer).
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -197,6 +261,20 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused for swizzled K-major)
     d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;      // SBO
     d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
+    d |= layout << 61;
+    return d;
+}
+// Same, with an explicit 8-row-group pitch (SBO) and matrix base offset: used when the 128 rows of the operand are a
+// shifted window of a larger swizzled tile (start address not aligned to the swizzle atom, groups not 8 rows apart).
+__device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo_bytes,
+                                                        uint32_t base_offset) {
+    const uint64_t layout = (row_bytes == 128) ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7u) << 49;
     d |= layout << 61;
     return d;
 }

@@ -65,6 +65,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_e(uint32_t leader, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %6, 0;\n\t"
+        "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+        : "memory");
+}
 // MN-major operand: atoms of (row_bytes/2) channels, K rows of row_bytes; LBO = atom stride, SBO = 8-row group.
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t row_bytes, uint32_t atom_stride) {
     const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
@@ -95,7 +101,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint64_t* tfull = bars + 2 * S;
     uint64_t* tempty = bars + 2 * S + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp: uniform for the compiler
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_d); }
     if (warp == 1 && lane == 0) {
@@ -115,78 +121,86 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int hw = p.H * p.W;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            SegIter it;
-            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-            int tile, kb0, kb1;
-            while (it.next(tile, kb0, kb1)) {
-                const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-                const int atom0 = mt * p.apt;
-                const int valid_atoms = min(p.apt, p.total_atoms - atom0);
-                const uint32_t tx = 2u * (uint32_t)(valid_atoms * a_atom + b_plane);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const int p0 = kb * WG_KPIX;
-                    const int img = p0 / hw, rem = p0 - img * hw;
-                    const int y0 = rem / p.W, x0 = rem - y0 * p.W;
-                    mbar_wait(&empty[stage], phase ^ 1u, 0x600u + stage);
-                    uint8_t* st = smem + (size_t)stage * stage_bytes;
-                    mbar_expect_tx(&full[stage], tx);
-                    for (int a = 0; a < valid_atoms; ++a) {
-                        const int ga = atom0 + a;
-                        const int tap = ga / p.apc, c0 = (ga - tap * p.apc) * p.atom_ch;
-                        const int dy = (p.ksize == 3) ? tap / 3 : 0, dx = (p.ksize == 3) ? tap - dy * 3 : 0;
-                        tma_load_im2col_4d(st + a * a_atom, &map_x, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
-                        tma_load_im2col_4d(st + a_plane + a * a_atom, &map_x, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
-                                           (uint16_t)dx, (uint16_t)dy);
-                    }
-                    uint8_t* sb = st + 2 * a_plane;
-                    for (int j = 0; j < nb; ++j) {
-                        tma_load_3d(sb + j * b_atom, &map_d, &full[stage], nt * p.block_n + j * 64, p0, 0);
-                        tma_load_3d(sb + b_plane + j * b_atom, &map_d, &full[stage], nt * p.block_n + j * 64, p0, 1);
-                    }
-                    if (++stage == S) { stage = 0; phase ^= 1u; }
+        // TMA producer: whole warp converged (operands stay in uniform registers), the elected lane issues
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        SegIter it;
+        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        int tile, kb0, kb1;
+        while (it.next(tile, kb0, kb1)) {
+            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            const int atom0 = __shfl_sync(0xffffffffu, mt * p.apt, 0);
+            const int ncol0 = __shfl_sync(0xffffffffu, nt * p.block_n, 0);
+            const int valid_atoms = min(p.apt, p.total_atoms - atom0);
+            const uint32_t tx = 2u * (uint32_t)(valid_atoms * a_atom + b_plane);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int p0 = kb * WG_KPIX;
+                const int img = p0 / hw, rem = p0 - img * hw;
+                const int y0 = rem / p.W, x0 = rem - y0 * p.W;
+                mbar_wait(&empty[stage], phase ^ 1u, 0x600u + stage);
+                __syncwarp();
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx_e(leader, &full[stage], tx);
+                for (int a = 0; a < valid_atoms; ++a) {
+                    const int ga = atom0 + a;
+                    const int tap = ga / p.apc, c0 = (ga - tap * p.apc) * p.atom_ch;
+                    const int dy = (p.ksize == 3) ? tap / 3 : 0, dx = (p.ksize == 3) ? tap - dy * 3 : 0;
+                    tma_load_im2col_4d_e(leader, st + a * a_atom, &map_x, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                    tma_load_im2col_4d_e(leader, st + a_plane + a * a_atom, &map_x, &full[stage], c0, x0 - pad, y0 - pad, img + p.B,
+                                         (uint16_t)dx, (uint16_t)dy);
                 }
+                uint8_t* sb = st + 2 * a_plane;
+                for (int j = 0; j < nb; ++j) {
+                    tma_load_3d_e(leader, sb + j * b_atom, &map_d, &full[stage], ncol0 + j * 64, p0, 0);
+                    tma_load_3d_e(leader, sb + b_plane + j * b_atom, &map_d, &full[stage], ncol0 + j * 64, p0, 1);
+                }
+                if (++stage == S) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D = f32, A = B = bf16, both MN-major (bits 15, 16)
-            const uint32_t idesc = make_idesc_bf16(WG_M, (uint32_t)p.block_n) | (1u << 15) | (1u << 16);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            SegIter it;
-            it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-            int tile, kb0, kb1;
-            while (it.next(tile, kb0, kb1)) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x700u + acc);
+        // MMA issuer: whole warp converged, the elected lane issues.  D = f32, A = B = bf16, both MN-major (bits 15, 16)
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc = make_idesc_bf16(WG_M, (uint32_t)p.block_n) | (1u << 15) | (1u << 16);
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t ha = (uint32_t)(make_mnmajor_desc(0, a_row, a_atom) >> 32);      // high words: constants
+        const uint32_t hb = (uint32_t)(make_mnmajor_desc(0, 128, b_atom) >> 32);
+        const uint32_t la = (uint32_t)make_mnmajor_desc(0, a_row, a_atom);               // LBO field of the low words
+        const uint32_t lb = (uint32_t)make_mnmajor_desc(0, 128, b_atom);
+        const uint32_t a_kstep = (uint32_t)(16 * a_row) >> 4, b_kstep = (16u * 128u) >> 4;
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        SegIter it;
+        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        int tile, kb0, kb1;
+        while (it.next(tile, kb0, kb1)) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x700u + acc);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(acc * WG_ACC), 0);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase, 0x800u + stage);
+                __syncwarp();
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_ACC);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[stage], phase, 0x800u + stage);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + a_plane;
-                    const uint32_t b_hi = a_hi + 2 * a_plane;
-                    const uint32_t b_lo = b_hi + b_plane;
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                const uint32_t a_hi = smem_base + (uint32_t)(stage * stage_bytes);
+                const uint32_t da_hi = la + (a_hi >> 4), da_lo = la + ((a_hi + (uint32_t)a_plane) >> 4);
+                const uint32_t db_hi = lb + ((a_hi + 2u * (uint32_t)a_plane) >> 4);
+                const uint32_t db_lo = lb + ((a_hi + 2u * (uint32_t)a_plane + (uint32_t)b_plane) >> 4);
 #pragma unroll
-                    for (int k = 0; k < WG_KPIX / 16; ++k) {
-                        const uint64_t da_hi = make_mnmajor_desc(a_hi + k * 16 * a_row, a_row, a_atom);
-                        const uint64_t da_lo = make_mnmajor_desc(a_lo + k * 16 * a_row, a_row, a_atom);
-                        const uint64_t db_hi = make_mnmajor_desc(b_hi + k * 16 * 128, 128, b_atom);
-                        const uint64_t db_lo = make_mnmajor_desc(b_lo + k * 16 * 128, 128, b_atom);
-                        tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-                        tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                    }
-                    tc_commit(&empty[stage]);
-                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                for (int k = 0; k < WG_KPIX / 16; ++k) {
+                    const uint32_t ak = (uint32_t)k * a_kstep, bk = (uint32_t)k * b_kstep;
+                    tc_mma_f16_e(leader, d_tmem, da_hi + ak, ha, db_hi + bk, hb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc_mma_f16_e(leader, d_tmem, da_hi + ak, ha, db_lo + bk, hb, idesc, 1u);
+                    tc_mma_f16_e(leader, d_tmem, da_lo + ak, ha, db_hi + bk, hb, idesc, 1u);
                 }
-                tc_commit(&tfull[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                tc_commit_e(leader, &empty[stage]);
+                if (++stage == S) { stage = 0; phase ^= 1u; }
             }
+            tc_commit_e(leader, &tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
     } else if (warp >= WG_EPI0) {
         const int q = warp - WG_EPI0;
