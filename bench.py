@@ -360,7 +360,9 @@ def main():
     peaks, peak_kind = measured_peaks()
     # DRAM traffic of the 21 conv launches of one step, from the committed ncu --set full capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "conv_step_traffic_r1.json")
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "conv_step_traffic_*.json")))   # newest capture (tags sort by round)
+    tpath = tfiles[-1] if tfiles else os.path.join(ROOT, "profiles", "conv_step_traffic_r1.json")
     if os.path.exists(tpath) and (B, size, C) == (32, 416, 80):
         traffic = json.load(open(tpath)).get("traffic_bytes")
     imgs = B * world * args.steps
@@ -397,7 +399,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (21 tcgen05 conv launches per step, conv1..conv20 + final)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "profiles/conv_step_traffic_r1.json: dram__bytes_read+write summed over the 21 conv launches of one step (ncu --set full)" if traffic else None,
+                     "traffic_source": "profiles/" + os.path.basename(tpath) + ": dram__bytes_read+write summed over the 21 conv launches of one step (ncu --set full)" if traffic else None,
                      "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                      "algorithmic_flops_per_step": flops_tc, "kernel_ms_per_step": tc_ms,
                      "tensor_pipe_frac_incl_3x_split": (3.0 if args.precision == 0 else 1.0) * achieved / peak,

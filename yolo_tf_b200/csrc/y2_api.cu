@@ -346,6 +346,7 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
             p.out_lo = P.act[i] + M * L.d.cout;
             if (fuse && !L.d.passthrough) p.out_hi = p.out_lo = nullptr;   // the un-pooled tensor is never materialised
         }
+        if (tc_conv_bind_output(&T)) return -1;
         input = L.d.pool ? P.pooled[i] : P.act[i];
     }
     P.valid = true;
@@ -483,6 +484,7 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
         if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk, 0, halo)) break;
         T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
         T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
+        if (tc_conv_bind_output(&T)) break;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         unsigned long long* dbg = nullptr;
@@ -512,7 +514,9 @@ int y2_debug_set(int key, double value) {
     if (key == 0) g_sched_override = (int)value;
     else if (key == 1) g_sched_handoff_kb = value;
     else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
-    else if (key == 4) g_conv_force_halo = (int)value;      // y2_conv2d: halo mode (1|2) where applicable
+    else if (key == 4) g_conv_force_halo = (int)value;
+    else if (key == 6) g_conv_tma_store = (int)value;       // TMA-store epilogue (default 1)
+    else if (key == 5) g_conv_pdl = (int)value;             // programmatic dependent launch of the conv kernels (default 1)      // y2_conv2d: halo mode (1|2) where applicable
     else if (key == 2) { if (value != 0 && !g_dbg_host) g_dbg_host = new unsigned long long[1024 * 4]; if (value == 0) { delete[] g_dbg_host; g_dbg_host = nullptr; } }
     else return -1;
     return 0;

@@ -64,6 +64,24 @@ __device__ __forceinline__ void flag_wait(const unsigned int* f, unsigned int ep
     }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read(int pending) {     // pending in {0, 1}
+    if (pending == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // (x0, x1) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi); one packed convert per pair of values.
 __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);              // .x (low half) = x0
@@ -76,13 +94,14 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
 template <int BK, bool SPLIT3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const ConvParams p) {
+               const __grid_constant__ CUtensorMap map_o, const ConvParams p) {
     constexpr int ROW_BYTES = BK * 2;                       // 128 (SW128) or 64 (SW64)
     constexpr int A_TILE = BLOCK_M * ROW_BYTES;
     constexpr int PLANES = SPLIT3 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic)
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem = smem0 + p.stg_bytes;                    // [store staging | resident weights | ring | scale/bias | barriers]
 
     const int b_tile = p.block_n * ROW_BYTES;
     const int stage_bytes = p.halo ? PLANES * p.halo_plane_bytes : PLANES * (A_TILE + b_tile);
@@ -103,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
+        if (p.tma_store) tma_prefetch_desc(&map_o);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) {
@@ -121,6 +141,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the
+    // previous kernel in the stream; nothing below may start before that kernel's memory is visible.  The next
+    // kernel may be scheduled onto SMs as soon as this grid's CTAs retire (no-ops without the launch attribute).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int KB = p.kblocks_total;
     const long long sk_total = (long long)(p.m_tiles * p.n_tiles - p.dp_tiles) * KB;   // stream-K part
@@ -292,6 +317,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int et = threadIdx.x - EPI_WARP0 * 32;       // 0..127
         int acc = 0, sb_nt = -1;
         uint32_t acc_phase = 0;
+        uint32_t store_seq = 0;
+        const uint32_t stg_base = smem_u32(smem0) + (uint32_t)(q * p.store_bufs * 4096);
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
         SegIter it;
         it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
@@ -411,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], sb[c + j], sb[256 + c + j]);   // folded BN (1, 0 when absent)
-                if (!row_ok) continue;
+                if (!row_ok && !p.tma_store) continue;       // (the TMA store clips rows >= M itself; all lanes must take part)
                 if (p.mode == EPI_PLANES) {
                     if (p.out_hi) {                          // un-pooled tensor: leaky, hi/lo split, 64 B per plane
                         uint32_t hi[16], lo[16];
@@ -420,6 +447,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const float t0 = f[2 * j], t1 = f[2 * j + 1];
                             split_pack2(p.leaky ? fmaxf(t0, 0.1f * t0) : t0, p.leaky ? fmaxf(t1, 0.1f * t1) : t1, hi[j], lo[j]);
                         }
+                        if (p.tma_store) {
+                            // slab = [plane][32 rows][64 B], SWIZZLE_64B: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)
+                            const uint32_t slab = stg_base + (uint32_t)((store_seq % p.store_bufs) * 4096);
+                            if (lane == 0) bulk_wait_read(p.store_bufs - 1);   // the store that last read this slab is done
+                            __syncwarp();
+                            const uint32_t rowa = slab + (uint32_t)(lane * 64), sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                st_shared_v4(rowa + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                st_shared_v4(rowa + 2048u + ((j ^ sw) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_3d(&map_o, slab, n0 + c, mt * BLOCK_M + q * 32, 0);
+                                bulk_commit();
+                            }
+                            ++store_seq;
+                        } else {
                         const size_t off = (size_t)row * p.ldc + n0 + c;
                         uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
                         uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
@@ -427,6 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int j = 0; j < 4; ++j) {
                             dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                             dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
                         }
                     }
                     if (p.pool_hi) {
@@ -463,7 +510,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
                     }
                     float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c;
-                    if ((p.ldc & 3) == 0 && n0 + c + 32 <= p.N) {
+                    if (p.tma_store) {
+                        // slab = [32 rows][128 B], SWIZZLE_128B: 16-byte piece j of row r sits at j ^ (r & 7)
+                        const uint32_t slab = stg_base + (uint32_t)((store_seq % p.store_bufs) * 4096);
+                        if (lane == 0) bulk_wait_read(p.store_bufs - 1);
+                        __syncwarp();
+                        const uint32_t rowa = slab + (uint32_t)(lane * 128), sw = (uint32_t)(lane & 7);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(rowa + ((j ^ sw) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_o, slab, n0 + c, mt * BLOCK_M + q * 32);
+                            bulk_commit();
+                        }
+                        ++store_seq;
+                    } else if ((p.ldc & 3) == 0 && n0 + c + 32 <= p.N) {
                         float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -486,6 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (acc == 0) acc_phase ^= 1u;
         }
         if (p.dbg && et == 0) p.dbg[blockIdx.x * 4 + 3] = gtime_ns();
+        if (p.tma_store && lane == 0) bulk_wait_read(0);    // the slabs have been read out before the CTA (its smem) retires
     }
 
     tc_fence_before();
@@ -530,7 +595,18 @@ static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
         Y2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    kern<<<L.grid, NUM_THREADS, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.p);
+    if (g_conv_pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        Y2_CUDA(cudaLaunchKernelEx(&cfg, kern, L.map_a, L.map_w, L.map_o, L.p));
+    } else {
+        kern<<<L.grid, NUM_THREADS, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.map_o, L.p);
+    }
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -581,7 +657,39 @@ bool tc_conv_can_fuse_pool(int B, int H, int W) {
     return pool_tiling(B, H, W, &a, &b, &c);
 }
 
-int g_conv_dbg_flags = 0, g_conv_force_halo = 0;
+int tc_conv_bind_output(TcConvLaunch* L) {
+    ConvParams& p = L->p;
+    p.tma_store = 0;
+    if (p.store_bufs == 0 || p.tx != 0) return 0;
+    if (load_driver_entry_points()) return -1;
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (p.mode == EPI_F32) {
+        if (!p.out_f32 || (p.ldc & 3) != 0 || (reinterpret_cast<uintptr_t>(p.out_f32) & 15) != 0) return 0;
+        cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+        cuuint64_t strides[1] = {(cuuint64_t)p.ldc * 4};
+        cuuint32_t box[2] = {32, 32};
+        CUresult r = g_encodeTiled(&L->map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.out_f32, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 output) failed (%d) M=%d N=%d ldc=%lld", (int)r, p.M, p.N, p.ldc);
+        p.tma_store = 1;
+    } else {
+        if (!p.out_hi || !p.out_lo || p.out_lo <= p.out_hi || (p.ldc & 7) != 0 || (reinterpret_cast<uintptr_t>(p.out_hi) & 15) != 0 ||
+            (((p.out_lo - p.out_hi) * 2) & 15) != 0)
+            return 0;
+        cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.M, 2};
+        cuuint64_t strides[2] = {(cuuint64_t)p.ldc * 2, (cuuint64_t)(p.out_lo - p.out_hi) * 2};
+        cuuint32_t box[3] = {32, 32, 2};
+        CUresult r = g_encodeTiled(&L->map_o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.out_hi, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        Y2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (plane output) failed (%d) M=%d N=%d ldc=%lld", (int)r, p.M, p.N, p.ldc);
+        p.tma_store = 1;
+    }
+    return 0;
+}
+
+int g_conv_dbg_flags = 0, g_conv_force_halo = 0, g_conv_pdl = 1, g_conv_tma_store = 1;
 
 // Halo mode: 3x3, 32 input channels, a single N tile whose 9 weight taps fit next to the halo ring.
 bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int block_n, int split3) {
@@ -635,11 +743,19 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
     const int planes = split3 ? 2 : 1;
     const int stage_bytes = halo ? planes * p.halo_plane_bytes : planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
-    int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES - p.bres_bytes) / stage_bytes;
+    if (p.tx == 0 && g_conv_tma_store) {          // linear tiles: room for the TMA-store staging slabs (2 per warp if the ring keeps its depth)
+        const int avail = SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES;
+        int st0 = avail / stage_bytes; if (st0 > 8) st0 = 8;
+        int st2 = (avail - 32768) / stage_bytes; if (st2 > 8) st2 = 8;
+        int st1 = (avail - 16384) / stage_bytes; if (st1 > 8) st1 = 8;
+        p.store_bufs = (st2 == st0 || st2 >= 4) ? 2 : ((st1 == st0 || st1 >= 3) ? 1 : 0);
+        p.stg_bytes = p.store_bufs * 16384;
+    }
+    int stages = (SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES - p.bres_bytes - p.stg_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     Y2_REQUIRE(stages >= 2, "tc conv: tile does not fit shared memory");
     p.num_stages = stages;
-    L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES + p.bres_bytes;
+    L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES + p.bres_bytes + p.stg_bytes;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
     choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0),

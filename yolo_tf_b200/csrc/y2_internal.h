@@ -68,9 +68,14 @@ struct ConvParams {
     // fetched ONCE per tile (tile-mode TMA) and every tap's A operand is a shifted window of it; the packed weights of
     // all 9 taps stay resident in shared memory (descriptor starts are whole-row shifts, 8-row group pitch = 10 rows).
     int halo, halo_plane_bytes, halo_tx_bytes, bres_bytes;
+    // TMA-store epilogue (linear tiles): every epilogue warp stages its 32 rows x 32 columns in a private swizzled
+    // shared-memory slab and one lane writes it out with cp.async.bulk.tensor (full lines, off the LSU).  stg_bytes =
+    // 4 warps x store_bufs x 4 KiB at the start of dynamic shared memory; tma_store is set by tc_conv_bind_output.
+    int tma_store, store_bufs, stg_bytes;
     int dbg_flags;           // diagnostics: 1 = skip TMA loads, 2 = skip MMAs
 };
-extern int g_conv_dbg_flags, g_conv_force_halo;
+extern int g_conv_tma_store;   // 1 = TMA-store epilogue where the layout allows it
+extern int g_conv_dbg_flags, g_conv_force_halo, g_conv_pdl;   // g_conv_pdl: launch convs with programmatic stream serialization
 
 // Hybrid schedule for `tiles` output tiles of `KB` k-blocks on `ctas` persistent CTAs (max_ctas > 0 caps it):
 // full waves of whole tiles run data-parallel; the last partial wave of r tiles is either one more
@@ -116,6 +121,7 @@ static inline void choose_schedule(long long tiles, int KB, int num_sms, int max
 struct TcConvLaunch {
     CUtensorMap map_a;       // im2col map over the input planes (C, W, H, 2B)
     CUtensorMap map_w;       // tiled map over packed weights (K, 2*cout_pad)
+    CUtensorMap map_o;       // output map for the TMA-store epilogue (tc_conv_bind_output)
     ConvParams p;
     int grid, smem_bytes, block_k, split3;
 };
@@ -125,6 +131,9 @@ struct TcConvLaunch {
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
                  const bf16* wpack, int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms,
                  void* streamk_ws, int fuse_pool = 0, int halo = 0);
+// Call after the output pointers / pitch / mode of L->p are final: builds the output tensor map and enables the TMA-store
+// epilogue when the layout allows it (linear tiles, 16-byte pitches); otherwise the per-thread store path stays.
+int tc_conv_bind_output(TcConvLaunch* L);
 // true when the layer can run in halo mode (see ConvParams::halo)
 bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int block_n, int split3);
 // true when (B, H, W) admits the spatial tiling the fused max-pool epilogue needs

@@ -71,24 +71,26 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(RedArgs a) {
         }
         int flush = 0;
         if (active) {
-            for (size_t r = (size_t)blockIdx.x * rows_per_pass + rlane; r < a.rows; r += (size_t)gridDim.x * rows_per_pass) {
-                float zv[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};
-                if (MODE != 2) {
-                    if (c + 3 < a.C) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.C + c));
-                        zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
-                    } else {
-                        for (int j = 0; j < 4; ++j) if (c + j < a.C) zv[j] = __ldg(a.z + r * a.C + c + j);
-                    }
+            const bool zvec = c + 3 < a.C, gvec = zvec && (a.ldg & 3) == 0;
+            auto load_z = [&](size_t r, float (&zv)[4]) {
+                if (MODE == 2) return;
+                if (zvec) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.C + c));
+                    zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (c + j < a.C) zv[j] = __ldg(a.z + r * a.C + c + j);
                 }
-                if (MODE != 0) {
-                    if (c + 3 < a.C && (a.ldg & 3) == 0) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(a.g + r * a.ldg + c));
-                        gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w;
-                    } else {
-                        for (int j = 0; j < 4; ++j) if (c + j < a.C) gv[j] = __ldg(a.g + r * a.ldg + c + j);
-                    }
+            };
+            auto load_g = [&](size_t r, float (&gv)[4]) {
+                if (MODE == 0) return;
+                if (gvec) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(a.g + r * a.ldg + c));
+                    gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (c + j < a.C) gv[j] = __ldg(a.g + r * a.ldg + c + j);
                 }
+            };
+            auto accum = [&](const float (&zv)[4], const float (&gv)[4]) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (MODE == 0) { s1[j] += zv[j]; s2[j] += zv[j] * zv[j]; }
@@ -104,6 +106,31 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(RedArgs a) {
                     for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
                     flush = 0;
                 }
+            };
+            const size_t rstep = (size_t)gridDim.x * rows_per_pass;
+            size_t r = (size_t)blockIdx.x * rows_per_pass + rlane;
+            for (; r + 3 * rstep < a.rows; r += 4 * rstep) {  // four rows of loads in flight; same summation order as one by one
+                float zz[4][4], gg[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { zz[u][j] = 0.f; gg[u][j] = 0.f; }
+                    load_z(r + u * rstep, zz[u]);
+                    load_g(r + u * rstep, gg[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) accum(zz[u], gg[u]);
+            }
+            for (; r + rstep < a.rows; r += 2 * rstep) {
+                float z0[4] = {0, 0, 0, 0}, g0[4] = {0, 0, 0, 0}, z1[4] = {0, 0, 0, 0}, g1[4] = {0, 0, 0, 0};
+                load_z(r, z0); load_g(r, g0); load_z(r + rstep, z1); load_g(r + rstep, g1);
+                accum(z0, g0);
+                accum(z1, g1);
+            }
+            if (r < a.rows) {
+                float z0[4] = {0, 0, 0, 0}, g0[4] = {0, 0, 0, 0};
+                load_z(r, z0); load_g(r, g0);
+                accum(z0, g0);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
@@ -234,15 +261,17 @@ int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* d
 
 // ---------------------------------------------------------------------------------------------
 // bn apply (forward): y = leaky(z*scale + bias) -> planes.   4 channels per thread.
-__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
-                                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, size_t rows, int C, long long ldy) {
+// Thread -> fixed channel group (tid % c4) and row lane (tid / c4): per-channel parameters live in registers, the row loop
+// has no integer division and keeps two rows of loads in flight.  Requires c4 = C/4 to divide 256 (C <= 1024).
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
+                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, size_t rows, int C, long long ldy) {
     const int c4 = C / 4;
-    const size_t total = rows * (size_t)c4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / c4;
-        const int c = (int)(i - r * c4) * 4;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), bi = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const int c = (int)(threadIdx.x % c4) * 4;
+    const int rpb = 256 / c4;
+    const size_t rstep = (size_t)gridDim.x * rpb;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), bi = __ldg(reinterpret_cast<const float4*>(bias + c));
+    auto one = [&](size_t r, const float4& t) {
         float f[4] = {t.x * sc.x + bi.x, t.y * sc.y + bi.y, t.z * sc.z + bi.z, t.w * sc.w + bi.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
@@ -250,7 +279,15 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
         split4(f, &h, &l);
         *reinterpret_cast<uint2*>(y_hi + r * ldy + c) = h;
         *reinterpret_cast<uint2*>(y_lo + r * ldy + c) = l;
+    };
+    size_t r = (size_t)blockIdx.x * rpb + threadIdx.x / c4;
+    for (; r + rstep < rows; r += 2 * rstep) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(z + (r + rstep) * C + c));
+        one(r, t0);
+        one(r + rstep, t1);
     }
+    if (r < rows) one(r, __ldg(reinterpret_cast<const float4*>(z + r * C + c)));
 }
 static inline int ew_grid(size_t items) {
     size_t b = (items + 255) / 256;
@@ -260,54 +297,65 @@ static inline int ew_grid(size_t items) {
 }
 int bn_apply_launch(const float* z, const float* scale, const float* bias, bf16* y_hi, bf16* y_lo, size_t rows, int C,
                     long long ldy, cudaStream_t s) {
-    Y2_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "bn_apply: C and pitch must be multiples of 4");
-    bn_apply_kernel<<<ew_grid(rows * (size_t)(C / 4)), 256, 0, s>>>(z, scale, bias, y_hi, y_lo, rows, C, ldy);
+    Y2_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && 256 % (C / 4) == 0, "bn_apply: C/4 must divide 256 and the pitch be a multiple of 4");
+    bn_apply_kernel<<<ew_grid(rows * (size_t)(C / 4) / 2), 256, 0, s>>>(z, scale, bias, y_hi, y_lo, rows, C, ldy);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
 }
 
 // bn backward apply: dx = scale * (dz - m1 - zhat * m2) -> planes (operand of dgrad / wgrad)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ g, long long ldg,
-                                    const float* __restrict__ scale, const float* __restrict__ bias,
-                                    const float* __restrict__ mean, const float* __restrict__ inv,
-                                    const float* __restrict__ m1, const float* __restrict__ m2, bf16* __restrict__ dx_hi,
-                                    bf16* __restrict__ dx_lo, size_t rows, int C) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ g, long long ldg,
+                    const float* __restrict__ scale, const float* __restrict__ bias,
+                    const float* __restrict__ mean, const float* __restrict__ inv,
+                    const float* __restrict__ m1, const float* __restrict__ m2, bf16* __restrict__ dx_hi,
+                    bf16* __restrict__ dx_lo, size_t rows, int C) {
     const int c4 = C / 4;
-    const size_t total = rows * (size_t)c4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / c4;
-        const int c = (int)(i - r * c4) * 4;
-        const float4 zt = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
-        float gv[4];
-        if ((ldg & 3) == 0) {
-            const float4 gt = __ldg(reinterpret_cast<const float4*>(g + r * ldg + c));
-            gv[0] = gt.x; gv[1] = gt.y; gv[2] = gt.z; gv[3] = gt.w;
-        } else {
+    const int c = (int)(threadIdx.x % c4) * 4;
+    const int rpb = 256 / c4;
+    const size_t rstep = (size_t)gridDim.x * rpb;
+    float sc[4], bi[4], mu[4], iv[4], q1[4], q2[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gv[j] = __ldg(g + r * ldg + c + j);
-        }
-        const float zv[4] = {zt.x, zt.y, zt.z, zt.w};
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = __ldg(scale + c + j); bi[j] = __ldg(bias + c + j); mu[j] = __ldg(mean + c + j); iv[j] = __ldg(inv + c + j);
+        q1[j] = __ldg(m1 + c + j); q2[j] = __ldg(m2 + c + j);
+    }
+    const bool vec = (ldg & 3) == 0;
+    auto load_g = [&](size_t r) -> float4 {
+        if (vec) return __ldg(reinterpret_cast<const float4*>(g + r * ldg + c));
+        return make_float4(__ldg(g + r * ldg + c), __ldg(g + r * ldg + c + 1), __ldg(g + r * ldg + c + 2), __ldg(g + r * ldg + c + 3));
+    };
+    auto one = [&](size_t r, const float4& zt, const float4& gt) {
+        const float zv[4] = {zt.x, zt.y, zt.z, zt.w}, gv[4] = {gt.x, gt.y, gt.z, gt.w};
         float f[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float sc = __ldg(scale + c + j);
-            const float zb = zv[j] * sc + __ldg(bias + c + j);
+            const float zb = zv[j] * sc[j] + bi[j];
             const float dz = gv[j] * (zb >= 0.f ? 1.0f : 0.1f);
-            const float zh = (zv[j] - __ldg(mean + c + j)) * __ldg(inv + c + j);
-            f[j] = sc * (dz - __ldg(m1 + c + j) - zh * __ldg(m2 + c + j));
+            const float zh = (zv[j] - mu[j]) * iv[j];
+            f[j] = sc[j] * (dz - q1[j] - zh * q2[j]);
         }
         uint2 h, l;
         split4(f, &h, &l);
         *reinterpret_cast<uint2*>(dx_hi + r * C + c) = h;
         *reinterpret_cast<uint2*>(dx_lo + r * C + c) = l;
+    };
+    size_t r = (size_t)blockIdx.x * rpb + threadIdx.x / c4;
+    for (; r + rstep < rows; r += 2 * rstep) {
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(z + (r + rstep) * C + c));
+        const float4 g0 = load_g(r), g1 = load_g(r + rstep);
+        one(r, z0, g0);
+        one(r + rstep, z1, g1);
     }
+    if (r < rows) one(r, __ldg(reinterpret_cast<const float4*>(z + r * C + c)), load_g(r));
 }
 int bn_bwd_apply_launch(const float* z, const float* g, long long ldg, const float* scale, const float* bias,
                         const float* mean, const float* inv, const float* m1, const float* m2, bf16* dx_hi, bf16* dx_lo,
                         size_t rows, int C, cudaStream_t s) {
-    Y2_REQUIRE(C % 4 == 0, "bn_bwd_apply: C must be a multiple of 4");
-    bn_bwd_apply_kernel<<<ew_grid(rows * (size_t)(C / 4)), 256, 0, s>>>(z, g, ldg, scale, bias, mean, inv, m1, m2, dx_hi, dx_lo,
+    Y2_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "bn_bwd_apply: C/4 must divide 256");
+    bn_bwd_apply_kernel<<<ew_grid(rows * (size_t)(C / 4) / 2), 256, 0, s>>>(z, g, ldg, scale, bias, mean, inv, m1, m2, dx_hi, dx_lo,
                                                                        rows, C);
     Y2_CUDA(cudaGetLastError());
     note_launch();
@@ -340,12 +388,17 @@ int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, 
 __global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp, const bf16* __restrict__ y_hi,
                                    const bf16* __restrict__ y_lo, float* __restrict__ g, int B, int H, int W, int C) {
     const int Ho = H / 2, Wo = W / 2, c4 = C / 4;
-    const size_t total = (size_t)B * Ho * Wo * c4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % c4);
-        size_t t = i / c4;
-        const int xo = (int)(t % Wo);
-        t /= Wo;
+    // thread -> fixed channel group; windows walked with 32-bit index arithmetic (c4 divides 256 or is a multiple of it)
+    const unsigned windows = (unsigned)B * Ho * Wo;
+    const unsigned cpb = c4 < 256 ? c4 : 256;                // channel groups covered by one block
+    const unsigned wpb = 256 / cpb;                          // windows per block per pass
+    const unsigned cblocks = (c4 + cpb - 1) / cpb;           // blocks along the channel axis
+    const unsigned bx = blockIdx.x % cblocks, by = blockIdx.x / cblocks;
+    const int cv = (int)(bx * cpb + threadIdx.x % cpb);
+    const unsigned wstep = (gridDim.x / cblocks) * wpb;
+    for (unsigned w = by * wpb + threadIdx.x / cpb; w < windows && by < gridDim.x / cblocks; w += wstep) {
+        const int xo = (int)(w % Wo);
+        const unsigned t = w / Wo;
         const int yo = (int)(t % Ho);
         const int b = (int)(t / Ho);
         const size_t prow = ((size_t)b * Ho + yo) * Wo + xo;
@@ -384,7 +437,9 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp,
 int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
                        int C, cudaStream_t s) {
     Y2_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool_bwd: bad shape");
-    maxpool_bwd_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C);
+    Y2_REQUIRE(256 % (C / 4) == 0 || (C / 4) % 256 == 0, "maxpool_bwd: C/4 must divide 256 or be a multiple of it");
+    Y2_REQUIRE((size_t)B * (H / 2) * (W / 2) < (1ull << 31), "maxpool_bwd: too many windows");
+    maxpool_bwd_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)) / ((C / 4 + 255) / 256) * ((C / 4 + 255) / 256), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -233,17 +233,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 __syncwarp();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
-            // other contributors' partials: staged through the idle smem ring with cp.async, one chunk ahead
-            // (same scheme as the forward kernel: per-thread row slots, 16-byte pieces XOR-swizzled by row)
+            // Other contributors' partials: staged through the idle smem ring with cp.async in batches of `cap`
+            // contributors per 32-column chunk, one (chunk, batch) step ahead of the adds (per-thread row slots, 16-byte
+            // pieces XOR-swizzled by row).  A 1x1 layer at 104x104 has ONE output tile and 147 contributors: every
+            // batch keeps cap x 16 KiB in flight instead of one exposed L2 round trip per contributor.
             const int ncontrib = last_contrib - (int)blockIdx.x;
-            const int max_staged = (int)(((size_t)S * stage_bytes) / (2u * WG_M * 128u));
-            const int nstaged = ncontrib < max_staged ? ncontrib : max_staged;
+            const int cap = (int)(((size_t)S * stage_bytes) / (2u * WG_M * 128u));
+            const int nbatch = (ncontrib + cap - 1) / cap;
             auto stage_slot = [&](int buf, int hh) -> uint32_t {
-                return smem_u32(smem) + (uint32_t)(((buf * nstaged + hh) * WG_M + r) * 128);
+                return smem_u32(smem) + (uint32_t)(((buf * cap + hh) * WG_M + r) * 128);
             };
-            auto stage_issue = [&](int c, int buf) {
-                for (int hh = 0; hh < nstaged; ++hh) {
-                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + hh) * WG_M * p.block_n + (size_t)r * p.block_n + c;
+            auto stage_issue = [&](int c, int bt, int buf) {
+                const int h0 = bt * cap, cnt = min(cap, ncontrib - h0);
+                for (int hh = 0; hh < cnt; ++hh) {
+                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + h0 + hh) * WG_M * p.block_n + (size_t)r * p.block_n + c;
                     const uint32_t dst = stage_slot(buf, hh);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -251,7 +254,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            if (is_head && nstaged > 0) stage_issue(0, 0);
+            int step = 0;
+            if (is_head && nbatch > 0) stage_issue(0, 0, 0);
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
@@ -267,15 +271,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (nstaged > 0) {
-                    const int buf = (c >> 5) & 1;
-                    if (c + 32 < p.block_n) {
-                        stage_issue(c + 32, buf ^ 1);
+                for (int bt = 0; bt < nbatch; ++bt, ++step) {           // ascending contributor order: deterministic sum
+                    const int buf = step & 1;
+                    const bool more = (bt + 1 < nbatch) || (c + 32 < p.block_n);
+                    if (more) {
+                        if (bt + 1 < nbatch) stage_issue(c, bt + 1, buf ^ 1); else stage_issue(c + 32, 0, buf ^ 1);
                         asm volatile("cp.async.wait_group 1;" ::: "memory");
                     } else {
                         asm volatile("cp.async.wait_group 0;" ::: "memory");
                     }
-                    for (int hh = 0; hh < nstaged; ++hh) {
+                    const int cnt = min(cap, ncontrib - bt * cap);
+                    for (int hh = 0; hh < cnt; ++hh) {
                         const uint32_t src = stage_slot(buf, hh);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -285,14 +291,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                                          : "r"(src + (uint32_t)((j ^ (r & 7)) << 4)));
                             f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
                         }
-                    }
-                }
-                for (int h = blockIdx.x + 1 + nstaged; h <= last_contrib; ++h) {
-                    const float4* src = reinterpret_cast<const float4*>(p.sk_partial + (size_t)h * WG_M * p.block_n + (size_t)r * p.block_n + c);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = __ldcg(src + j);
-                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
                     }
                 }
                 if (!row_ok) continue;
@@ -373,6 +371,9 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     const int npad = dpitch;
     const int nt = (npad + 255) / 256;
     int bn = ((npad + nt - 1) / nt + 63) / 64 * 64;
+    // few output tiles and a huge K (1x1 layers): narrower N tiles give more tiles, i.e. fewer stream-K contributors per
+    // tile to add up in the hand-off (the MMAs of these layers are a few microseconds either way)
+    while (bn > 64 && (long long)p.m_tiles * ((npad + bn - 1) / bn) < 16) bn = (bn / 2 + 63) / 64 * 64;
     p.block_n = bn;
     p.n_tiles = (npad + bn - 1) / bn;
     p.kblocks_total = (int)((P + WG_KPIX - 1) / WG_KPIX);
