@@ -232,6 +232,14 @@ struct SegIter {
             cur = end = 0;
         }
     }
+    // K-aligned split: CTA i owns k-range (i / tiles) of tile (i % tiles) -- all CTAs sit at the same K phase of their
+    // tiles at the same time, so the operand slices the tiles share are fetched from HBM once and re-read from L2.
+    __device__ __forceinline__ void init_split(int tiles, int chunks, int KB_) {
+        dp_next = 0; dp_tiles = 0; stride = gridDim.x; KB = KB_;
+        const int t = (int)blockIdx.x % tiles, c = (int)blockIdx.x / tiles;
+        cur = (long long)t * KB + (long long)KB * c / chunks;
+        end = (long long)t * KB + (long long)KB * (c + 1) / chunks;
+    }
     __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
         if (dp_next < dp_tiles) {
             tile = dp_next; kb0 = 0; kb1 = KB; dp_next += stride;

@@ -31,6 +31,7 @@ struct WgradParams {
     int P, B, H, W, Cin, Cout, ksize;
     int atom_ch, apt, apc, total_atoms;       // channels per atom (64|32), atoms per tile, atoms per tap, taps*apc
     int m_tiles, n_tiles, block_n, kblocks_total, num_stages;
+    int split_tiles, split_chunks;   // K-aligned split (few tiles, huge K): grid = tiles x chunks, CTA i -> (tile i % tiles, k-range i / tiles)
     int dp_tiles, sk_ctas;
     float* dw;                                // [taps][Cin][Cout]
     float* sk_partial;
@@ -126,7 +127,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
         int tile, kb0, kb1;
         while (it.next(tile, kb0, kb1)) {
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
@@ -172,7 +173,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
         int tile, kb0, kb1;
         while (it.next(tile, kb0, kb1)) {
             mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x700u + acc);
@@ -210,7 +211,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint32_t acc_phase = 0;
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * WG_M * p.block_n + (size_t)r * p.block_n;
         SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
         int tile, kb0, kb1;
         while (it.next(tile, kb0, kb1)) {
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
@@ -221,15 +222,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int cch = row_ok ? (ga - tap * p.apc) * p.atom_ch + (r % p.atom_ch) : 0;
             float* drow = p.dw + ((size_t)tap * p.Cin + cch) * p.Cout;
             const bool is_head = (kb0 == 0);
-            int last_contrib = blockIdx.x;
+            // the other CTAs holding k-ranges of this tile: ids cfirst + j * cstride, j < ncontrib
+            int cfirst = blockIdx.x + 1, cstride = 1, ncontrib = 0;
             if (is_head && kb1 < KB) {
-                const long long tile_end = (long long)(tile - p.dp_tiles + 1) * KB;
-                while (last_contrib + 1 < p.sk_ctas && sk_total * (last_contrib + 1) / p.sk_ctas < tile_end) ++last_contrib;
+                if (p.split_chunks) {
+                    cfirst = blockIdx.x + p.split_tiles; cstride = p.split_tiles; ncontrib = p.split_chunks - 1;
+                } else {
+                    int last_contrib = blockIdx.x;
+                    const long long tile_end = (long long)(tile - p.dp_tiles + 1) * KB;
+                    while (last_contrib + 1 < p.sk_ctas && sk_total * (last_contrib + 1) / p.sk_ctas < tile_end) ++last_contrib;
+                    ncontrib = last_contrib - (int)blockIdx.x;
+                }
             }
             mbar_wait(&tfull[acc], acc_phase, 0xA00u + acc);
             tc_fence_after();
-            for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {
-                if (lane == 0) wg_flag_wait(p.sk_flags + h, p.epoch);
+            for (int j = 0; j < ncontrib; ++j) {
+                if (lane == 0) wg_flag_wait(p.sk_flags + cfirst + j * cstride, p.epoch);
                 __syncwarp();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
@@ -237,7 +245,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // contributors per 32-column chunk, one (chunk, batch) step ahead of the adds (per-thread row slots, 16-byte
             // pieces XOR-swizzled by row).  A 1x1 layer at 104x104 has ONE output tile and 147 contributors: every
             // batch keeps cap x 16 KiB in flight instead of one exposed L2 round trip per contributor.
-            const int ncontrib = last_contrib - (int)blockIdx.x;
             const int cap = (int)(((size_t)S * stage_bytes) / (2u * WG_M * 128u));
             const int nbatch = (ncontrib + cap - 1) / cap;
             auto stage_slot = [&](int buf, int hh) -> uint32_t {
@@ -246,7 +253,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             auto stage_issue = [&](int c, int bt, int buf) {
                 const int h0 = bt * cap, cnt = min(cap, ncontrib - h0);
                 for (int hh = 0; hh < cnt; ++hh) {
-                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + h0 + hh) * WG_M * p.block_n + (size_t)r * p.block_n + c;
+                    const float* src = p.sk_partial + (size_t)(cfirst + (h0 + hh) * cstride) * WG_M * p.block_n + (size_t)r * p.block_n + c;
                     const uint32_t dst = stage_slot(buf, hh);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -373,7 +380,7 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     int bn = ((npad + nt - 1) / nt + 63) / 64 * 64;
     // few output tiles and a huge K (1x1 layers): narrower N tiles give more tiles, i.e. fewer stream-K contributors per
     // tile to add up in the hand-off (the MMAs of these layers are a few microseconds either way)
-    while (bn > 64 && (long long)p.m_tiles * ((npad + bn - 1) / bn) < 16) bn = (bn / 2 + 63) / 64 * 64;
+    while (ksize == 1 && bn > 64 && (long long)p.m_tiles * ((npad + bn - 1) / bn) < 16) bn = (bn / 2 + 63) / 64 * 64;
     p.block_n = bn;
     p.n_tiles = (npad + bn - 1) / bn;
     p.kblocks_total = (int)((P + WG_KPIX - 1) / WG_KPIX);
@@ -387,6 +394,18 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     p.num_stages = stages;
     L.smem_bytes = stages * stage_bytes + 1024 + 256;
     choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, bn / 256.0, 0, &p.dp_tiles, &p.sk_ctas, &L.grid);
+    {
+        // Few tiles, huge K (the early layers: 3..36 tiles, 10^4 k-blocks): K-aligned split instead of tile-major
+        // stream-K.  Tile-major ranges make every tile stream dx (and its taps of x) from HBM on its own -- conv2's
+        // wgrad moved 3.5 GB for 0.53 GB of operands; with all CTAs at the same K phase the re-reads hit L2.
+        const int tiles = p.m_tiles * p.n_tiles;
+        if (max_ctas == 0 && g_sched_override == 0 && tiles * 2 <= num_sms && p.kblocks_total >= 8 * (num_sms / tiles)) {
+            p.split_tiles = tiles;
+            p.split_chunks = num_sms / tiles;
+            p.dp_tiles = 0; p.sk_ctas = 0;
+            L.grid = tiles * p.split_chunks;
+        }
+    }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(2 * B)};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
