@@ -236,11 +236,73 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
             mbar_wait(&tfull[acc], acc_phase, 0xA00u + acc);
             tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
+            if (p.split_chunks) {
+                // K-aligned split: cooperative hand-off.  EVERY CTA of the tile publishes its raw partial, waits for the
+                // others, then reduces its own 1/chunks slice of the tile over all partials in chunk order (fixed order =
+                // deterministic) and writes that slice of dW.  The adds of a tile are spread over all its CTAs instead of
+                // serialised on one (conv3's single 128x64 tile has 148 partials).
+                for (int c = 0; c < p.block_n; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+                    tmem_ld_wait();
+                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) wg_flag_set(p.sk_flags + blockIdx.x, p.epoch);
+                const int tile_id = (int)blockIdx.x % p.split_tiles, my_chunk = (int)blockIdx.x / p.split_tiles;
+                for (int j = et; j < p.split_chunks; j += 128)
+                    if (j != my_chunk) wg_flag_wait(p.sk_flags + tile_id + j * p.split_tiles, p.epoch);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int bn4 = p.block_n / 4;
+                const int e4 = WG_M * bn4;                                 // float4 elements of the tile
+                const int lo = (int)((long long)e4 * my_chunk / p.split_chunks), hi = (int)((long long)e4 * (my_chunk + 1) / p.split_chunks);
+                const size_t slot = (size_t)WG_M * p.block_n;
+                const float* base = p.sk_partial + (size_t)tile_id * slot;
+                const size_t jstride = (size_t)p.split_tiles * slot;
+                for (int e = lo + et; e < hi; e += 128) {
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int j = 0;
+                    for (; j + 8 <= p.split_chunks; j += 8) {
+                        float4 t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(j + u) * jstride) + e);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { sum.x += t[u].x; sum.y += t[u].y; sum.z += t[u].z; sum.w += t[u].w; }
+                    }
+                    for (; j < p.split_chunks; ++j) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * jstride) + e);
+                        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+                    }
+                    const int rr = e / bn4, col = (e - rr * bn4) * 4;
+                    const int ga2 = mt * p.apt + rr / p.atom_ch;
+                    if (ga2 >= p.total_atoms) continue;
+                    const int tap2 = ga2 / p.apc;
+                    const int cch2 = (ga2 - tap2 * p.apc) * p.atom_ch + (rr % p.atom_ch);
+                    float* d = p.dw + ((size_t)tap2 * p.Cin + cch2) * p.Cout + n0 + col;
+                    if ((p.Cout & 3) == 0 && n0 + col + 4 <= p.Cout) {
+                        *reinterpret_cast<float4*>(d) = sum;
+                    } else {
+                        const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+                        for (int u = 0; u < 4; ++u) if (n0 + col + u < p.Cout) d[u] = sv[u];
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+                continue;
+            }
             for (int j = 0; j < ncontrib; ++j) {
                 if (lane == 0) wg_flag_wait(p.sk_flags + cfirst + j * cstride, p.epoch);
                 __syncwarp();
             }
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
             // Other contributors' partials: staged through the idle smem ring with cp.async in batches of `cap`
             // contributors per 32-column chunk, one (chunk, batch) step ahead of the adds (per-thread row slots, 16-byte
             // pieces XOR-swizzled by row).  A 1x1 layer at 104x104 has ONE output tile and 147 contributors: every
