@@ -16,7 +16,7 @@ static inline int red_blocks(size_t rows, int cols) {
     // each block strides over rows; enough blocks to fill the GPU, few enough to keep the finish cheap
     size_t work = rows * (size_t)((cols + 3) / 4);
     size_t b = (work + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
-    if (b > 148 * 4) b = 148 * 4;
+    if (b > 148 * 2) b = 148 * 2;      // one resident wave of the widest variant (2 blocks / SM); halves the finish traffic
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -158,21 +158,35 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(RedArgs a) {
 }
 
 // ---- finish kernels: a block owns 32 channels (lane = channel: coalesced 256-byte rows of the partial matrix); its
-// 8 warps sum interleaved subsets of the per-block partials, then warp 0 combines them in fixed order (deterministic).
-static constexpr int FIN_THREADS = 256;
+// 32 warps sum interleaved subsets of the per-block partials, then warp 0 combines them in fixed order (deterministic).
+static constexpr int FIN_THREADS = 1024;
+static constexpr int FIN_WARPS = FIN_THREADS / 32;
 __device__ __forceinline__ bool finish_sums(const double* __restrict__ partial, int nblocks, int C, double* s1, double* s2) {
-    __shared__ double sm[2][8][32];
+    __shared__ double sm[2][FIN_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     double a1 = 0, a2 = 0;
-    if (c < C)
-        for (int b = warp; b < nblocks; b += 8) { a1 += partial[((size_t)b * 2) * C + c]; a2 += partial[((size_t)b * 2 + 1) * C + c]; }
+    if (c < C) {
+        // this warp's partial blocks: warp, warp + 32, ... ; four loads in flight, combined in a fixed order
+        int b = warp;
+        for (; b + 3 * FIN_WARPS < nblocks; b += 4 * FIN_WARPS) {
+            double u1[4], u2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                u1[k] = partial[((size_t)(b + k * FIN_WARPS) * 2) * C + c];
+                u2[k] = partial[((size_t)(b + k * FIN_WARPS) * 2 + 1) * C + c];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a1 += u1[k]; a2 += u2[k]; }
+        }
+        for (; b < nblocks; b += FIN_WARPS) { a1 += partial[((size_t)b * 2) * C + c]; a2 += partial[((size_t)b * 2 + 1) * C + c]; }
+    }
     sm[0][warp][lane] = a1; sm[1][warp][lane] = a2;
     __syncthreads();
     if (warp != 0 || c >= C) return false;
     double t1 = 0, t2 = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { t1 += sm[0][w][lane]; t2 += sm[1][w][lane]; }
+    for (int w = 0; w < FIN_WARPS; ++w) { t1 += sm[0][w][lane]; t2 += sm[1][w][lane]; }
     *s1 = t1; *s2 = t2;
     return true;
 }
