@@ -22,7 +22,9 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("b,hw,cin,k,cout,max_ctas", [
     (2, 13, 512, 3, 256, 0), (1, 32, 32, 3, 64, 0), (2, 26, 64, 3, 128, 0), (3, 13, 1024, 1, 425, 0),
-    (1, 13, 3072, 3, 1024, 0), (2, 26, 128, 1, 64, 0), (2, 13, 512, 3, 256, -37), (4, 52, 128, 3, 256, 0)])
+    (1, 13, 3072, 3, 1024, 0), (2, 26, 128, 1, 64, 0), (2, 13, 512, 3, 256, -37), (4, 52, 128, 3, 256, 0),
+    # K-aligned split + cooperative hand-off: 1 tile x 148 k-ranges, 5 tiles x 29, 3 tiles x 49 (tap-packed Cin = 32)
+    (8, 104, 128, 1, 64, 0), (4, 104, 64, 3, 128, 0), (2, 208, 32, 3, 64, 0)])
 def test_wgrad_kernel_vs_fp64(cuda, b, hw, cin, k, cout, max_ctas):
     import torch
     import torch.nn.functional as F

@@ -65,8 +65,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banner / debug lines off stdout
         dist.init_process_group("nccl", device_id=dev)
     Bn, size, C = args.batch, args.size, args.classes
     params = B.synthetic_checkpoint(C, 5)
