@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--classes", type=int, default=20)
+    ap.add_argument("--timeline", default="", help="write a kernel timeline summary (torch.profiler / CUPTI) of 2 steps to this JSON")
     args = ap.parse_args()
     from yolo_tf_b200 import _lib, variables
     from yolo_tf_b200.model.yolo2 import Builder
@@ -88,6 +89,9 @@ def main():
     _lib.check(_lib.lib().y2_check_async_errors())
     if world > 1:
         dist.barrier()
+    if args.timeline:
+        timeline(step, args.timeline)
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.lib().y2_launch_count()
     e0.record()
@@ -125,6 +129,45 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def timeline(step, path):
+    """Kernel timeline of 2 training steps: busy time per kernel, idle time between consecutive kernels."""
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+    ks = sorted([(e.time_range.start, e.time_range.end, e.name) for e in ev if "emcpy" not in e.name and "emset" not in e.name])
+    span = ks[-1][1] - ks[0][0]
+    busy, agg, gaps = 0.0, {}, []
+    for i, (a, b, n) in enumerate(ks):
+        busy += b - a
+        key = n.split("(")[0].replace("void ", "").replace("y2::", "")[:48]
+        agg.setdefault(key, [0, 0.0])
+        agg[key][0] += 1
+        agg[key][1] += b - a
+        if i + 1 < len(ks):
+            g = ks[i + 1][0] - b
+            gaps.append((g, key, ks[i + 1][2].split("(")[0].replace("void ", "").replace("y2::", "")[:48]))
+    gapsum = sum(g for g, _, _ in gaps if g > 0)
+    by_pair = {}
+    for g, a, b in gaps:
+        if g > 0:
+            by_pair.setdefault(a + " -> " + b, [0, 0.0])
+            by_pair[a + " -> " + b][0] += 1
+            by_pair[a + " -> " + b][1] += g
+    out = {"steps": 2, "kernels": len(ks), "span_us": span, "busy_us": busy, "idle_us": gapsum,
+           "per_kernel_us": {k: {"n": v[0], "us": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+           "idle_by_pair_us": {k: {"n": v[0], "us": v[1]} for k, v in sorted(by_pair.items(), key=lambda kv: -kv[1][1])[:25]}}
+    json.dump(out, open(path, "w"), indent=1)
+    print(json.dumps({k: out[k] for k in ("kernels", "span_us", "busy_us", "idle_us")}))
+    for k, v in list(out["per_kernel_us"].items())[:14]:
+        print("%-50s %4d %10.1f" % (k, v["n"], v["us"]))
+    print("-- idle between:")
+    for k, v in list(out["idle_by_pair_us"].items())[:14]:
+        print("%-100s %4d %10.1f" % (k, v["n"], v["us"]))
 
 
 if __name__ == "__main__":

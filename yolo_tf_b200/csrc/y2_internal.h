@@ -175,6 +175,12 @@ int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* d
 int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, size_t rows, int C, int Cpad, cudaStream_t s);
 int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
                        int C, cudaStream_t s);
+// pool layers without passthrough: forward z -> pooled planes; backward z + pooled gradient -> dgamma/dbeta + dx planes
+int bn_apply_pool_launch(const float* z, const float* scale, const float* bias, bf16* p_hi, bf16* p_lo, int B, int H, int W, int C,
+                         cudaStream_t s);
+int bn_bwd_pool_launch(const float* z, const float* gp, long long ldgp, int B, int H, int W, int C, const float* scale, const float* bias,
+                       const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1, float* m2, bf16* dx_hi,
+                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s);
 int reorg_bwd_add_launch(const float* gr, long long ldr, float* g, int B, int H, int W, int C, cudaStream_t s);
 int pack_dgrad_weights_launch(const float* w_hwio, bf16* out, int ksize, int cin, int cout, int cin_pad, int cout_pad,
                               cudaStream_t s);

@@ -459,6 +459,218 @@ int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pool layers without a passthrough (conv0, conv1, conv4, conv7): the un-pooled activation and its gradient are never
+// materialised.  Everything a 2x2 window needs is a function of the stored raw conv output z: y = leaky(z*scale+bias),
+// rounded to the split-plane value hi+lo the inference path would have stored, first maximum in row-major window order
+// (strict >) wins -- forward writes the winner's planes, backward routes the pooled gradient to the same pixel.
+// One thread = one window x 4 channels; thread -> fixed channel group, 32-bit window arithmetic.
+struct PoolWin {
+    float z[4][4];      // raw conv output of the 4 window pixels
+    float yb[4][4];     // z*scale + bias (sign decides the leaky slope)
+    uint32_t hi[4][2], lo[4][2];   // planes of y (2 packed words = 4 channels)
+    int best[4];        // winning pixel per channel
+    float zw[4], ybw[4];   // z and z*scale+bias of the winner
+    size_t off[4];      // element offsets of the 4 pixels (row pitch C)
+};
+__device__ __forceinline__ void pool_window_load(PoolWin& w, const float* __restrict__ z, const float (&sc)[4], const float (&bi)[4],
+                                                 int b, int yo, int xo, int H, int W, int C, int c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        w.off[q] = (((size_t)b * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C + c;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(z + w.off[q]));
+        w.z[q][0] = t.x; w.z[q][1] = t.y; w.z[q][2] = t.z; w.z[q][3] = t.w;
+    }
+    float v[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w.yb[q][j] = w.z[q][j] * sc[j] + bi[j];
+            y[j] = fmaxf(w.yb[q][j], 0.1f * w.yb[q][j]);
+        }
+        uint2 h, l;
+        split4(y, &h, &l);
+        w.hi[q][0] = h.x; w.hi[q][1] = h.y; w.lo[q][0] = l.x; w.lo[q][1] = l.y;
+        v[q][0] = bf16lo(h.x) + bf16lo(l.x); v[q][1] = bf16hi(h.x) + bf16hi(l.x);
+        v[q][2] = bf16lo(h.y) + bf16lo(l.y); v[q][3] = bf16hi(h.y) + bf16hi(l.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int best = 0;
+        float bv = v[0][j], bz = w.z[0][j], byb = w.yb[0][j];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            const bool gt = v[q][j] > bv;
+            bv = gt ? v[q][j] : bv; bz = gt ? w.z[q][j] : bz; byb = gt ? w.yb[q][j] : byb; best = gt ? q : best;
+        }
+        w.best[j] = best; w.zw[j] = bz; w.ybw[j] = byb;
+    }
+}
+struct PoolIdx {
+    unsigned windows, wstep, w0;
+    int c, Ho, Wo;
+};
+__device__ __forceinline__ PoolIdx pool_index(int B, int H, int W, int C) {
+    PoolIdx ix;
+    const int c4 = C / 4;
+    ix.Ho = H / 2; ix.Wo = W / 2;
+    ix.windows = (unsigned)B * ix.Ho * ix.Wo;
+    ix.c = (int)(threadIdx.x % c4) * 4;
+    const unsigned wpb = 256 / c4;
+    ix.wstep = gridDim.x * wpb;
+    ix.w0 = blockIdx.x * wpb + threadIdx.x / c4;
+    return ix;
+}
+
+// forward: z -> pooled planes
+__global__ void __launch_bounds__(256)
+bn_apply_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
+                     bf16* __restrict__ p_hi, bf16* __restrict__ p_lo, int B, int H, int W, int C) {
+    const PoolIdx ix = pool_index(B, H, W, C);
+    float sc[4], bi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sc[j] = __ldg(scale + ix.c + j); bi[j] = __ldg(bias + ix.c + j); }
+    for (unsigned w = ix.w0; w < ix.windows; w += ix.wstep) {
+        const int xo = (int)(w % ix.Wo);
+        const unsigned t = w / ix.Wo;
+        const int yo = (int)(t % ix.Ho), b = (int)(t / ix.Ho);
+        PoolWin pw;
+        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c);
+        uint32_t oh[2], ol[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int qa = pw.best[2 * k], qb = pw.best[2 * k + 1];
+            uint32_t ha = 0, hb = 0, la = 0, lb = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q == qa) { ha = pw.hi[q][k] & 0xFFFFu; la = pw.lo[q][k] & 0xFFFFu; }
+                if (q == qb) { hb = pw.hi[q][k] & 0xFFFF0000u; lb = pw.lo[q][k] & 0xFFFF0000u; }
+            }
+            oh[k] = ha | hb; ol[k] = la | lb;
+        }
+        const size_t po = (size_t)w * C + ix.c;
+        *reinterpret_cast<uint2*>(p_hi + po) = make_uint2(oh[0], oh[1]);
+        *reinterpret_cast<uint2*>(p_lo + po) = make_uint2(ol[0], ol[1]);
+    }
+}
+int bn_apply_pool_launch(const float* z, const float* scale, const float* bias, bf16* p_hi, bf16* p_lo, int B, int H, int W, int C,
+                         cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0 && H % 2 == 0 && W % 2 == 0, "bn_apply_pool: bad shape");
+    Y2_REQUIRE((size_t)B * (H / 2) * (W / 2) < (1ull << 31), "bn_apply_pool: too many windows");
+    bn_apply_pool_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(z, scale, bias, p_hi, p_lo, B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// backward: APPLY = false -> per-block partial sums of dz and dz*zhat (only the winning pixel of a window has dz != 0);
+//           APPLY = true  -> dx = scale * (dz - m1 - zhat * m2) for all 4 pixels -> planes.   gp = pooled gradient, pitch ldgp.
+//           gy_out (optional, tests): the un-pooled dL/dy this layer would have received.
+template <bool APPLY>
+__global__ void __launch_bounds__(256)
+bn_bwd_pool_kernel(const float* __restrict__ z, const float* __restrict__ gp, long long ldgp, const float* __restrict__ scale,
+                   const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ inv,
+                   const float* __restrict__ m1, const float* __restrict__ m2, bf16* __restrict__ dx_hi, bf16* __restrict__ dx_lo,
+                   double* __restrict__ partial, float* __restrict__ gy_out, int B, int H, int W, int C) {
+    const PoolIdx ix = pool_index(B, H, W, C);
+    const int c4 = C / 4;
+    float sc[4], bi[4], mu[4], iv[4], q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = __ldg(scale + ix.c + j); bi[j] = __ldg(bias + ix.c + j); mu[j] = __ldg(mean + ix.c + j); iv[j] = __ldg(inv + ix.c + j);
+        if (APPLY) { q1[j] = __ldg(m1 + ix.c + j); q2[j] = __ldg(m2 + ix.c + j); }
+    }
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+    int flush = 0;
+    for (unsigned w = ix.w0; w < ix.windows; w += ix.wstep) {
+        const int xo = (int)(w % ix.Wo);
+        const unsigned t = w / ix.Wo;
+        const int yo = (int)(t % ix.Ho), b = (int)(t / ix.Ho);
+        float g[4];
+        if ((ldgp & 3) == 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(gp + (size_t)w * ldgp + ix.c));
+            g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = __ldg(gp + (size_t)w * ldgp + ix.c + j);
+        }
+        PoolWin pw;
+        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c);
+        if (!APPLY) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dz = g[j] * (pw.ybw[j] >= 0.f ? 1.0f : 0.1f);
+                s1[j] += dz; s2[j] += dz * ((pw.zw[j] - mu[j]) * iv[j]);
+            }
+            if (++flush == 16) {                      // the same fp32 run length (64 pixels) as the dense reduction
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+                flush = 0;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float f[4], gq[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    gq[j] = (q == pw.best[j]) ? g[j] : 0.f;
+                    const float dz = gq[j] * (pw.yb[q][j] >= 0.f ? 1.0f : 0.1f);
+                    const float zh = (pw.z[q][j] - mu[j]) * iv[j];
+                    f[j] = sc[j] * (dz - q1[j] - zh * q2[j]);
+                }
+                uint2 h, l;
+                split4(f, &h, &l);
+                *reinterpret_cast<uint2*>(dx_hi + pw.off[q]) = h;
+                *reinterpret_cast<uint2*>(dx_lo + pw.off[q]) = l;
+                if (gy_out) *reinterpret_cast<float4*>(gy_out + pw.off[q]) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+            }
+        }
+    }
+    if (!APPLY) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
+        __shared__ double sm1[256][4], sm2[256][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sm1[threadIdx.x][j] = d1[j]; sm2[threadIdx.x][j] = d2[j]; }
+        __syncthreads();
+        if ((int)threadIdx.x < c4) {
+            double t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+            for (int rl = 0; rl < 256 / c4; ++rl)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { t1[j] += sm1[rl * c4 + threadIdx.x][j]; t2[j] += sm2[rl * c4 + threadIdx.x][j]; }
+            const int cc = (int)threadIdx.x * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                partial[((size_t)blockIdx.x * 2 + 0) * C + cc + j] = t1[j];
+                partial[((size_t)blockIdx.x * 2 + 1) * C + cc + j] = t2[j];
+            }
+        }
+    }
+}
+int bn_bwd_pool_launch(const float* z, const float* gp, long long ldgp, int B, int H, int W, int C, const float* scale, const float* bias,
+                       const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1, float* m2, bf16* dx_hi,
+                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s) {
+    Y2_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0 && H % 2 == 0 && W % 2 == 0 && C <= 1024, "bn_bwd_pool: bad shape");
+    const size_t windows = (size_t)B * (H / 2) * (W / 2);
+    Y2_REQUIRE(windows < (1ull << 31), "bn_bwd_pool: too many windows");
+    int nb = red_blocks(windows * 4, C);
+    bn_bwd_pool_kernel<false><<<nb, 256, 0, s>>>(z, gp, ldgp, scale, bias, mean, inv, nullptr, nullptr, nullptr, nullptr, partial, nullptr,
+                                                  B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    bn_bwd_finish_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(partial, nb, C, 1.0 / (double)(windows * 4), dgamma, dbeta, m1, m2);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    bn_bwd_pool_kernel<true><<<ew_grid(windows * (size_t)(C / 4)), 256, 0, s>>>(z, gp, ldgp, scale, bias, mean, inv, m1, m2, dx_hi, dx_lo,
+                                                                               nullptr, gy_out, B, H, W, C);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
 // reorg backward (accumulating): g[b, 2y+dy, 2x+dx, c] += gr[b, y, x, (dy*2+dx)*C + c], gr pitch ldr.
 __global__ void reorg_bwd_add_kernel(const float* __restrict__ gr, long long ldr, float* __restrict__ g, int B, int H, int W,
                                      int C) {
