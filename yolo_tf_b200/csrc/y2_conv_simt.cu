@@ -116,47 +116,62 @@ conv0_pool_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio,
 // Training mode: conv0 WITHOUT BN/pool (batch statistics need the raw output first): z[B,H,W,32] fp32.
 __global__ void __launch_bounds__(128)
 conv0_raw_kernel(const float* __restrict__ x, const float* __restrict__ w_hwio, float* __restrict__ z, int B, int H, int W) {
+    // One thread = two horizontally adjacent output pixels x all 32 channels: every 128-bit weight read from shared memory
+    // (warp-broadcast) feeds 8 FMAs instead of 4, which moves the kernel from LDS-bound to FFMA2-bound.
     __shared__ __align__(16) float sw[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w_hwio[i];
     __syncthreads();
-    const size_t total = (size_t)B * H * W;
+    const int W2 = W / 2;
+    const size_t total = (size_t)B * H * W2;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int xx0 = (int)(idx % W);
-        size_t t = idx / W;
+        const int xx0 = (int)(idx % W2) * 2;
+        size_t t = idx / W2;
         const int yy0 = (int)(t % H);
         const int b = (int)(t / H);
-        float patch[27];
+        float patch[3][4][3];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 const int yy = yy0 - 1 + r, xx = xx0 - 1 + c;
                 const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
                 const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) patch[(r * 3 + c) * 3 + ch] = ok ? __ldg(src + ch) : 0.f;
+                for (int ch = 0; ch < 3; ++ch) patch[r][c][ch] = ok ? __ldg(src + ch) : 0.f;
             }
-        float2 acc[16];
+        float2 acc0[16], acc1[16];
 #pragma unroll
-        for (int n = 0; n < 16; ++n) acc[n] = make_float2(0.f, 0.f);
+        for (int n = 0; n < 16; ++n) { acc0[n] = make_float2(0.f, 0.f); acc1[n] = make_float2(0.f, 0.f); }
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            const float2 vv = make_float2(patch[k], patch[k]);
-            const float4* wr = reinterpret_cast<const float4*>(&sw[k * 32]);
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 q = wr[j];
-                acc[2 * j] = __ffma2_rn(vv, make_float2(q.x, q.y), acc[2 * j]);
-                acc[2 * j + 1] = __ffma2_rn(vv, make_float2(q.z, q.w), acc[2 * j + 1]);
-            }
-        }
-        float4* dst = reinterpret_cast<float4*>(z + idx * 32);
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float2 v0 = make_float2(patch[r][c][ch], patch[r][c][ch]);
+                    const float2 v1 = make_float2(patch[r][c + 1][ch], patch[r][c + 1][ch]);
+                    const float4* wr = reinterpret_cast<const float4*>(&sw[((r * 3 + c) * 3 + ch) * 32]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 q = wr[j];
+                        const float2 wa = make_float2(q.x, q.y), wb = make_float2(q.z, q.w);
+                        acc0[2 * j] = __ffma2_rn(v0, wa, acc0[2 * j]);
+                        acc0[2 * j + 1] = __ffma2_rn(v0, wb, acc0[2 * j + 1]);
+                        acc1[2 * j] = __ffma2_rn(v1, wa, acc1[2 * j]);
+                        acc1[2 * j + 1] = __ffma2_rn(v1, wb, acc1[2 * j + 1]);
+                    }
+                }
+        const size_t pix = ((size_t)b * H + yy0) * W + xx0;
+        float4* dst = reinterpret_cast<float4*>(z + pix * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc0[2 * j].x, acc0[2 * j].y, acc0[2 * j + 1].x, acc0[2 * j + 1].y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[8 + j] = make_float4(acc1[2 * j].x, acc1[2 * j].y, acc1[2 * j + 1].x, acc1[2 * j + 1].y);
     }
 }
 int conv0_raw_launch(const float* x, const float* w_hwio, float* z, int B, int H, int W, cudaStream_t s) {
-    const size_t total = (size_t)B * H * W;
+    Y2_REQUIRE(W % 2 == 0, "conv0 raw: W must be even");
+    const size_t total = (size_t)B * H * (W / 2);          // pixel pairs
     size_t blocks = (total + 127) / 128;
     if (blocks > 148 * 16) blocks = 148 * 16;
     conv0_raw_kernel<<<(int)blocks, 128, 0, s>>>(x, w_hwio, z, B, H, W);
