@@ -98,7 +98,9 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
 
 /* Options.  "fuse_pool" (default 1): fuse the 2x2/2 max-pools (inference.py:74,83,96) into the conv epilogues when
  * the batch and extent admit the spatial tiling (e.g. batch 32 at 416/608); 0 keeps the separate pool pass and
- * materialises the un-pooled activations for y2_get_activation. */
+ * materialises the un-pooled activations for y2_get_activation.  "halo" (default 1): run the 32-channel 3x3 layer
+ * (conv1, inference.py:75) from one halo tile per output tile with its weights resident in shared memory instead of nine
+ * im2col fetches; 0 selects the im2col path (bit-identical results, used by the equivalence tests). */
 int y2_set_option(y2_handle* h, const char* key, int value);
 
 /* One conv (+scale/bias +leaky) on float32 NHWC tensors through the same tcgen05 kernel the

@@ -597,3 +597,4 @@ int y2_check_async_errors(void) {
 }  // extern "C"
 
 #include "y2_train_api.inc"
+#include "y2_optim_api.inc"

@@ -193,6 +193,12 @@ int conv0_raw_launch(const float* x, const float* w_hwio, float* z, int B, int H
 int conv0_wgrad_launch(const float* x, const bf16* dx_hi, const bf16* dx_lo, float* dw, double* partial, int B, int H, int W,
                        cudaStream_t s);
 
+// ---- optimizer step on the flat bucket (y2_optim.cu) ----
+struct AdamChunk { unsigned long long off; unsigned int count; unsigned int tensor; };   // <= 16384 elements, inside one tensor
+int adam_launch(const float* g, float* m, float* v, float* const* params_dev, const unsigned long long* tensor_start_dev,
+                const AdamChunk* tab_dev, const int* first_chunk_dev, int nchunks, int ntensors, double* partial, float* scale,
+                float alpha, float beta1, float beta2, float eps, float clip, cudaStream_t s);
+
 // ---- SIMT convs (y2_conv_simt.cu) ----
 // conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.
 int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,
