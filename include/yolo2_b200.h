@@ -85,6 +85,20 @@ int y2_param_offsets(const y2_handle* h, int layer, size_t* w_off, size_t* gamma
 int y2_get_bn_state(y2_handle* h, int layer, float* gamma, float* beta, float* moving_mean, float* moving_variance,
                     void* stream);
 
+/* Optimizer step -- the apply-gradients part of slim.learning.create_train_op (train.py:127-129) with the default
+ * optimizer tf.train.AdamOptimizer(lr, beta1, beta2, epsilon) (train.py:70-72, config.ini [optimizer_adam]) on the flat
+ * bucket y2_darknet_backward filled (after the all-reduce).  TF-1.0 arithmetic: alpha = lr*sqrt(1-beta2^t)/(1-beta1^t);
+ * m += (g-m)*(1-beta1); v += (g*g-v)*(1-beta2); var -= m*alpha/(sqrt(v)+epsilon); clip_norm > 0 first rescales every
+ * tensor's gradient by clip*min(rsqrt(sum g*g), 1/clip) (tf.clip_by_norm, --gradient_clip train.py:159).
+ * params: HOST array of y2_num_param_tensors() DEVICE pointers in bucket order (per layer weights, gamma, beta | biases),
+ * updated in place; m, v: device buffers of y2_param_count() floats (zero before the first step); t = 1, 2, ...
+ * The learning-rate schedule (tf.train.exponential_decay, train.py:120) is the caller's: pass the decayed rate. */
+int y2_num_param_tensors(const y2_handle* h);
+size_t y2_adam_workspace_bytes(const y2_handle* h);
+int y2_adam_step(y2_handle* h, const float* flat_grads, float* m, float* v, float* const* params, int ntensors,
+                 float learning_rate, float beta1, float beta2, float epsilon, long long t, float clip_norm, void* ws,
+                 size_t ws_bytes, void* stream);
+
 /* Test hooks of the training step (per-layer "teacher-forced" backward parity): y2_train_probe arms the next
  * y2_darknet_backward to copy dL/dy of `layer` (dense [M][cout]) and dL/d(input of layer) (dense [M][cin]);
  * y2_train_get_tensor reads saved forward state: kind 0 raw conv output, 1 activation, 2 pooled, 3 concat. */

@@ -115,6 +115,20 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         ar_ms = a0.elapsed_time(a1) / 5
+    # optimizer step alone: Adam + per-tensor clip on the bucket; 28 B per parameter (+4 B for the clip norms)
+    from yolo_tf_b200.optimizer import AdamOptimizer, create_train_op
+    top = create_train_op(builder, AdamOptimizer(1e-6), clip_gradient_norm=1.0)
+    _, views = builder.backward(allreduce=False)
+    for _ in range(2):
+        top.apply_gradients(flat, views)
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(10):
+        top.apply_gradients(flat, views)
+    o1.record()
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().y2_check_async_errors())
+    adam_ms = o0.elapsed_time(o1) / 10
     if rank == 0:
         peaks, kind = B.measured_peaks()
         gf_img = (3 * B.conv_flops(size, size, C, 5) - 2 * size * size * 27 * 32) / 1e9          # fwd + dgrad + wgrad, no dgrad for conv0
@@ -124,7 +138,9 @@ def main():
                 "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "batch_per_gpu": Bn, "classes": C,
                 "algorithmic_gflop_per_image": gf_img, "algorithmic_tflops": ips * gf_img / 1e3,
                 "frac_of_bf16_peak": ips * gf_img / 1e3 / world / float(peaks.get("bf16_tflops_sustained", 1450.3)), "peak_source": kind,
-                "gpu_launches": int(launches), "allreduce_ms_alone": ar_ms, "grad_bucket_mb": flat.numel() * 4 / 1e6,
+                "gpu_launches": int(launches), "allreduce_ms_alone": ar_ms,
+                "adam_clip_step_ms": adam_ms, "adam_clip_algorithmic_GBs": flat.numel() * 32 / adam_ms / 1e6,
+                "adam_frac_of_hbm_peak": flat.numel() * 32 / adam_ms / 1e6 / float(peaks.get("hbm_gbs", 6511.9)), "grad_bucket_mb": flat.numel() * 4 / 1e6,
                 "total_loss": float(builder.objectives.total_loss())}
         print(json.dumps(line), flush=True)
     if world > 1:

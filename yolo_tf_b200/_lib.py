@@ -52,6 +52,9 @@ _SIGNATURES = {
     "y2_set_profiling": (c_i, [c_p, c_i]),
     "y2_get_layer_ms": (c_i, [c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f)]),
     "y2_launch_count": (ctypes.c_ulonglong, []),
+    "y2_num_param_tensors": (c_i, [c_p]),
+    "y2_adam_workspace_bytes": (c_sz, [c_p]),
+    "y2_adam_step": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_f, c_f, c_f, c_f, ctypes.c_longlong, c_f, c_p, c_sz, c_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
