@@ -99,6 +99,19 @@ int y2_adam_step(y2_handle* h, const float* flat_grads, float* m, float* v, floa
                  float learning_rate, float beta1, float beta2, float epsilon, long long t, float clip_norm, void* ws,
                  size_t ws_bytes, void* stream);
 
+/* utils/preprocess.py:23-25 per_image_standardization, batched on the device (detect.py:62 applies it to the resized uint8
+ * image cast to float32): out[b] = (x[b] - mean_b) / max(std_b, 1/sqrt(n)), mean and POPULATION std over all
+ * n = H*W*3 elements of image b.  x: uint8 (elem_bytes 1; the cast is fused, a quarter of the H2D bytes) or float32 (4). */
+size_t y2_standardize_workspace_bytes(int B, size_t n_per_image);
+int y2_per_image_standardization(const void* x, int elem_bytes, int B, size_t n_per_image, float* out, void* ws,
+                                 size_t ws_bytes, void* stream);
+
+/* detect.py:72-87 after non_max_suppress: per box index = argmax_c conf (first maximum), kept iff conf[index] > threshold;
+ * kept boxes are appended in box-index order: box[b][i], cls[b][i], score[b][i], xywh[b][i] = (xy_min*scale,
+ * (xy_max-xy_min)*scale) with scale = image size / cells (detect.py:72), count[b] = number kept.  All device, [B][N]. */
+int y2_detections(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
+                  float scale_x, float scale_y, int* count, int* box, int* cls, float* score, float* xywh, void* stream);
+
 /* Test hooks of the training step (per-layer "teacher-forced" backward parity): y2_train_probe arms the next
  * y2_darknet_backward to copy dL/dy of `layer` (dense [M][cout]) and dL/d(input of layer) (dense [M][cin]);
  * y2_train_get_tensor reads saved forward state: kind 0 raw conv output, 1 activation, 2 pooled, 3 concat. */

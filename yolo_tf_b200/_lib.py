@@ -54,6 +54,9 @@ _SIGNATURES = {
     "y2_launch_count": (ctypes.c_ulonglong, []),
     "y2_num_param_tensors": (c_i, [c_p]),
     "y2_adam_workspace_bytes": (c_sz, [c_p]),
+    "y2_standardize_workspace_bytes": (c_sz, [c_i, c_sz]),
+    "y2_per_image_standardization": (c_i, [c_p, c_i, c_i, c_sz, c_p, c_p, c_sz, c_p]),
+    "y2_detections": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
     "y2_adam_step": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_f, c_f, c_f, c_f, ctypes.c_longlong, c_f, c_p, c_sz, c_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

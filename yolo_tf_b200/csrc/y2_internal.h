@@ -199,6 +199,12 @@ int adam_launch(const float* g, float* m, float* v, float* const* params_dev, co
                 const AdamChunk* tab_dev, const int* first_chunk_dev, int nchunks, int ntensors, double* partial, float* scale,
                 float alpha, float beta1, float beta2, float eps, float clip, cudaStream_t s);
 
+// ---- pre / post steps (y2_prepost.cu) ----
+size_t standardize_workspace_bytes(int B, size_t n);
+int standardize_launch(const void* x, int elem_bytes, int B, size_t n, float* out, void* ws, cudaStream_t s);
+int detections_launch(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold, float sx, float sy,
+                      int* count, int* box, int* cls, float* score, float* xywh, cudaStream_t s);
+
 // ---- SIMT convs (y2_conv_simt.cu) ----
 // conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.
 int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,

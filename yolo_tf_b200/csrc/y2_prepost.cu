@@ -1,0 +1,151 @@
+// Steps either side of the detection path:
+//   per_image_standardization  <- utils/preprocess.py:23-25 (detect.py:62: applied to the resized uint8 image cast to float32)
+//       out = (x - mean(x)) / max(std(x), 1/sqrt(n)),  mean / population std over ALL n = H*W*3 elements of one image
+//   detections                 <- detect.py:72-87: per box index = argmax_c conf (first maximum), kept iff conf[index] > threshold,
+//       box scaled from cell units to pixels (xy_min * scale, (xy_max - xy_min) * scale)
+// Both are HBM-bound passes; reductions are two-stage with fp64 partials and a fixed-order finish (deterministic).
+#include "y2_internal.h"
+
+namespace y2 {
+
+static constexpr int STD_CHUNK = 16384;
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p, size_t i);
+template <> __device__ __forceinline__ float ld_as_float<unsigned char>(const unsigned char* p, size_t i) { return (float)__ldg(p + i); }
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p, size_t i) { return __ldg(p + i); }
+
+// PASS 0: partial[b][chunk] = sum x ; PASS 1: partial[b][chunk] = sum (x - mean[b])^2
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256)
+std_partial_kernel(const T* __restrict__ x, size_t n, const float* __restrict__ mean, double* __restrict__ partial) {
+    const int b = blockIdx.y, chunks = gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * STD_CHUNK, hi = lo + STD_CHUNK < n ? lo + STD_CHUNK : n;
+    const T* src = x + (size_t)b * n;
+    const float mu = PASS == 1 ? mean[b] : 0.f;
+    float s = 0.f;                                           // <= 64 terms per thread in fp32, then fp64
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+        const float v = ld_as_float<T>(src, i);
+        if (PASS == 0) s += v; else { const float d = v - mu; s = fmaf(d, d, s); }
+    }
+    __shared__ double sm[256];
+    sm[threadIdx.x] = (double)s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)b * chunks + blockIdx.x] = sm[0];
+}
+
+// one warp per image: fixed-order sum of the chunk partials.  PASS 0 -> mean ; PASS 1 -> denom = max(std, 1/sqrt(n))
+template <int PASS>
+__global__ void std_finish_kernel(const double* __restrict__ partial, int chunks, int B, double n, float* __restrict__ mean,
+                                  float* __restrict__ denom) {
+    const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int c = lane; c < chunks; c += 32) s += partial[(size_t)b * chunks + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (PASS == 0) mean[b] = (float)(s / n);
+        else denom[b] = fmaxf((float)sqrt(s / n), (float)(1.0 / sqrt(n)));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+std_apply_kernel(const T* __restrict__ x, size_t n, const float* __restrict__ mean, const float* __restrict__ denom, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float mu = mean[b], d = denom[b];
+    const T* src = x + (size_t)b * n;
+    float* dst = out + (size_t)b * n;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        dst[i] = __fdiv_rn(ld_as_float<T>(src, i) - mu, d);
+}
+
+template <typename T>
+static int standardize_run(const T* x, int B, size_t n, float* out, double* partial, float* mean, float* denom, cudaStream_t s) {
+    const int chunks = (int)((n + STD_CHUNK - 1) / STD_CHUNK);
+    dim3 grid(chunks, B);
+    std_partial_kernel<T, 0><<<grid, 256, 0, s>>>(x, n, nullptr, partial);
+    std_finish_kernel<0><<<(B + 7) / 8, 256, 0, s>>>(partial, chunks, B, (double)n, mean, denom);
+    std_partial_kernel<T, 1><<<grid, 256, 0, s>>>(x, n, mean, partial);
+    std_finish_kernel<1><<<(B + 7) / 8, 256, 0, s>>>(partial, chunks, B, (double)n, mean, denom);
+    int ab = (int)((n + 2047) / 2048);
+    if (ab > 148 * 4) ab = 148 * 4;
+    std_apply_kernel<T><<<dim3(ab, B), 256, 0, s>>>(x, n, mean, denom, out);
+    Y2_CUDA(cudaGetLastError());
+    for (int i = 0; i < 5; ++i) note_launch();
+    return 0;
+}
+size_t standardize_workspace_bytes(int B, size_t n) {
+    const size_t chunks = (n + STD_CHUNK - 1) / STD_CHUNK;
+    return ((size_t)B * chunks * sizeof(double) + 255) / 256 * 256 + 2 * (((size_t)B * sizeof(float) + 255) / 256 * 256);
+}
+int standardize_launch(const void* x, int elem_bytes, int B, size_t n, float* out, void* ws, cudaStream_t s) {
+    const size_t chunks = (n + STD_CHUNK - 1) / STD_CHUNK;
+    char* p = static_cast<char*>(ws);
+    double* partial = reinterpret_cast<double*>(p); p += ((size_t)B * chunks * sizeof(double) + 255) / 256 * 256;
+    float* mean = reinterpret_cast<float*>(p); p += ((size_t)B * sizeof(float) + 255) / 256 * 256;
+    float* denom = reinterpret_cast<float*>(p);
+    if (elem_bytes == 1) return standardize_run(static_cast<const unsigned char*>(x), B, n, out, partial, mean, denom, s);
+    return standardize_run(static_cast<const float*>(x), B, n, out, partial, mean, denom, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// detections: one block (8 warps) per image, a warp per box: coalesced row read, shuffle argmax with "first maximum"
+// tie-break, then an ordered append (box index order) through a per-chunk warp prefix in shared memory.
+__global__ void __launch_bounds__(256)
+detections_kernel(const float* __restrict__ conf, const float* __restrict__ xy_min, const float* __restrict__ xy_max, int N, int C,
+                  float threshold, float sx, float sy, int* __restrict__ count, int* __restrict__ box, int* __restrict__ cls,
+                  float* __restrict__ score, float* __restrict__ xywh) {
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int keep[8], base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        const int n = n0 + warp;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        if (n < N) {
+            const float* row = conf + ((size_t)b * N + n) * C;
+            for (int c = lane; c < C; c += 32) {
+                const float v = __ldg(row + c);
+                if (v > best) { best = v; bi = c; }         // ascending c per lane: strict > keeps the first maximum
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+        }
+        const bool k = (n < N) && (best > threshold);
+        if (lane == 0) keep[warp] = k ? 1 : 0;
+        __syncthreads();
+        int pos = base;
+        for (int w = 0; w < warp; ++w) pos += keep[w];
+        if (k && lane == 0) {
+            const size_t o = (size_t)b * N + pos;
+            box[o] = n; cls[o] = bi; score[o] = best;
+            const float x0 = xy_min[((size_t)b * N + n) * 2], y0 = xy_min[((size_t)b * N + n) * 2 + 1];
+            const float x1 = xy_max[((size_t)b * N + n) * 2], y1 = xy_max[((size_t)b * N + n) * 2 + 1];
+            xywh[o * 4 + 0] = __fmul_rn(x0, sx); xywh[o * 4 + 1] = __fmul_rn(y0, sy);
+            xywh[o * 4 + 2] = __fmul_rn(__fsub_rn(x1, x0), sx); xywh[o * 4 + 3] = __fmul_rn(__fsub_rn(y1, y0), sy);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += keep[w]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[b] = base;
+}
+int detections_launch(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold, float sx, float sy,
+                      int* count, int* box, int* cls, float* score, float* xywh, cudaStream_t s) {
+    detections_kernel<<<B, 256, 0, s>>>(conf, xy_min, xy_max, N, C, threshold, sx, sy, count, box, cls, score, xywh);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace y2

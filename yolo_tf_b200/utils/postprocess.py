@@ -45,3 +45,25 @@ def non_max_suppress(conf, xy_min, xy_max, threshold, threshold_iou):
     order = non_max_suppress_device(d_conf, d_lo, d_hi, threshold, threshold_iou, want_order=True)
     score[...] = d_conf[0].cpu().numpy()                    # the reference's in-place side effect
     return [(score[i], lo[i], hi[i]) for i in order[0].cpu().numpy()]
+
+
+def detections_device(conf, xy_min, xy_max, threshold, scale):
+    """The selection loop of detect.py:72-87 for a batch, on the device, after ``non_max_suppress_device``:
+    per box ``index = argmax(conf_row)`` (first maximum), kept iff ``conf_row[index] > threshold``; boxes scaled from cell
+    units to pixels with ``scale = [image_width / cell_width, image_height / cell_height]`` (detect.py:72).
+    conf [B,N,C], xy_min/xy_max [B,N,2] float32 CUDA tensors.  Returns (count [B] int32, box [B,N] int32, cls [B,N] int32,
+    score [B,N] float32, xywh [B,N,4] float32 = (x_min, y_min, width, height) in pixels); entries [b, :count[b]] are valid,
+    in box-index order (the reference walks them in its NMS list order; the SET is the same)."""
+    import torch
+    L = _lib.lib()
+    b, n, c = conf.shape
+    dev = conf.device
+    count = torch.empty((b,), dtype=torch.int32, device=dev)
+    box = torch.empty((b, n), dtype=torch.int32, device=dev)
+    cls = torch.empty((b, n), dtype=torch.int32, device=dev)
+    score = torch.empty((b, n), dtype=torch.float32, device=dev)
+    xywh = torch.empty((b, n, 4), dtype=torch.float32, device=dev)
+    _lib.check(L.y2_detections(_lib.ptr(conf, torch.float32), _lib.ptr(xy_min, torch.float32), _lib.ptr(xy_max, torch.float32), b, n, c,
+                               float(threshold), float(scale[0]), float(scale[1]), _lib.ptr(count), _lib.ptr(box), _lib.ptr(cls),
+                               _lib.ptr(score), _lib.ptr(xywh), _lib.current_stream()))
+    return count, box, cls, score, xywh
