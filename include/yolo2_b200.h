@@ -34,6 +34,19 @@ int y2_version(void);
 int y2_create(y2_handle** out, int device, int classes, int num_anchors);
 void y2_destroy(y2_handle* h);
 
+/* The `inference` function is string-dispatched from the INI config (`getattr(inference, config.get(section,
+ * 'inference'))`, model/yolo2/__init__.py:107; config/yolo2/{darknet,tiny}-*.ini).  y2_create_net selects it:
+ *   Y2_ARCH_DARKNET  `darknet()`  model/yolo2/inference.py:61-120  (y2_create == this)
+ *   Y2_ARCH_TINY     `tiny()`     model/yolo2/inference.py:25-50: 16..512-channel 3x3 convs, five 2x2/2 max-pools, one
+ *                    2x2 stride-1 SAME max-pool (:42), two 1024-channel 3x3 convs, linear 1x1 conv.  Inference only:
+ *                    the training entry points return an error for this network (the reference trains it through the
+ *                    same TF autodiff; here only Darknet-19's backward is built).
+ * Layers whose channel count is below 32 (tiny conv0: 16) are stored zero-padded to 32; y2_layer_info,
+ * y2_load_weights and y2_get_activation speak the logical (variable) shapes. */
+#define Y2_ARCH_DARKNET 0
+#define Y2_ARCH_TINY 1
+int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int arch);
+
 /* Number of conv layers (22) and the per-layer geometry, in graph order conv0..conv20, conv (final). */
 int y2_num_layers(const y2_handle* h);
 int y2_layer_info(const y2_handle* h, int layer, int* ksize, int* cin, int* cout, int* has_bn);
@@ -111,6 +124,19 @@ int y2_per_image_standardization(const void* x, int elem_bytes, int B, size_t n_
  * (xy_max-xy_min)*scale) with scale = image size / cells (detect.py:72), count[b] = number kept.  All device, [B][N]. */
 int y2_detections(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
                   float scale_x, float scale_y, int* count, int* box, int* cls, float* score, float* xywh, void* stream);
+
+/* utils/data/__init__.py:112-145 transform_labels, batched on the device (train.py feeds it per image through
+ * tf.py_func, utils/data/__init__.py:148-150): ragged object lists -> the six label tensors Objectives consumes.
+ * objects_class int32 [T], objects_coord float32 [T][4] = (xmin, ymin, xmax, ymax) normalised to the image, image b owns
+ * objects offsets[b] .. offsets[b+1]-1 (offsets int32 [B+1], device).  Outputs (device, fully overwritten):
+ * mask [B][cells][1], prob [B][cells][1][classes], coords [B][cells][1][4] = (offset_x, offset_y, sqrt w, sqrt h),
+ * offset_xy_min / offset_xy_max [B][cells][1][2], areas [B][cells][1].  One box per cell: the LAST object landing in a cell
+ * wins, class bits accumulate (numpy fancy-index assignment).  float32 arithmetic in the reference's order.
+ * status (nullable, int32 [B]): bit 0 = an object's cell or class index is out of range (IndexError in the reference; the
+ * object is skipped), bit 1 = negative width/height (`assert np.all(wh >= 0)`, :142). */
+int y2_transform_labels(const int32_t* objects_class, const float* objects_coord, const int32_t* offsets, int B, int classes,
+                        int cell_width, int cell_height, float* mask, float* prob, float* coords, float* offset_xy_min,
+                        float* offset_xy_max, float* areas, int32_t* status, void* stream);
 
 /* Test hooks of the training step (per-layer "teacher-forced" backward parity): y2_train_probe arms the next
  * y2_darknet_backward to copy dL/dy of `layer` (dense [M][cout]) and dL/d(input of layer) (dense [M][cin]);

@@ -13,6 +13,9 @@ Restates, with torch-CPU float32 (or float64 "truth") tensors:
   training mode uses the batch mean and the *population* variance over (B,H,W).
 * ``max_pool2d`` 2x2 stride 2 SAME (inference.py:69); every pooled extent is even,
   so SAME never pads.
+* ``tiny_oracle``     <- ``tiny()``        model/yolo2/inference.py:25-50, including its
+  2x2 **stride-1** SAME max-pool (:42): TF SAME with k=2, s=1 pads one row/column at
+  the bottom/right only (pad_total = 1, pad_before = 0) and max-pool ignores padding.
 
 PARITY UNPINNED for conv/BN/pool arithmetic: TensorFlow 1.0 is not installable in
 the authoring container and the reference ships no golden vector for this part
@@ -73,7 +76,23 @@ def layer_table(classes, num_anchors):
     return t
 
 
-def init_params(classes, num_anchors, seed=1, mode="conditioned"):
+def tiny_layer_table(classes, num_anchors):
+    """Same tuple format as layer_table for ``tiny()`` (inference.py:33-48); ``then`` in
+    {None,'pool','pool_s1','linear'}."""
+    t, cin, ch = [], 3, 16
+    for _ in range(5):                       # :35-39
+        t.append(("conv%d" % len(t), 3, cin, ch, "pool"))
+        cin, ch = ch, ch * 2
+    t.append(("conv%d" % len(t), 3, cin, ch, "pool_s1"))   # :40-42
+    cin, ch = ch, ch * 2
+    for _ in range(2):                       # :45-47
+        t.append(("conv%d" % len(t), 3, cin, ch, None))
+        cin = ch
+    t.append(("conv", 1, ch, num_anchors * (5 + classes), "linear"))   # :48
+    return t
+
+
+def init_params(classes, num_anchors, seed=1, mode="conditioned", table=None):
     """Synthetic "random-init checkpoint" (there is no network for real weights).
 
     mode='xavier'      : what slim would create: Xavier-uniform weights, BN gamma=1,
@@ -84,7 +103,7 @@ def init_params(classes, num_anchors, seed=1, mode="conditioned"):
     """
     rs = np.random.RandomState(seed)
     p = {}
-    for name, k, cin, cout, then in layer_table(classes, num_anchors):
+    for name, k, cin, cout, then in (table or layer_table(classes, num_anchors)):
         fan_in, fan_out = k * k * cin, k * k * cout
         if mode == "xavier":
             lim = math.sqrt(6.0 / (fan_in + fan_out))
@@ -133,8 +152,20 @@ def _conv_same(x_nchw, w_hwio):
     return F.conv2d(x_nchw, w, padding=k // 2)
 
 
+def max_pool_s1_same_oracle(x_nchw):
+    """slim.max_pool2d(kernel 2, stride 1, padding SAME) (tiny, inference.py:42): out[y,x] = max over rows y..min(y+1,H-1),
+    columns x..min(x+1,W-1) -- the single SAME pad row/column sits at the bottom/right and never wins."""
+    return F.max_pool2d(F.pad(x_nchw, (0, 1, 0, 1), value=float("-inf")), 2, 1)
+
+
+def tiny_oracle(x_nhwc, params, classes, num_anchors, dtype=torch.float32, taps=None, threads=None):
+    """``tiny()`` forward (inference.py:25-50), inference-mode BN.  Same conventions as darknet_oracle."""
+    return darknet_oracle(x_nhwc, params, classes, num_anchors, False, dtype, taps, threads,
+                          table=tiny_layer_table(classes, num_anchors))
+
+
 def darknet_oracle(x_nhwc, params, classes, num_anchors, training=False, dtype=torch.float32,
-                   taps=None, threads=None):
+                   taps=None, threads=None, table=None):
     """Forward pass.  x_nhwc [B,H,W,3]; returns [B,H/32,W/32,A*(5+C)] ndarray of `dtype`.
 
     taps: optional dict that receives every layer's post-activation NHWC output
@@ -146,7 +177,7 @@ def darknet_oracle(x_nhwc, params, classes, num_anchors, training=False, dtype=t
     P = {k: torch.as_tensor(v).to(dtype) for k, v in params.items()}
     passthrough = None
     with torch.no_grad():
-        for name, k, cin, cout, then in layer_table(classes, num_anchors):
+        for name, k, cin, cout, then in (table or layer_table(classes, num_anchors)):
             if then == "after_concat":
                 r = reorg_oracle(passthrough.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
                 x = torch.cat([r, x], dim=1)                       # inference.py:116
@@ -171,6 +202,10 @@ def darknet_oracle(x_nhwc, params, classes, num_anchors, training=False, dtype=t
                 x = F.max_pool2d(x, 2, 2)
                 if taps is not None:
                     taps[name + "/pool"] = x.permute(0, 2, 3, 1).contiguous().numpy()
+            if then == "pool_s1":
+                x = max_pool_s1_same_oracle(x)
+                if taps is not None:
+                    taps[name + "/pool"] = x.permute(0, 2, 3, 1).contiguous().numpy()
     return x.permute(0, 2, 3, 1).contiguous().numpy()
 
 
@@ -185,11 +220,11 @@ def conv_bn_leaky_oracle(x_nhwc, w_hwio, scale, bias, leaky=True, dtype=torch.fl
     return y.permute(0, 2, 3, 1).contiguous().numpy()
 
 
-def flops_per_image(h, w, classes, num_anchors):
+def flops_per_image(h, w, classes, num_anchors, table=None):
     """2*MAC of the 22 convs (SURVEY.md section 8a layer table)."""
     total = 0
     hh, ww = h, w
-    for name, k, cin, cout, then in layer_table(classes, num_anchors):
+    for name, k, cin, cout, then in (table or layer_table(classes, num_anchors)):
         total += 2 * hh * ww * k * k * cin * cout
         if then in ("pool", "passthrough+pool"):
             hh //= 2

@@ -82,3 +82,33 @@ def test_variable_store_names_and_shapes():
     s = V.VariableStore()
     with pytest.raises(Exception):
         s.get("yolo2_darknet/conv0/weights", (3, 3, 3, 32), V.xavier_uniform, "cuda")   # no GPU here -> loud
+
+
+def test_tiny_host_geometry_matches_oracle_table_and_config_dispatch(tmp_path):
+    """config/yolo2/tiny-20.ini: `inference = tiny` -> inference.tiny / TINY_DOWNSAMPLING (model/yolo2/__init__.py:107,
+    utils/__init__.py:47-49)."""
+    import configparser
+    import torch
+    from oracle.darknet_oracle import tiny_layer_table
+    from yolo_tf_b200 import _lib, utils, variables
+    from yolo_tf_b200.model.yolo2 import inference
+    host = inference.tiny_layer_geometry(20, 5)
+    assert [(n, k, ci, co) for n, k, ci, co, _, _ in host] == [(n, k, ci, co) for n, k, ci, co, _ in tiny_layer_table(20, 5)]
+    assert [p for *_, p in host] == [True] * 5 + ['s1', False, False, False]
+    cfg = configparser.ConfigParser()
+    ini = tmp_path / "tiny.ini"
+    ini.write_text("[config]\nmodel = yolo2\n[yolo2]\ninference = tiny\n")
+    utils.load_config(cfg, [str(ini)])
+    assert utils.calc_cell_width_height(cfg, 416, 416) == (13, 13)
+    assert getattr(inference, cfg.get("yolo2", "inference")) is inference.tiny
+    with pytest.raises(_lib.Y2Error):
+        inference.tiny(torch.zeros(1, 32, 32, 3), 20, 5)           # no CPU path
+    w = variables.truncated_normal_01((3, 3, 16, 32))
+    assert np.abs(w).max() <= 0.2 and 0.07 < w.std() < 0.1
+
+
+def test_label_encoder_has_no_cpu_path():
+    from yolo_tf_b200 import _lib
+    from yolo_tf_b200.utils import data
+    with pytest.raises(_lib.Y2Error):
+        data.transform_labels_batch([np.array([1])], [np.zeros((1, 4), np.float32)], 20, 13, 13, device="cpu")

@@ -90,3 +90,28 @@ def test_darknet_oracle_fp32_vs_fp64_small():
     y64 = darknet_oracle(x, p, 20, 5, dtype=torch.float64)
     assert y32.shape == (1, 2, 2, 125)
     assert np.abs(y32 - y64).max() <= 1e-4 * np.abs(y64).max()
+
+
+def test_tiny_oracle_table_pool_semantics_and_fp64():
+    """tiny() (model/yolo2/inference.py:25-50): 9 convs, 6.971 GFLOP per 416x416 image (C=20); the stride-1 SAME pool clips
+    its window at the bottom/right edge (TF pads after, never before, and max-pool ignores padding)."""
+    import torch
+    from oracle.darknet_oracle import max_pool_s1_same_oracle, tiny_layer_table, tiny_oracle
+    t = tiny_layer_table(20, 5)
+    assert [(c[2], c[3]) for c in t] == [(3, 16), (16, 32), (32, 64), (64, 128), (128, 256), (256, 512), (512, 1024), (1024, 1024), (1024, 125)]
+    assert [c[4] for c in t] == ["pool"] * 5 + ["pool_s1", None, None, "linear"]
+    assert abs(flops_per_image(416, 416, 20, 5, table=t) / 1e9 - 6.971) < 1e-3
+    a = torch.arange(2 * 3 * 4 * 5, dtype=torch.float32).reshape(2, 3, 4, 5)
+    a = (a * 7919 % 101) - 50
+    b = max_pool_s1_same_oracle(a)
+    assert b.shape == a.shape
+    for y in range(4):
+        for x in range(5):
+            assert torch.equal(b[:, :, y, x], a[:, :, y:y + 2, x:x + 2].amax(dim=(2, 3)))
+    rs = np.random.RandomState(4)
+    p = init_params(20, 5, seed=2, table=t)
+    x = rs.normal(0, 1, size=(1, 96, 96, 3)).astype(np.float32)
+    y32 = tiny_oracle(x, p, 20, 5)
+    y64 = tiny_oracle(x, p, 20, 5, dtype=torch.float64)
+    assert y32.shape == (1, 3, 3, 125)
+    assert np.abs(y32 - y64).max() <= 1e-4 * np.abs(y64).max()

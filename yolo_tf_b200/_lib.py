@@ -24,6 +24,7 @@ _SIGNATURES = {
     "y2_last_error": (ctypes.c_char_p, []),
     "y2_version": (c_i, []),
     "y2_create": (c_i, [ctypes.POINTER(c_p), c_i, c_i, c_i]),
+    "y2_create_net": (c_i, [ctypes.POINTER(c_p), c_i, c_i, c_i, c_i]),
     "y2_destroy": (None, [c_p]),
     "y2_num_layers": (c_i, [c_p]),
     "y2_layer_info": (c_i, [c_p, c_i] + [ctypes.POINTER(c_i)] * 4),
@@ -57,6 +58,7 @@ _SIGNATURES = {
     "y2_standardize_workspace_bytes": (c_sz, [c_i, c_sz]),
     "y2_per_image_standardization": (c_i, [c_p, c_i, c_i, c_sz, c_p, c_p, c_sz, c_p]),
     "y2_detections": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "y2_transform_labels": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "y2_adam_step": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_f, c_f, c_f, c_f, ctypes.c_longlong, c_f, c_p, c_sz, c_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

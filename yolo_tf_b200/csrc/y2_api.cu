@@ -48,18 +48,37 @@ int nms_launch(float*, const float*, const float*, int, int, int, float, float, 
                cudaStream_t);
 
 // ---------------------------------------------------------------- network description
-// Darknet-19 + passthrough, model/yolo2/inference.py:70-118.
+// Darknet-19 + passthrough, model/yolo2/inference.py:70-118; tiny, model/yolo2/inference.py:25-50.
 struct LayerDesc {
-    int ksize, cin, cout;
-    int pool;          // 2x2 max-pool after (inference.py:74,83,96)
+    int ksize, cin, cout;   // logical = the variable's shape
+    int pool;          // max-pool after: 1 = 2x2 stride 2 (inference.py:74,83,96 / :37), 2 = 2x2 stride 1 SAME (tiny, :42)
     int passthrough;   // tapped for reorg (:95)
     int has_bn;
+    // stored channel counts: a multiple of 32 (the tcgen05 conv's K granule and the conv0 kernel's width); channels past
+    // the logical count hold exact zeros (zero weights, zero scale/bias), so they add nothing to any sum
+    int cin_s, cout_s;
+    int to_concat;     // output lands in the concat buffer behind the reorg channels (conv19, :116)
+    int from_concat;   // input is concat([reorg(passthrough), previous]) (conv20, :117)
 };
+static inline int store_channels(int c) { return c <= 3 ? c : (c + 31) / 32 * 32; }
+static std::vector<LayerDesc> tiny_layers(int classes, int anchors) {
+    std::vector<LayerDesc> L;
+    int cin = 3, ch = 16;
+    auto add = [&](int k, int cout, int pool) {
+        L.push_back({k, cin, cout, pool, 0, 1, store_channels(cin), store_channels(cout), 0, 0});
+        cin = cout;
+    };
+    for (int i = 0; i < 5; ++i) { add(3, ch, 1); ch *= 2; }     // :35-39
+    add(3, ch, 2); ch *= 2;                                     // :40-44 (max_pool2d stride=1)
+    add(3, ch, 0); add(3, ch, 0);                               // :45-47
+    L.push_back({1, ch, anchors * (5 + classes), 0, 0, 0, ch, anchors * (5 + classes), 0, 0});   // :48
+    return L;
+}
 static std::vector<LayerDesc> darknet19_layers(int classes, int anchors) {
     std::vector<LayerDesc> L;
     int cin = 3, ch = 32;
     auto add = [&](int k, int cout, int pool, int pt) {
-        L.push_back({k, cin, cout, pool, pt, 1});
+        L.push_back({k, cin, cout, pool, pt, 1, cin, cout, 0, 0});
         cin = cout;
     };
     for (int i = 0; i < 2; ++i) { add(3, ch, 1, 0); ch *= 2; }
@@ -68,9 +87,11 @@ static std::vector<LayerDesc> darknet19_layers(int classes, int anchors) {
     ch *= 2;
     add(3, ch, 0, 0); add(1, ch / 2, 0, 0); add(3, ch, 0, 0); add(1, ch / 2, 0, 0);
     add(3, ch, 0, 0); add(3, ch, 0, 0); add(3, ch, 0, 0);
+    L.back().to_concat = 1;
     cin = 4 * 512 + ch;                      // concat([reorg(passthrough), net]) :115-116
     add(3, ch, 0, 0);
-    L.push_back({1, ch, anchors * (5 + classes), 0, 0, 0});   // linear + bias :118
+    L.back().from_concat = 1;
+    L.push_back({1, ch, anchors * (5 + classes), 0, 0, 0, ch, anchors * (5 + classes), 0, 0});   // linear + bias :118
     return L;
 }
 
@@ -127,6 +148,8 @@ using namespace y2;
 
 struct y2_handle {
     int device = 0, classes = 0, anchors = 0, num_sms = 148;
+    int arch = Y2_ARCH_DARKNET;        // Y2_ARCH_* (y2_create_net)
+    int cat_c = 0;                     // channels of the concat buffer (0: the network has none)
     std::vector<LayerState> layers;
     Plan plan;
     TrainPlan tplan;
@@ -154,7 +177,12 @@ const char* y2_last_error(void) { return y2::last_error(); }
 int y2_version(void) { return 100; }
 
 int y2_create(y2_handle** out, int device, int classes, int num_anchors) {
+    return y2_create_net(out, device, classes, num_anchors, Y2_ARCH_DARKNET);
+}
+
+int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int arch) {
     Y2_REQUIRE(out, "y2_create: null out");
+    Y2_REQUIRE(arch == Y2_ARCH_DARKNET || arch == Y2_ARCH_TINY, "y2_create_net: unknown architecture %d", arch);
     Y2_REQUIRE(classes > 0 && num_anchors > 0, "y2_create: classes and num_anchors must be positive");
     int ndev = 0;
     Y2_CUDA(cudaGetDeviceCount(&ndev));
@@ -167,17 +195,21 @@ int y2_create(y2_handle** out, int device, int classes, int num_anchors) {
     y2_handle* h = new y2_handle();
     h->device = device; h->classes = classes; h->anchors = num_anchors;
     h->num_sms = prop.multiProcessorCount;
-    auto descs = darknet19_layers(classes, num_anchors);
+    h->arch = arch;
+    auto descs = arch == Y2_ARCH_TINY ? tiny_layers(classes, num_anchors) : darknet19_layers(classes, num_anchors);
     for (size_t i = 0; i < descs.size(); ++i) {
         LayerState s;
         s.d = descs[i];
-        choose_tiles(s.d.cout, &s.block_n, &s.cout_pad);
-        const size_t K = (size_t)s.d.ksize * s.d.ksize * s.d.cin;
-        if (cudaMalloc(&s.w_f32, K * s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        if (s.d.from_concat) h->cat_c = s.d.cin_s;
+        choose_tiles(s.d.cout_s, &s.block_n, &s.cout_pad);
+        const size_t K = (size_t)s.d.ksize * s.d.ksize * s.d.cin_s;
+        if (cudaMalloc(&s.w_f32, K * s.d.cout_s * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
         if (i > 0 && cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
-        if (cudaMalloc(&s.scale, s.d.cout * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&s.bias, s.d.cout * sizeof(float)) != cudaSuccess ||
+        if (cudaMalloc(&s.scale, s.d.cout_s * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&s.bias, s.d.cout_s * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+        cudaMemset(s.scale, 0, s.d.cout_s * sizeof(float));      // padded channels: scale = bias = 0 -> exact zeros
+        cudaMemset(s.bias, 0, s.d.cout_s * sizeof(float));
         s.beta = s.gamma + s.d.cout; s.mmean = s.beta + s.d.cout; s.mvar = s.mmean + s.d.cout;
         h->layers.push_back(s);
     }
@@ -216,9 +248,13 @@ int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* g
     Y2_CUDA(cudaSetDevice(h->device));
     LayerState& L = h->layers[layer];
     const size_t K = (size_t)L.d.ksize * L.d.ksize * L.d.cin;
-    if (w_hwio != L.w_f32)
+    if (L.d.cin_s != L.d.cin || L.d.cout_s != L.d.cout) {
+        Y2_REQUIRE(w_hwio != L.w_f32, "y2_load_weights: layer %d stores padded channels; pass the variable itself", layer);
+        if (pad_weights_launch(w_hwio, L.w_f32, L.d.ksize, L.d.cin, L.d.cout, L.d.cin_s, L.d.cout_s, s)) return -1;
+    } else if (w_hwio != L.w_f32) {
         Y2_CUDA(cudaMemcpyAsync(L.w_f32, w_hwio, K * L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if (layer > 0 && pack_weights_launch(L.w_f32, L.wpack, L.d.ksize, L.d.cin, L.d.cout, L.cout_pad, s)) return -1;
+    }
+    if (layer > 0 && pack_weights_launch(L.w_f32, L.wpack, L.d.ksize, L.d.cin_s, L.d.cout_s, L.cout_pad, s)) return -1;
     L.dgrad_fresh = false;
     if (L.d.has_bn) {
         Y2_REQUIRE(moving_mean && moving_variance, "y2_load_weights: layer %d needs BN statistics", layer);
@@ -258,25 +294,28 @@ static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* o
         const size_t M = (size_t)B * ch * cw;
         if (i == 0) {                              // conv0 writes its pooled output only
             out->act_off[i] = off;
-            off = align_up(off + 2 * (M / 4) * L.d.cout * sizeof(bf16), 1024);
+            off = align_up(off + 2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
             ch /= 2; cw /= 2;
             continue;
         }
         if (i == nl - 1) break;                    // final layer writes the caller's buffer
-        if (i == nl - 3) {                         // conv19 writes into the concat buffer
+        if (L.d.to_concat) {                       // conv19 writes into the concat buffer
             out->act_off[i] = (size_t)-1;
         } else {
             out->act_off[i] = off;
-            off = align_up(off + 2 * M * L.d.cout * sizeof(bf16), 1024);
+            off = align_up(off + 2 * M * L.d.cout_s * sizeof(bf16), 1024);
         }
-        if (L.d.pool) {
+        if (L.d.pool == 1) {
             out->pool_off[i] = off;
-            off = align_up(off + 2 * (M / 4) * L.d.cout * sizeof(bf16), 1024);
+            off = align_up(off + 2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
             ch /= 2; cw /= 2;
+        } else if (L.d.pool == 2) {                // stride 1: same extent
+            out->pool_off[i] = off;
+            off = align_up(off + 2 * M * L.d.cout_s * sizeof(bf16), 1024);
         }
     }
     out->concat_off = off;
-    off = align_up(off + 2 * (size_t)B * ch * cw * (4 * 512 + 1024) * sizeof(bf16), 1024);
+    off = align_up(off + 2 * (size_t)B * ch * cw * h->cat_c * sizeof(bf16), 1024);
     out->streamk_off = off;
     off = align_up(off + tc_conv_streamk_bytes(h->num_sms), 1024);
     out->total = off;
@@ -310,40 +349,40 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
         if (l.act_off[i] != (size_t)-1 && i != nl - 1) P.act[i] = reinterpret_cast<bf16*>(base + l.act_off[i]);
         if (i > 0 && h->layers[i].d.pool) P.pooled[i] = reinterpret_cast<bf16*>(base + l.pool_off[i]);
     }
-    const int cat_c = 4 * 512 + 1024;
+    const int cat_c = h->cat_c;
     const bf16* input = P.act[0];
     for (int i = 1; i < nl; ++i) {
         const LayerState& L = h->layers[i];
         const int oh = l.oh[i], ow = l.ow[i];
         const size_t M = (size_t)B * oh * ow;
-        if (i == nl - 2) input = P.concat;         // conv20 reads concat([reorg, conv19])
+        if (L.d.from_concat) input = P.concat;     // conv20 reads concat([reorg, conv19])
         TcConvLaunch& T = P.launch[i];
         // max-pool layers: fuse the 2x2/2 pool into the conv epilogue when the batch / extent admit the spatial tiling
-        const int halo = (h->halo && tc_conv_can_halo(B, oh, ow, L.d.cin, L.d.ksize, L.cout_pad, L.block_n, precision == 0)) ? h->halo : 0;
-        const bool fuse = L.d.pool && h->fuse_pool && (halo || tc_conv_can_fuse_pool(B, oh, ow));
+        const int halo = (h->halo && tc_conv_can_halo(B, oh, ow, L.d.cin_s, L.d.ksize, L.cout_pad, L.block_n, precision == 0)) ? h->halo : 0;
+        const bool fuse = L.d.pool == 1 && h->fuse_pool && (halo || tc_conv_can_fuse_pool(B, oh, ow));
         P.fused[i] = fuse;
-        if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin, L.d.ksize, L.wpack, L.d.cout, L.cout_pad, L.block_n,
+        if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin_s, L.d.ksize, L.wpack, L.d.cout_s, L.cout_pad, L.block_n,
                          0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0, halo))
             return -1;
         ConvParams& p = T.p;
         if (fuse) {
             p.pool_hi = P.pooled[i];
-            p.pool_lo = P.pooled[i] + (M / 4) * L.d.cout;
-            p.ldp = L.d.cout;
+            p.pool_lo = P.pooled[i] + (M / 4) * L.d.cout_s;
+            p.ldp = L.d.cout_s;
         }
         p.scale = L.d.has_bn ? L.scale : nullptr;
         p.bias = L.bias;
         p.leaky = L.d.has_bn ? 1 : 0;
         if (i == nl - 1) {
             p.mode = EPI_F32; p.ldc = L.d.cout;    // out pointer patched per call
-        } else if (i == nl - 3) {
+        } else if (L.d.to_concat) {
             p.mode = EPI_PLANES; p.ldc = cat_c;
-            p.out_hi = P.concat + 2048;
-            p.out_lo = P.concat + M * cat_c + 2048;
+            p.out_hi = P.concat + (cat_c - L.d.cout_s);
+            p.out_lo = P.concat + M * cat_c + (cat_c - L.d.cout_s);
         } else {
-            p.mode = EPI_PLANES; p.ldc = L.d.cout;
+            p.mode = EPI_PLANES; p.ldc = L.d.cout_s;
             p.out_hi = P.act[i];
-            p.out_lo = P.act[i] + M * L.d.cout;
+            p.out_lo = P.act[i] + M * L.d.cout_s;
             if (fuse && !L.d.passthrough) p.out_hi = p.out_lo = nullptr;   // the un-pooled tensor is never materialised
         }
         if (tc_conv_bind_output(&T)) return -1;
@@ -369,7 +408,8 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
     if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[0], s));
     {
         const size_t M0 = (size_t)B * (H / 2) * (W / 2);
-        if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout, B, H, W, s)) return -1;
+        Y2_REQUIRE(L0.d.cout_s == 32 && L0.d.pool == 1, "y2_darknet_forward: conv0 kernel is built for 32 stored output channels + pool");
+        if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout_s, B, H, W, s)) return -1;
     }
     if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[1], s));
     for (int i = 1; i < nl; ++i) {
@@ -383,11 +423,12 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
         const size_t M = (size_t)B * oh * ow;
         if (L.d.passthrough) {
             // reorg(passthrough) -> concat channels [0, 2048); both planes in one launch (batch 2B)
-            if (reorg_launch(P.act[i], P.concat, 2 * B, oh, ow, L.d.cout, 2, 2, 4 * L.d.cout + 1024, s)) return -1;
+            if (reorg_launch(P.act[i], P.concat, 2 * B, oh, ow, L.d.cout_s, 2, 2, h->cat_c, s)) return -1;
         }
         if (L.d.pool && !P.fused[i]) {
-            if (maxpool_planes_launch(P.act[i], P.act[i] + M * L.d.cout, P.pooled[i],
-                                      P.pooled[i] + (M / 4) * L.d.cout, B, oh, ow, L.d.cout, s))
+            const size_t Mp = L.d.pool == 1 ? M / 4 : M;
+            if (maxpool_planes_launch(P.act[i], P.act[i] + M * L.d.cout_s, P.pooled[i],
+                                      P.pooled[i] + Mp * L.d.cout_s, B, oh, ow, L.d.cout_s, s, L.d.pool == 1 ? 2 : 1))
                 return -1;
         }
         if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i + 2], s));
@@ -433,20 +474,21 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
     const size_t M = (size_t)P.B * P.oh[layer] * P.ow[layer];
     if (layer == 0) {
         Y2_REQUIRE(pooled, "y2_get_activation: conv0 is fused with its max-pool; only the pooled tensor exists");
-        return merge_planes_launch(P.act[0], P.act[0] + (M / 4) * d.cout, dst, M / 4, d.cout, d.cout, s);
+        return merge_planes_launch(P.act[0], P.act[0] + (M / 4) * d.cout_s, dst, M / 4, d.cout, d.cout_s, s);
     }
     if (pooled) {
         Y2_REQUIRE(d.pool, "y2_get_activation: layer %d has no pool", layer);
-        return merge_planes_launch(P.pooled[layer], P.pooled[layer] + (M / 4) * d.cout, dst, M / 4, d.cout, d.cout, s);
+        const size_t Mp = d.pool == 1 ? M / 4 : M;
+        return merge_planes_launch(P.pooled[layer], P.pooled[layer] + Mp * d.cout_s, dst, Mp, d.cout, d.cout_s, s);
     }
-    if (layer == nl - 3) {
-        const int cat_c = 4 * 512 + 1024;
-        return merge_planes_launch(P.concat + 2048, P.concat + M * cat_c + 2048, dst, M, d.cout, cat_c, s);
+    if (d.to_concat) {
+        const int cat_c = h->cat_c;
+        return merge_planes_launch(P.concat + (cat_c - d.cout_s), P.concat + M * cat_c + (cat_c - d.cout_s), dst, M, d.cout, cat_c, s);
     }
     Y2_REQUIRE(!(P.fused[layer] && !d.passthrough),
                "y2_get_activation: layer %d's max-pool is fused into its conv epilogue; the un-pooled tensor is not "
                "materialised (y2_set_option(h, \"fuse_pool\", 0) keeps it)", layer);
-    return merge_planes_launch(P.act[layer], P.act[layer] + M * d.cout, dst, M, d.cout, d.cout, s);
+    return merge_planes_launch(P.act[layer], P.act[layer] + M * d.cout_s, dst, M, d.cout, d.cout_s, s);
 }
 
 /* Options: "fuse_pool" (default 1) -- fuse the 2x2 max-pools into the conv epilogues when the shape allows it. */

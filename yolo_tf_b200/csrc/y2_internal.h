@@ -153,7 +153,8 @@ int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, in
 int bn_fold_launch(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                    float* scale, float* bias, int n, cudaStream_t s);
 int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
-                          int C, cudaStream_t s);
+                          int C, cudaStream_t s, int stride = 2);
+int pad_weights_launch(const float* w_hwio, float* out, int ksize, int cin, int cout, int cin_s, int cout_s, cudaStream_t s);
 // reorg (space-to-depth 2) on 16-byte vectors; elem_bytes in {2,4}; out row pitch in elements.
 int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes,
                  long long out_ld, cudaStream_t s);
@@ -204,6 +205,9 @@ size_t standardize_workspace_bytes(int B, size_t n);
 int standardize_launch(const void* x, int elem_bytes, int B, size_t n, float* out, void* ws, cudaStream_t s);
 int detections_launch(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold, float sx, float sy,
                       int* count, int* box, int* cls, float* score, float* xywh, cudaStream_t s);
+
+int transform_labels_launch(const int* ocls, const float* ocoord, const int* offsets, int B, int classes, int cw, int ch, float* mask,
+                            float* prob, float* coords, float* oxy_min, float* oxy_max, float* areas, int* status, cudaStream_t s);
 
 // ---- SIMT convs (y2_conv_simt.cu) ----
 // conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.

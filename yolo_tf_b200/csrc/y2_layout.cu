@@ -83,6 +83,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
         out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
+// HWIO [taps][cin][cout] -> HWIO [taps][cin_s][cout_s], zero-filled where the stored channel count is padded
+// (tiny: conv0's 16 outputs / conv1's 16 inputs are stored as 32 so the same kernels serve both networks).
+__global__ void pad_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int cin_s,
+                                   int cout_s) {
+    const size_t total = (size_t)taps * cin_s * cout_s;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % cout_s);
+        const size_t r = i / cout_s;
+        const int c = (int)(r % cin_s);
+        const size_t tap = r / cin_s;
+        out[i] = (n < cout && c < cin) ? __ldg(w + (tap * cin + c) * cout + n) : 0.f;
+    }
+}
+int pad_weights_launch(const float* w_hwio, float* out, int ksize, int cin, int cout, int cin_s, int cout_s, cudaStream_t s) {
+    const size_t total = (size_t)ksize * ksize * cin_s * cout_s;
+    pad_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, out, ksize * ksize, cin, cout, cin_s, cout_s);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
 int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad, cudaStream_t s) {
     const size_t total = (size_t)cout_pad * ksize * ksize * cin;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, wpack, ksize * ksize, cin, cout, cout_pad);
@@ -109,13 +129,15 @@ int bn_fold_launch(const float* gamma, const float* beta, const float* mean, con
     return 0;
 }
 
-// ---------------------------------------------------------------- 2x2/2 max-pool on planes
+// ---------------------------------------------------------------- 2x2 max-pool on planes (stride 2, or stride 1 SAME)
 // One thread = 8 channels of one pooled pixel (16-byte vectors of each plane).  The winner is
 // chosen on the exact value hi+lo (16 significand bits, exact in fp32) and its (hi,lo) pair copied.
+// stride 1 (tiny's last pool, model/yolo2/inference.py:42): TF SAME pads one row/column at the bottom/right only and
+// max-pool ignores padding, so the window of the last row/column is clipped (the clipped taps re-read a valid one).
 __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
                                       bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W,
-                                      int C) {
-    const int Ho = H / 2, Wo = W / 2, c8 = C / 8;
+                                      int C, int stride) {
+    const int Ho = H / stride, Wo = W / stride, c8 = C / 8;
     const size_t total = (size_t)B * Ho * Wo * c8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int cv = (int)(i % c8);
@@ -124,16 +146,17 @@ __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16
         t /= Wo;
         const int yo = (int)(t % Ho);
         const int b = (int)(t / Ho);
-        const size_t base = (((size_t)b * H + 2 * yo) * W + 2 * xo) * C + (size_t)cv * 8;
+        const size_t base = (((size_t)b * H + stride * yo) * W + stride * xo) * C + (size_t)cv * 8;
+        const size_t ox = (stride * xo + 1 < W) ? (size_t)C : 0, oy = (stride * yo + 1 < H) ? (size_t)W * C : 0;
         uint4 h[4], l[4];
         h[0] = __ldg(reinterpret_cast<const uint4*>(in_hi + base));
-        h[1] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + C));
-        h[2] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + (size_t)W * C));
-        h[3] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + (size_t)W * C + C));
+        h[1] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + ox));
+        h[2] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + oy));
+        h[3] = __ldg(reinterpret_cast<const uint4*>(in_hi + base + oy + ox));
         l[0] = __ldg(reinterpret_cast<const uint4*>(in_lo + base));
-        l[1] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + C));
-        l[2] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + (size_t)W * C));
-        l[3] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + (size_t)W * C + C));
+        l[1] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + ox));
+        l[2] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + oy));
+        l[3] = __ldg(reinterpret_cast<const uint4*>(in_lo + base + oy + ox));
         uint32_t oh[4], ol[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -159,10 +182,11 @@ __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16
     }
 }
 int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
-                          int C, cudaStream_t s) {
-    Y2_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C%%8, H%%2, W%%2 must be 0");
-    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-    maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C);
+                          int C, cudaStream_t s, int stride) {
+    Y2_REQUIRE(stride == 1 || stride == 2, "maxpool: stride must be 1 or 2");
+    Y2_REQUIRE(C % 8 == 0 && H % stride == 0 && W % stride == 0, "maxpool: C%%8, H%%stride, W%%stride must be 0");
+    const size_t total = (size_t)B * (H / stride) * (W / stride) * (C / 8);
+    maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C, stride);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -4,6 +4,8 @@
 //   detections                 <- detect.py:72-87: per box index = argmax_c conf (first maximum), kept iff conf[index] > threshold,
 //       box scaled from cell units to pixels (xy_min * scale, (xy_max - xy_min) * scale)
 // Both are HBM-bound passes; reductions are two-stage with fp64 partials and a fixed-order finish (deterministic).
+#include <limits.h>
+
 #include "y2_internal.h"
 
 namespace y2 {
@@ -143,6 +145,85 @@ detections_kernel(const float* __restrict__ conf, const float* __restrict__ xy_m
 int detections_launch(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold, float sx, float sy,
                       int* count, int* box, int* cls, float* score, float* xywh, cudaStream_t s) {
     detections_kernel<<<B, 256, 0, s>>>(conf, xy_min, xy_max, N, C, threshold, sx, sy, count, box, cls, score, xywh);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transform_labels (utils/data/__init__.py:112-145), batched: one block per image.  Phase 1 zero-fills the image's slice of
+// the six label tensors with 128-bit stores (this is the byte traffic: 4*cells*(C+10) B per image); phase 2 gives each
+// object a thread.  numpy's fancy-index assignment lets the LAST object that lands in a cell win mask/coords/offsets
+// (class bits accumulate over all of them): a thread writes those only if no later object of the image maps to its cell.
+// All arithmetic is float32 in the reference's evaluation order (float32 arrays x Python ints), round-to-nearest, no FMA.
+__device__ __forceinline__ int label_cell(const float* __restrict__ c, int cw, int ch, float* ox, float* oy) {
+    const float x = __fdiv_rn(__fmul_rn((float)cw, __fadd_rn(c[0], c[2])), 2.0f);      // cell_width * (xmin + xmax) / 2
+    const float y = __fdiv_rn(__fmul_rn((float)ch, __fadd_rn(c[1], c[3])), 2.0f);
+    const float ix = floorf(x), iy = floorf(y);
+    *ox = __fsub_rn(x, ix); *oy = __fsub_rn(y, iy);
+    const float fi = __fadd_rn(__fmul_rn(iy, (float)cw), ix);                          // (iy * cell_width + ix).astype(int)
+    if (!(fi > -2.0e9f && fi < 2.0e9f)) return INT_MIN;                                // NaN / overflow: out of range below
+    return (int)fi;
+}
+__global__ void __launch_bounds__(256)
+transform_labels_kernel(const int* __restrict__ ocls, const float* __restrict__ ocoord, const int* __restrict__ offsets, int classes,
+                        int cw, int ch, float* __restrict__ mask, float* __restrict__ prob, float* __restrict__ coords,
+                        float* __restrict__ oxy_min, float* __restrict__ oxy_max, float* __restrict__ areas, int* __restrict__ status) {
+    const int b = blockIdx.x, cells = cw * ch;
+    auto zero = [&](float* base, size_t n) {            // n floats at base (16-byte aligned when n % 4 == 0 per image; else scalar)
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+            float4* v = reinterpret_cast<float4*>(base);
+            for (size_t i = threadIdx.x; i < n / 4; i += blockDim.x) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (size_t i = threadIdx.x; i < n; i += blockDim.x) base[i] = 0.f;
+        }
+    };
+    zero(mask + (size_t)b * cells, cells);
+    zero(prob + (size_t)b * cells * classes, (size_t)cells * classes);
+    zero(coords + (size_t)b * cells * 4, (size_t)cells * 4);
+    zero(oxy_min + (size_t)b * cells * 2, (size_t)cells * 2);
+    zero(oxy_max + (size_t)b * cells * 2, (size_t)cells * 2);
+    zero(areas + (size_t)b * cells, cells);
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    const int o0 = offsets[b], n = offsets[b + 1] - o0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const float* c = ocoord + (size_t)(o0 + t) * 4;
+        float ox, oy;
+        int idx = label_cell(c, cw, ch, &ox, &oy);
+        const int k = ocls[o0 + t];
+        if (idx < 0 && idx >= -cells) idx += cells;                  // numpy wraps negative indices
+        if (idx < 0 || idx >= cells) { atomicOr(&bad, 1); continue; }        // IndexError in the reference
+        if (k < -classes || k >= classes) { atomicOr(&bad, 1); continue; }
+        prob[((size_t)b * cells + idx) * classes + (k < 0 ? k + classes : k)] = 1.0f;   // every object sets its class bit
+        bool last = true;
+        for (int j = t + 1; j < n && last; ++j) {
+            float tx, ty;
+            int ij = label_cell(ocoord + (size_t)(o0 + j) * 4, cw, ch, &tx, &ty);
+            if (ij < 0 && ij >= -cells) ij += cells;
+            if (ij == idx) last = false;
+        }
+        const float w = __fsub_rn(c[2], c[0]), h = __fsub_rn(c[3], c[1]);
+        const float hw = __fmul_rn(__fdiv_rn(w, 2.0f), (float)cw), hh = __fmul_rn(__fdiv_rn(h, 2.0f), (float)ch);   // w / 2 * cell_width
+        const float x0 = __fsub_rn(ox, hw), y0 = __fsub_rn(oy, hh), x1 = __fadd_rn(ox, hw), y1 = __fadd_rn(oy, hh);
+        const float dw = __fsub_rn(x1, x0), dh = __fsub_rn(y1, y0);
+        if (!(dw >= 0.f) || !(dh >= 0.f)) atomicOr(&bad, 2);         // `assert np.all(wh >= 0)` (:142)
+        if (!last) continue;
+        const size_t cell = (size_t)b * cells + idx;
+        mask[cell] = 1.0f;
+        coords[cell * 4 + 0] = ox; coords[cell * 4 + 1] = oy;
+        coords[cell * 4 + 2] = __fsqrt_rn(w); coords[cell * 4 + 3] = __fsqrt_rn(h);
+        oxy_min[cell * 2 + 0] = x0; oxy_min[cell * 2 + 1] = y0;
+        oxy_max[cell * 2 + 0] = x1; oxy_max[cell * 2 + 1] = y1;
+        areas[cell] = __fmul_rn(dw, dh);                             // np.multiply.reduce(offset_xy_max - offset_xy_min, -1)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && status) status[b] = bad;
+}
+int transform_labels_launch(const int* ocls, const float* ocoord, const int* offsets, int B, int classes, int cw, int ch, float* mask,
+                            float* prob, float* coords, float* oxy_min, float* oxy_max, float* areas, int* status, cudaStream_t s) {
+    transform_labels_kernel<<<B, 256, 0, s>>>(ocls, ocoord, offsets, classes, cw, ch, mask, prob, coords, oxy_min, oxy_max, areas, status);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -5,6 +5,10 @@
 The graph it stands for -- 21x (3x3|1x1 conv -> BN -> leaky), 5 max-pools, the passthrough reorg +
 concat, the final linear 1x1 conv -- runs as hand-written sm_100a kernels behind one C-ABI call
 (y2_darknet_forward); weights live in the variable store under the reference's TF names.
+
+``tiny`` (inference.py:25-50) is the second function the shipped configs select
+(config/yolo2/tiny-{20,80}.ini): the same kernels behind a different layer table (y2_create_net with
+Y2_ARCH_TINY); inference only.
 """
 import sys
 
@@ -42,15 +46,34 @@ def layer_geometry(classes, num_anchors):
     return t
 
 
+ARCH_DARKNET, ARCH_TINY = 0, 1      # Y2_ARCH_* (include/yolo2_b200.h)
+
+
+def tiny_layer_geometry(classes, num_anchors):
+    """[(name, ksize, cin, cout, has_bn, pool_after)] of tiny's 9 convs (inference.py:33-48); pool_after is
+    False, True (2x2 stride 2) or 's1' (2x2 stride 1 SAME, :42)."""
+    t, cin, ch = [], 3, 16
+    for _ in range(5):
+        t.append(("conv%d" % len(t), 3, cin, ch, True, True))
+        cin, ch = ch, ch * 2
+    t.append(("conv%d" % len(t), 3, cin, ch, True, 's1'))
+    cin, ch = ch, ch * 2
+    for _ in range(2):
+        t.append(("conv%d" % len(t), 3, cin, ch, True, False))
+        cin = ch
+    t.append(("conv", 1, ch, num_anchors * (5 + classes), False, False))
+    return t
+
+
 class _Engine(object):
-    """One y2_handle per (device, classes, anchors); re-uploads weights when the store changes."""
+    """One y2_handle per (device, classes, anchors, network); re-uploads weights when the store changes."""
     _cache = {}
 
-    def __init__(self, device_index, classes, num_anchors):
+    def __init__(self, device_index, classes, num_anchors, arch=ARCH_DARKNET):
         import ctypes
         self.h = ctypes.c_void_p()
-        _lib.check(_lib.lib().y2_create(ctypes.byref(self.h), device_index, classes, num_anchors))
-        self.classes, self.num_anchors = classes, num_anchors
+        _lib.check(_lib.lib().y2_create_net(ctypes.byref(self.h), device_index, classes, num_anchors, arch))
+        self.classes, self.num_anchors, self.arch = classes, num_anchors, arch
         self.loaded_version = None
         self.loaded_store = None
         self.ws = None
@@ -62,20 +85,20 @@ class _Engine(object):
             self.layers.append((k.value, cin.value, cout.value, bn.value))
 
     @classmethod
-    def get(cls, device, classes, num_anchors):
-        key = (device.index or 0, classes, num_anchors)
+    def get(cls, device, classes, num_anchors, arch=ARCH_DARKNET):
+        key = (device.index or 0, classes, num_anchors, arch)
         if key not in cls._cache:
-            cls._cache[key] = cls(key[0], classes, num_anchors)
+            cls._cache[key] = cls(key[0], classes, num_anchors, arch)
         return cls._cache[key]
 
-    def sync_weights(self, scope, store, device, center=True):
+    def sync_weights(self, scope, store, device, center=True, weights_initializer=V.xavier_uniform):
         if self.loaded_store is store and self.loaded_version == store.version:
             return
         L = _lib.lib()
         n = len(self.layers)
         for i, (k, cin, cout, bn) in enumerate(self.layers):
             name = "%s/conv%d" % (scope, i) if i < n - 1 else "%s/conv" % scope
-            w = store.get(name + "/weights", (k, k, cin, cout), V.xavier_uniform, device)
+            w = store.get(name + "/weights", (k, k, cin, cout), weights_initializer, device)
             if bn:
                 g = store.get(name + "/BatchNorm/gamma", (cout,), V.ones, device)
                 # center=False (the `_darknet` variant, inference.py:62-66): no beta, a separate `biases` variable added after BN
@@ -188,6 +211,32 @@ def darknet(net, classes, num_anchors, training=False, center=True, precision=No
 
 
 DARKNET_DOWNSAMPLING = (2 ** 5, 2 ** 5)      # inference.py:122
+
+
+def tiny(net, classes, num_anchors, training=False, center=True, precision=None):
+    """Tiny YOLOv2 backbone (inference.py:25-50): conv0..conv4 (16..256 channels, each + 2x2/2 max-pool), conv5 (512) +
+    2x2 stride-1 SAME max-pool, conv6/conv7 (1024), linear 1x1 conv.  Same signature and ``(scope, net)`` return as the
+    reference; scope == 'yolo2_tiny'.  Weights not present in the variable store are created with the reference's
+    initializer for this function (truncated_normal(stddev=0.1), :33).  Inference only: training=True raises."""
+    scope = __name__.split('.')[-2] + '_' + sys._getframe().f_code.co_name
+    if not net.is_cuda:
+        raise _lib.Y2Error("tiny: input must be a CUDA tensor (no CPU path exists)")
+    if training:
+        raise _lib.Y2Error("tiny: the training step (batch-statistics BN + backward) is only built for darknet")
+    eng = _Engine.get(net.device, classes, num_anchors, ARCH_TINY)
+    eng.sync_weights(scope, V.default_store(), net.device, center=center, weights_initializer=V.truncated_normal_01)
+    return scope, eng.forward(net.contiguous(), precision=PRECISION if precision is None else precision)
+
+
+TINY_DOWNSAMPLING = (2 ** 5, 2 ** 5)         # inference.py:52
+
+
+def _tiny(net, classes, num_anchors, training=False):
+    """inference.py:55-56: tiny with center=False (BN without beta + separate `biases`)."""
+    return tiny(net, classes, num_anchors, training, False)
+
+
+_TINY_DOWNSAMPLING = (2 ** 5, 2 ** 5)
 
 
 def _darknet(net, classes, num_anchors, training=False):

@@ -73,6 +73,17 @@ def xavier_uniform(shape):
     return _rs.uniform(-lim, lim, size=shape)
 
 
+def truncated_normal_01(shape):
+    """tf.truncated_normal_initializer(stddev=0.1) (tiny, model/yolo2/inference.py:33): N(0, 0.1) with draws beyond two
+    standard deviations re-drawn."""
+    out = _rs.normal(0.0, 0.1, size=shape)
+    bad = np.abs(out) > 0.2
+    while bad.any():
+        out[bad] = _rs.normal(0.0, 0.1, size=int(bad.sum()))
+        bad = np.abs(out) > 0.2
+    return out
+
+
 def zeros(shape):
     return np.zeros(shape)
 
