@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--precision", type=int, default=0, help="0 = split-bf16 x3 (fp32-grade parity), 1 = single bf16 pass")
+    ap.add_argument("--pair", type=int, default=-1, help="CTA-pair (cta_group::2) conv mode: -1 = library default, 0 off, 1 = 3x3 N=256 layers, 2 = all eligible")
     ap.add_argument("--cpu-images", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-report", default="", help="write the per-layer timing table (JSON) here")
@@ -232,6 +233,8 @@ def main():
     store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
     builder = Builder.from_values([str(i) for i in range(C)], size, size, ANCHORS_COCO)
     inference.PRECISION = args.precision
+    if args.pair >= 0:
+        _lib.check(L.y2_set_option(inference._Engine.get(dev, C, 5).h, b"pair", args.pair))
 
     rs = np.random.RandomState(100 + rank)
     host_in = [torch.from_numpy(rs.normal(0, 1, size=(B, size, size, 3)).astype(np.float32)).pin_memory()

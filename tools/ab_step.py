@@ -1,7 +1,7 @@
 """Same-box A/B of kernel options on the bench step (Darknet-19 forward + decode + NMS, B=32, 416, C=80): configurations
 are interleaved after a thermal warm-up so the power-cap clock drift hits all of them alike.  Diagnostic tool.
 Usage: python tools/ab_step.py "name:key=val,key=val" ...     keys = y2_debug_set ids (5 = PDL, 6 = TMA-store epilogue),
-       or halo=<v> / fuse_pool=<v> (y2_set_option).  Writes gpurun_out/ab_step.json."""
+       or halo=<v> / fuse_pool=<v> / pair=<v> (y2_set_option).  Writes gpurun_out/ab_step.json."""
 import ctypes
 import json
 import os
@@ -43,9 +43,9 @@ def main():
     eng = inference._Engine.get(torch.device("cuda:0"), C, 5)
 
     def apply(kvs):
-        for k, v in [("5", "1"), ("6", "1")]:
+        for k, v in [("5", "1"), ("6", "1"), ("3", "0"), ("8", "32")]:
             L.y2_debug_set(int(k), float(v))
-        opts = {"halo": 1, "fuse_pool": 1}
+        opts = {"halo": 1, "fuse_pool": 1, "pair": 1}
         for k, v in kvs:
             if k in opts:
                 opts[k] = int(v)

@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--classes", type=int, default=20)
+    ap.add_argument("--pair", type=int, default=-1, help="CTA-pair conv mode (y2_set_option 'pair'); -1 = library default")
     ap.add_argument("--timeline", default="", help="write a kernel timeline summary (torch.profiler / CUPTI) of 2 steps to this JSON")
     args = ap.parse_args()
     from yolo_tf_b200 import _lib, variables
@@ -73,6 +74,9 @@ def main():
     store = variables.reset_default_store()
     store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
     builder = Builder.from_values([str(i) for i in range(C)], size, size, ANCHORS_VOC, hparam=HPARAM)
+    if args.pair >= 0:
+        from yolo_tf_b200.model.yolo2 import inference
+        _lib.check(_lib.lib().y2_set_option(inference._Engine.get(dev, C, 5).h, b"pair", args.pair))
     rs = np.random.RandomState(100 + rank)
     x = torch.from_numpy(rs.normal(0, 1, size=(Bn, size, size, 3)).astype(np.float32)).to(dev)
     labels = [torch.from_numpy(t).to(dev) for t in synthetic_labels(Bn, C, size // 32, size // 32, 3 + rank)]

@@ -155,6 +155,7 @@ struct y2_handle {
     TrainPlan tplan;
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
+    int pair = 1;                      // y2_set_option("pair"): CTA-pair (cta_group::2) convs: 0 off, 1 = 3x3 layers with 256-wide N tiles, 2 = every eligible layer
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
     bool profiling = false;
@@ -361,8 +362,10 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
         const int halo = (h->halo && tc_conv_can_halo(B, oh, ow, L.d.cin_s, L.d.ksize, L.cout_pad, L.block_n, precision == 0)) ? h->halo : 0;
         const bool fuse = L.d.pool == 1 && h->fuse_pool && (halo || tc_conv_can_fuse_pool(B, oh, ow));
         P.fused[i] = fuse;
+        const int pair = (h->pair && tc_conv_can_pair(L.d.cin_s, L.block_n, halo) &&
+                          (h->pair >= 2 || (L.d.ksize == 3 && L.block_n == 256))) ? 1 : 0;
         if (tc_conv_plan(&T, input, B, oh, ow, L.d.cin_s, L.d.ksize, L.wpack, L.d.cout_s, L.cout_pad, L.block_n,
-                         0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0, halo))
+                         0, precision == 0, h->num_sms, P.streamk, fuse ? 1 : 0, halo, pair))
             return -1;
         ConvParams& p = T.p;
         if (fuse) {
@@ -491,11 +494,13 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
     return merge_planes_launch(P.act[layer], P.act[layer] + M * d.cout_s, dst, M, d.cout, d.cout_s, s);
 }
 
-/* Options: "fuse_pool" (default 1) -- fuse the 2x2 max-pools into the conv epilogues when the shape allows it. */
+/* Options: "fuse_pool" (default 1) -- fuse the 2x2 max-pools into the conv epilogues when the shape allows it;
+ * "halo" (default 1); "pair" -- CTA-pair convs (see y2_handle::pair). */
 int y2_set_option(y2_handle* h, const char* key, int value) {
     Y2_REQUIRE(h && key, "y2_set_option: null argument");
     if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }
     if (strcmp(key, "halo") == 0) { h->halo = value; h->plan.valid = false; return 0; }
+    if (strcmp(key, "pair") == 0) { h->pair = value; h->plan.valid = false; return 0; }
     set_error("y2_set_option: unknown option '%s'", key);
     return -1;
 }
@@ -523,7 +528,8 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
         if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s)) break;
         TcConvLaunch T;
         const int halo = (g_conv_force_halo && tc_conv_can_halo(B, H, W, cin, ksize, cpad, bn, precision == 0)) ? g_conv_force_halo : 0;
-        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk, 0, halo)) break;
+        const int pair = (g_conv_force_pair && tc_conv_can_pair(cin, bn, halo)) ? 1 : 0;
+        if (tc_conv_plan(&T, xp, B, H, W, cin, ksize, wp, cout, cpad, bn, max_ctas, precision == 0, num_sms, sk, 0, halo, pair)) break;
         T.p.scale = scale; T.p.bias = bias; T.p.leaky = leaky;
         T.p.out_f32 = y; T.p.ldc = cout; T.p.mode = EPI_F32;
         if (tc_conv_bind_output(&T)) break;
@@ -557,6 +563,8 @@ int y2_debug_set(int key, double value) {
     else if (key == 1) g_sched_handoff_kb = value;
     else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
     else if (key == 4) g_conv_force_halo = (int)value;
+    else if (key == 8) g_conv_kcap = (int)value;            // longest tensor-core accumulation chain in k-blocks (0 = unlimited; default 32)
+    else if (key == 7) g_conv_force_pair = (int)value;      // y2_conv2d: CTA-pair mode where applicable
     else if (key == 6) g_conv_tma_store = (int)value;       // TMA-store epilogue (default 1)
     else if (key == 5) g_conv_pdl = (int)value;             // programmatic dependent launch of the conv kernels (default 1)      // y2_conv2d: halo mode (1|2) where applicable
     else if (key == 2) { if (value != 0 && !g_dbg_host) g_dbg_host = new unsigned long long[1024 * 4]; if (value == 0) { delete[] g_dbg_host; g_dbg_host = nullptr; } }

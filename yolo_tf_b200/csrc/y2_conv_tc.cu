@@ -91,20 +91,62 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int BK, bool SPLIT3>
+// Accumulation-chain cap.  The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so a long chain
+// biases the sum towards zero by ~(chain length) x 2^-24 -- measured: the 13x13 layers at batch 32 (171 k-blocks per
+// chain) carried 1.9e-4 to the network output against 4e-5 with 6-k-block chains (tools/diag_layers.py).  Segments of the
+// schedule are therefore cut into sub-segments of at most `cap` k-blocks, each accumulated from zero in the next TMEM
+// buffer; the epilogue warps (idle during the main loop) add the sub-results with round-to-nearest fp32 adds in the CTA's
+// own partial slot.  The producer never notices; the MMA warp only sees more, shorter "segments".
+struct CapIter {
+    SegIter it;
+    int cap, tile_, a, b, pos;
+    __device__ __forceinline__ void init(int worker, int nworkers, int dp_tiles, int sk_ctas, long long sk_total, int KB, int cap_) {
+        it.init_w(worker, nworkers, dp_tiles, sk_ctas, sk_total, KB);
+        cap = cap_ > 0 ? cap_ : 0x7fffffff;
+        a = b = pos = 0; tile_ = 0;
+    }
+    // [kb0, kb1) = next sub-segment of segment [seg_a, seg_b) of `tile`
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& seg_a, int& seg_b) {
+        if (pos >= b) {
+            if (!it.next(tile_, a, b)) return false;
+            pos = a;
+        }
+        const int len = b - pos;
+        int step = len;
+        if (len > cap) {                              // equal pieces, none longer than cap
+            const int n = (len + cap - 1) / cap;
+            step = (len + n - 1) / n;
+        }
+        tile = tile_; kb0 = pos; kb1 = pos + step; seg_a = a; seg_b = b;
+        pos = kb1;
+        return true;
+    }
+};
+
+// PAIR: the kernel runs as clusters of two CTAs (the two SMs of a TPC) that share one tcgen05.mma.cta_group::2 stream:
+// a pair owns a 256-row M tile (CTA rank r: rows r*128..), each CTA stages its own A rows and HALF of the B tile, rank 0
+// issues M = 256 MMAs whose accumulator rows live in each CTA's own TMEM.  Per k-block a CTA's shared memory then sees
+// 64 KiB of TMA writes + 96 KiB of MMA reads instead of 96 + 144 (the main loop was shared-memory-bandwidth bound,
+// profiles/README.md).  `worker` (the pair) replaces the CTA in the tile schedule; partial slots and flags stay per CTA.
+template <int BK, bool SPLIT3, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_o, const ConvParams p) {
     constexpr int ROW_BYTES = BK * 2;                       // 128 (SW128) or 64 (SW64)
     constexpr int A_TILE = BLOCK_M * ROW_BYTES;
     constexpr int PLANES = SPLIT3 ? 2 : 1;
+    constexpr int NCTA = PAIR ? 2 : 1;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic)
     uint8_t* smem0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem = smem0 + p.stg_bytes;                    // [store staging | resident weights | ring | scale/bias | barriers]
 
-    const int b_tile = p.block_n * ROW_BYTES;
-    const int stage_bytes = p.halo ? PLANES * p.halo_plane_bytes : PLANES * (A_TILE + b_tile);
+    const int b_rows = p.block_n / NCTA;                    // rows of the B (weight) tile this CTA stages
+    const int b_tile = b_rows * ROW_BYTES;
+    const int stage_bytes = (!PAIR && p.halo) ? PLANES * p.halo_plane_bytes : PLANES * (A_TILE + b_tile);
     const int S = p.num_stages;
     uint8_t* ring = smem + p.bres_bytes;                    // halo mode keeps the weights of all taps below the ring
     float* sb = reinterpret_cast<float*>(ring + (size_t)S * stage_bytes);       // [2][256]
@@ -131,14 +173,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], 4 * NCTA);               // the epilogue warps of both CTAs release rank 0's accumulator
         }
         mbar_init(bres, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        else tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                            // the peer's barriers exist before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the
@@ -158,19 +204,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t leader = elect_one() ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
-        if (BK == 32 && p.halo && !(p.dbg_flags & 1)) {      // all 9 taps of the packed weights: once per CTA
+        CapIter it;
+        it.init(worker, nworkers, p.dp_tiles, p.sk_ctas, sk_total, KB, p.kcap);
+        int tile, kb0, kb1, seg_a, seg_b;
+        if (!PAIR && BK == 32 && p.halo && !(p.dbg_flags & 1)) {      // all 9 taps of the packed weights: once per CTA
             mbar_expect_tx_e(leader, bres, (uint32_t)(9 * PLANES * b_tile));
             for (int tap = 0; tap < 9; ++tap) {
                 tma_load_2d_e(leader, smem + (size_t)(tap * PLANES) * b_tile, &map_w, bres, tap * BK, 0);
                 if (SPLIT3) tma_load_2d_e(leader, smem + (size_t)(tap * PLANES + 1) * b_tile, &map_w, bres, tap * BK, p.cout_pad);
             }
         }
-        while (it.next(tile, kb0, kb1)) {
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {
             const int nt = tile / p.m_tiles;
-            const int mt = tile - nt * p.m_tiles;
+            const int mt = (tile - nt * p.m_tiles) * NCTA + rank;     // this CTA's 128-row tile
             int img, y0, x0;
             if (p.tx) {                                      // spatial tile (tx x ty pixels x tb images)
                 const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
@@ -184,7 +230,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             // __shfl_sync(.., 0) marks a value warp-uniform for ptxas, so the TMA operands stay in uniform registers
             x0 = __shfl_sync(0xffffffffu, x0, 0); y0 = __shfl_sync(0xffffffffu, y0, 0); img = __shfl_sync(0xffffffffu, img, 0);
-            const int n0 = __shfl_sync(0xffffffffu, nt * p.block_n, 0);
+            const int n0 = __shfl_sync(0xffffffffu, nt * p.block_n + rank * b_rows, 0);   // pair: this CTA's half of the B tile
             int tap = kb0 / cblocks;
             int cb = kb0 - tap * cblocks;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -194,7 +240,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tap = __shfl_sync(0xffffffffu, tap, 0); cb = __shfl_sync(0xffffffffu, cb, 0);
                 uint8_t* st = ring + (size_t)stage * stage_bytes;
                 if (p.dbg_flags & 1) {                       // diagnostics: no loads, the MMAs read whatever is there
-                    mbar_arrive_e(leader, &full[stage]);
+                    if (rank == 0) mbar_arrive_e(leader, &full[stage]);
+                } else if (PAIR) {
+                    // both CTAs' bytes complete on rank 0's barrier, which expects them all
+                    const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+                    const int c0 = cb * BK;
+                    const int dy = (p.ksize == 3) ? tap / 3 : 0;
+                    const int dx = (p.ksize == 3) ? tap - dy * 3 : 0;
+                    if (rank == 0) mbar_expect_tx_e(leader, &full[stage], (uint32_t)(2 * stage_bytes));
+                    if (p.tx) {
+                        tma_load_4d_pair_e(leader, st, &map_a, fb, c0, x0 + dx - pad, y0 + dy - pad, img);
+                        if (SPLIT3) tma_load_4d_pair_e(leader, st + A_TILE, &map_a, fb, c0, x0 + dx - pad, y0 + dy - pad, img + p.B);
+                    } else {
+                        tma_load_im2col_4d_pair_e(leader, st, &map_a, fb, c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                        if (SPLIT3)
+                            tma_load_im2col_4d_pair_e(leader, st + A_TILE, &map_a, fb, c0, x0 - pad, y0 - pad, img + p.B,
+                                                      (uint16_t)dx, (uint16_t)dy);
+                    }
+                    uint8_t* sbt = st + PLANES * A_TILE;
+                    const int kcoord = tap * p.Cin + c0;
+                    tma_load_2d_pair_e(leader, sbt, &map_w, fb, kcoord, n0);
+                    if (SPLIT3) tma_load_2d_pair_e(leader, sbt + b_tile, &map_w, fb, kcoord, p.cout_pad + n0);
                 } else if (BK == 32 && p.halo) {             // one halo fetch serves all 9 taps of this tile
                     mbar_expect_tx_e(leader, &full[stage], (uint32_t)(PLANES * p.halo_tx_bytes));
                     tma_load_4d_e(leader, st, &map_a, &full[stage], 0, x0 - 1, y0 - 1, img);
@@ -225,10 +291,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues; pair: rank 0 only) ==========
         const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+        const uint32_t idesc = make_idesc_bf16(BLOCK_M * NCTA, (uint32_t)p.block_n);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -236,10 +302,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         bool bres_ready = false;
         const uint32_t ring_u32 = smem_u32(ring);
         const uint32_t bres_u32 = smem_u32(smem);
-        SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
-        while (it.next(tile, kb0, kb1)) {
+        CapIter it;
+        it.init(worker, nworkers, p.dp_tiles, p.sk_ctas, sk_total, KB, p.kcap);
+        int tile, kb0, kb1, seg_a, seg_b;
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {              // every sub-segment: a fresh accumulator buffer
             mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
             __syncwarp();
             tc_fence_after();
@@ -251,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tc_fence_after();
                 stage = __shfl_sync(0xffffffffu, stage, 0);
                 const uint32_t st = ring_u32 + (uint32_t)(stage * stage_bytes);
-                if (BK == 32 && p.halo) {
+                if (!PAIR && BK == 32 && p.halo) {
                     if (!bres_ready) {
                         if (!(p.dbg_flags & 1)) mbar_wait(bres, 0u, 0x310u);
                         __syncwarp();
@@ -293,21 +359,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint32_t koff = (uint32_t)(k * 2);   // 16 bf16 = 32 bytes along K inside the swizzle row (>> 4)
+                            if (PAIR) {
+                                tc_mma_f16_pair_e(leader, d_tmem, da_hi + koff, hd, db_hi + koff, hd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                                if (SPLIT3) {
+                                    tc_mma_f16_pair_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc, 1u);
+                                    tc_mma_f16_pair_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc, 1u);
+                                }
+                            } else {
                             tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_hi + koff, hd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                             if (SPLIT3) {
                                 tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc, 1u);
                                 tc_mma_f16_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc, 1u);
                             }
+                            }
                         }
                     }
                 }
-                tc_commit_e(leader, &empty[stage]);                  // smem slot reusable once these MMAs retire
+                if (PAIR) tc_commit_pair_e(leader, &empty[stage]);   // (both CTAs' slots)
+                else tc_commit_e(leader, &empty[stage]);             // smem slot reusable once these MMAs retire
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1u;
                 }
             }
-            tc_commit_e(leader, &tfull[acc]);                        // accumulator complete -> epilogue
+            if (PAIR) tc_commit_pair_e(leader, &tfull[acc]);         // (both CTAs' epilogues)
+            else tc_commit_e(leader, &tfull[acc]);                   // accumulator complete -> epilogue
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -320,14 +396,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t store_seq = 0;
         const uint32_t stg_base = smem_u32(smem0) + (uint32_t)(q * p.store_bufs * 4096);
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
-        SegIter it;
-        it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
+        // running sum of a segment's sub-segments: a slot of its own (the partial slot may still hold this CTA's contribution
+        // to the previous tile, not yet collected by that tile's head).  Only this thread ever reads what it writes there, so
+        // the layout is [32-column chunk][16-byte piece][row]: a warp's 32 rows form one contiguous 512 B run per access
+        // instead of 32 lines 1 KiB apart (the main loop is sensitive to every extra L2 request).
+        float4* run4 = reinterpret_cast<float4*>(p.sk_run + (size_t)blockIdx.x * BLOCK_M * p.block_n) + (q * 32 + lane);
+        CapIter it;
+        it.init(worker, nworkers, p.dp_tiles, p.sk_ctas, sk_total, KB, p.kcap);
+        const uint32_t tempty_r0 = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u, tempty_r1 = PAIR ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u;
+        int tile, kb0, kb1, seg_a, seg_b;
         if (p.dbg && et == 0) { p.dbg[blockIdx.x * 4 + 0] = gtime_ns(); p.dbg[blockIdx.x * 4 + 1] = 0; p.dbg[blockIdx.x * 4 + 2] = 0; }
-        while (it.next(tile, kb0, kb1)) {
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {
             if (p.dbg && et == 0 && tile >= p.dp_tiles && p.dbg[blockIdx.x * 4 + 1] == 0) p.dbg[blockIdx.x * 4 + 1] = gtime_ns();
             const int nt = tile / p.m_tiles;
-            const int mt = tile - nt * p.m_tiles;
+            const int mt = (tile - nt * p.m_tiles) * NCTA + rank;
             const int n0 = nt * p.block_n;
             long long row = (long long)mt * BLOCK_M + q * 32 + lane;
             size_t pool_row = 0;
@@ -339,11 +421,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 row = ((long long)pb * p.H + py) * p.W + px;
                 pool_row = ((size_t)pb * (p.H / 2) + py / 2) * (p.W / 2) + px / 2;
             }
-            const bool row_ok = row < p.M;
-            const bool is_head = (kb0 == 0);                 // owns the tile's output
-            // stream-K CTAs blockIdx.x+1 .. last_contrib start inside this tile and hold its other k-ranges
-            int last_contrib = blockIdx.x;
-            if (is_head && kb1 < KB) {
+            const bool row_ok = row < p.M && mt < p.m_tiles128;      // (pair: the odd last 128-row tile has no partner rows)
+            const bool first_sub = (kb0 == seg_a), last_sub = (kb1 == seg_b);   // position in this CTA's accumulation chain
+            const bool is_head = (seg_a == 0) && last_sub;   // owns the tile's output (written after its last sub-segment)
+            // stream-K workers worker+1 .. last_contrib start inside this tile and hold its other k-ranges
+            int last_contrib = worker;
+            if (is_head && seg_b < KB) {
                 const long long tile_end = (long long)(tile - p.dp_tiles + 1) * KB;
                 while (last_contrib + 1 < p.sk_ctas && sk_total * (last_contrib + 1) / p.sk_ctas < tile_end) ++last_contrib;
             }
@@ -365,9 +448,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
             tc_fence_after();
             // the other contributors ran at the START of their ranges: normally long done
-            if (p.dbg && et == 0 && last_contrib > (int)blockIdx.x) p.dbg[blockIdx.x * 4 + 2] = gtime_ns();   // own MMAs done, start waiting
-            for (int h = blockIdx.x + 1; h <= last_contrib; ++h) {
-                if (lane == 0) flag_wait(p.sk_flags + h, p.epoch, 0x500u);
+            if (p.dbg && et == 0 && last_contrib > worker) p.dbg[blockIdx.x * 4 + 2] = gtime_ns();   // own MMAs done, start waiting
+            for (int h = worker + 1; h <= last_contrib; ++h) {       // (pair: the contributor CTA of the same rank)
+                if (lane == 0) flag_wait(p.sk_flags + h * NCTA + rank, p.epoch, 0x500u);
                 __syncwarp();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
@@ -375,7 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // is always this CTA's last segment) smem ring with cp.async, one 32-column chunk ahead, so the adds never
             // wait on an L2 round trip per contributor.  Each thread copies and later reads only its own row slot
             // (128 B, 16-byte pieces XOR-swizzled by row against bank conflicts): no cross-thread sync needed.
-            const int ncontrib = last_contrib - (int)blockIdx.x;
+            const int ncontrib = last_contrib - worker;
             const int max_staged = (int)(((size_t)S * stage_bytes) / (2u * BLOCK_M * 128u));
             const int nstaged = ncontrib < max_staged ? ncontrib : max_staged;
             const int rr = q * 32 + lane;
@@ -384,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             };
             auto stage_issue = [&](int c, int buf) {
                 for (int hh = 0; hh < nstaged; ++hh) {
-                    const float* src = p.sk_partial + (size_t)(blockIdx.x + 1 + hh) * BLOCK_M * p.block_n + (size_t)rr * p.block_n + c;
+                    const float* src = p.sk_partial + (size_t)((worker + 1 + hh) * NCTA + rank) * BLOCK_M * p.block_n + (size_t)rr * p.block_n + c;
                     const uint32_t dst = stage_slot(buf, hh);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -401,7 +484,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (c + 32 < p.block_n) tmem_ld_32x32b_x32(t_row + (uint32_t)(c + 32), v);   // next chunk streams in behind the math
-                if (!is_head) {                              // raw partial -> this CTA's slot
+                float4* own = run4 + (size_t)(c >> 5) * 8 * BLOCK_M;
+                if (!first_sub && !(p.dbg_flags & 4)) {      // running sum of the earlier sub-segments (this thread wrote it)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = __ldcg(own + j * BLOCK_M);
+                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                    }
+                }
+                if (!last_sub) {                             // running sum -> this CTA's private slot
+                    if (!(p.dbg_flags & 8)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(own + j * BLOCK_M, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    }
+                    continue;
+                }
+                if (!is_head) {                              // raw partial -> this CTA's slot (row layout: the tile's head reads it)
                     float4* dst = reinterpret_cast<float4*>(my_partial + c);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
@@ -427,9 +525,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                 }
-                for (int h = blockIdx.x + 1 + nstaged; h <= last_contrib; ++h) {      // overflow (tiny-K corner): direct loads
+                for (int h = worker + 1 + nstaged; h <= last_contrib; ++h) {      // overflow (tiny-K corner): direct loads
                     const float4* src = reinterpret_cast<const float4*>(
-                        p.sk_partial + (size_t)h * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n + c);
+                        p.sk_partial + (size_t)(h * NCTA + rank) * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n + c);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 t = __ldcg(src + j);
@@ -540,8 +638,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (!is_head) {                                  // publish the partial: all 128 rows written -> flag
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(acc ? tempty_r1 : tempty_r0);
+                else mbar_arrive(&tempty[acc]);
+            }
+            if (!is_head && last_sub) {                      // publish the partial: all 128 rows written -> flag
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (et == 0) flag_set(p.sk_flags + blockIdx.x, p.epoch);
@@ -555,9 +656,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // neither CTA's shared memory / TMEM goes away while the other can still touch it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -587,22 +690,31 @@ static int load_driver_entry_points() {
     return 0;
 }
 
-template <int BK, bool SPLIT3>
+template <int BK, bool SPLIT3, bool PAIR>
 static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<BK, SPLIT3>;
+    auto kern = conv_tc_kernel<BK, SPLIT3, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
         Y2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
-    if (g_conv_pdl) {
+    if (g_conv_pdl || PAIR) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (g_conv_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (PAIR) {                                  // CTA pair = cluster of 2 (the two SMs of one TPC)
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr; cfg.numAttrs = na;
         Y2_CUDA(cudaLaunchKernelEx(&cfg, kern, L.map_a, L.map_w, L.map_o, L.p));
     } else {
         kern<<<L.grid, NUM_THREADS, L.smem_bytes, stream>>>(L.map_a, L.map_w, L.map_o, L.p);
@@ -614,15 +726,43 @@ static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
 
 static std::atomic<unsigned int> g_epoch{0};
 
-size_t tc_conv_streamk_bytes(int num_sms) { return (size_t)num_sms * (BLOCK_M * 256 * sizeof(float)) + 4096; }
+// flags page + one partial tile and one running-sum tile per CTA
+size_t tc_conv_streamk_bytes(int num_sms) { return 2 * (size_t)num_sms * (BLOCK_M * 256 * sizeof(float)) + 4096; }
 
 int tc_conv_launch(const TcConvLaunch& Lc, cudaStream_t stream) {
     TcConvLaunch L = Lc;
     unsigned int e = g_epoch.fetch_add(1) + 1;
     if (e == 0) e = g_epoch.fetch_add(1) + 1;          // 0 is the "never written" value of a fresh flag buffer
     L.p.epoch = e;
-    if (L.block_k == 64) return L.split3 ? launch_inst<64, true>(L, stream) : launch_inst<64, false>(L, stream);
-    return L.split3 ? launch_inst<32, true>(L, stream) : launch_inst<32, false>(L, stream);
+    if (L.p.pair) return L.split3 ? launch_inst<64, true, true>(L, stream) : launch_inst<64, false, true>(L, stream);
+    if (L.block_k == 64) return L.split3 ? launch_inst<64, true, false>(L, stream) : launch_inst<64, false, false>(L, stream);
+    return L.split3 ? launch_inst<32, true, false>(L, stream) : launch_inst<32, false, false>(L, stream);
+}
+
+// CTA pairs that can be co-resident (every worker of the persistent schedule must be: stream-K heads spin on the flags of
+// later workers).  Queried once per kernel instantiation with the real shared-memory size.
+static int max_active_pairs(int split3, int smem_bytes) {
+    static int cached[2] = {-1, -1};
+    if (cached[split3 ? 1 : 0] >= 0) return cached[split3 ? 1 : 0];
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e;
+    if (split3) {
+        cudaFuncSetAttribute(conv_tc_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        e = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<64, true, true>, &cfg);
+    } else {
+        cudaFuncSetAttribute(conv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        e = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<64, false, true>, &cfg);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cached[split3 ? 1 : 0] = n;
+    return n;
 }
 
 int tc_conv_check_watchdog() {
@@ -689,7 +829,13 @@ int tc_conv_bind_output(TcConvLaunch* L) {
     return 0;
 }
 
-int g_conv_dbg_flags = 0, g_conv_force_halo = 0, g_conv_pdl = 1, g_conv_tma_store = 1;
+int g_conv_dbg_flags = 0, g_conv_force_halo = 0, g_conv_pdl = 1, g_conv_tma_store = 1, g_conv_force_pair = 0, g_conv_kcap = 32;
+
+// CTA-pair mode: 64-channel k-blocks (SW128 operands), an even split of the N tile in 8-row swizzle groups, N a multiple of
+// 16 (the cta_group::2 MMA shape rule); halo mode keeps the single-CTA kernel.
+bool tc_conv_can_pair(int Cin, int block_n, int halo) {
+    return !halo && Cin % 64 == 0 && block_n % 16 == 0 && (block_n / 2) % 8 == 0 && block_n >= 32;
+}
 
 // Halo mode: 3x3, 32 input channels, a single N tile whose 9 weight taps fit next to the halo ring.
 bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int block_n, int split3) {
@@ -701,7 +847,7 @@ bool tc_conv_can_halo(int B, int H, int W, int Cin, int ksize, int cout_pad, int
 
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize, const bf16* wpack,
                  int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms, void* sk_ws, int fuse_pool,
-                 int halo) {
+                 int halo, int pair) {
     if (load_driver_entry_points()) return -1;
     Y2_REQUIRE(ksize == 1 || ksize == 3, "tc conv: ksize must be 1 or 3 (got %d)", ksize);
     Y2_REQUIRE(Cin % 32 == 0, "tc conv: Cin must be a multiple of 32 (got %d)", Cin);
@@ -734,6 +880,12 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
         p.halo_plane_bytes = 12288;                              // 1 KiB multiple: swizzle phase identical per plane
         p.bres_bytes = 9 * (split3 ? 2 : 1) * block_n * 64;
     }
+    p.m_tiles128 = p.m_tiles;
+    if (pair) {
+        Y2_REQUIRE(tc_conv_can_pair(Cin, block_n, halo), "tc conv: CTA-pair mode not applicable (Cin=%d block_n=%d halo=%d)", Cin, block_n, halo);
+        p.pair = 1;
+        p.m_tiles = (p.m_tiles128 + 1) / 2;                      // a pair owns two consecutive 128-row tiles
+    }
     p.dbg_flags = g_conv_dbg_flags;
     p.n_tiles = cout_pad / block_n;
     p.kblocks_total = halo ? 1 : taps * (Cin / BK);
@@ -741,8 +893,11 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     Y2_REQUIRE(sk_ws && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0, "tc conv: stream-K workspace missing/unaligned");
     p.sk_flags = static_cast<unsigned int*>(sk_ws);                         // [num_sms] (first 4 KiB)
     p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
+    p.sk_run = p.sk_partial + (size_t)num_sms * BLOCK_M * 256;
+    p.kcap = g_conv_kcap;
     const int planes = split3 ? 2 : 1;
-    const int stage_bytes = halo ? planes * p.halo_plane_bytes : planes * (BLOCK_M * BK * 2 + block_n * BK * 2);
+    const int b_rows = pair ? block_n / 2 : block_n;            // weight-tile rows staged per CTA
+    const int stage_bytes = halo ? planes * p.halo_plane_bytes : planes * (BLOCK_M * BK * 2 + b_rows * BK * 2);
     if (p.tx == 0 && g_conv_tma_store) {          // linear tiles: room for the TMA-store staging slabs (2 per warp if the ring keeps its depth)
         const int avail = SMEM_LIMIT - 1024 - SB_BYTES - BAR_BYTES;
         int st0 = avail / stage_bytes; if (st0 > 8) st0 = 8;
@@ -758,9 +913,16 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     L->smem_bytes = stages * stage_bytes + 1024 + SB_BYTES + BAR_BYTES + p.bres_bytes + p.stg_bytes;
     L->block_k = BK;
     L->split3 = split3 ? 1 : 0;
-    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, num_sms, max_ctas, (block_n / 256.0) * (BK / 64.0),
+    int workers = num_sms;
+    if (pair) {
+        workers = max_active_pairs(split3, L->smem_bytes);
+        Y2_REQUIRE(workers >= 1, "tc conv: no CTA pair can be resident (cluster launch unavailable?)");
+        if (workers > num_sms / 2) workers = num_sms / 2;
+    }
+    choose_schedule((long long)p.m_tiles * p.n_tiles, p.kblocks_total, workers, max_ctas, (block_n / 256.0) * (BK / 64.0),
                     (size_t)planes * cout_pad * taps * Cin * sizeof(bf16), &p.dp_tiles,
                     &p.sk_ctas, &L->grid);
+    if (pair) L->grid *= 2;
     if (halo) {                                                  // one k-block per tile: plain data-parallel waves
         p.dp_tiles = p.m_tiles; p.sk_ctas = 0;
         L->grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
@@ -818,7 +980,7 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
         const cuuint64_t K = (cuuint64_t)taps * Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)(2 * cout_pad)};
         cuuint64_t strides[1] = {K * 2};
-        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)block_n};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)b_rows};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = g_encodeTiled(&L->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(wpack), dims,
                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -60,6 +60,7 @@ struct ConvParams {
     bf16* out_lo;
     float* out_f32;          // EPI_F32
     float* sk_partial;       // stream-K: [grid][128][block_n] raw fp32 partial tiles
+    float* sk_run;           // [grid][128][block_n] running sums of capped accumulation chains (head segments)
     unsigned int* sk_flags;  // stream-K: [grid] hand-off flags (value = launch epoch)
     unsigned int epoch;      // set per launch
     unsigned long long* dbg; // optional [grid][4] globaltimer stamps: start, stream-K phase start, hand-off wait start, end
@@ -73,8 +74,13 @@ struct ConvParams {
     // 4 warps x store_bufs x 4 KiB at the start of dynamic shared memory; tma_store is set by tc_conv_bind_output.
     int tma_store, store_bufs, stg_bytes;
     int dbg_flags;           // diagnostics: 1 = skip TMA loads, 2 = skip MMAs
+    // CTA-pair mode (cta_group::2): m_tiles counts 256-row pair tiles, m_tiles128 the 128-row tiles that exist
+    int pair, m_tiles128;
+    int kcap;                // longest accumulation chain in k-blocks (0 = unlimited), see CapIter
 };
 extern int g_conv_tma_store;   // 1 = TMA-store epilogue where the layout allows it
+extern int g_conv_kcap;        // ConvParams::kcap of the convs planned from now on (default 32)
+extern int g_conv_force_pair;  // y2_conv2d: run eligible convs as CTA pairs (diagnostics / tests)
 extern int g_conv_dbg_flags, g_conv_force_halo, g_conv_pdl;   // g_conv_pdl: launch convs with programmatic stream serialization
 
 // Hybrid schedule for `tiles` output tiles of `KB` k-blocks on `ctas` persistent CTAs (max_ctas > 0 caps it):
@@ -130,7 +136,9 @@ struct TcConvLaunch {
 // wpack: bf16 [2][cout_pad][ksize*ksize*Cin] (k = tap*Cin + c).  Returns 0 or <0 (error set).
 int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, int Cin, int ksize,
                  const bf16* wpack, int cout, int cout_pad, int block_n, int max_ctas, int split3, int num_sms,
-                 void* streamk_ws, int fuse_pool = 0, int halo = 0);
+                 void* streamk_ws, int fuse_pool = 0, int halo = 0, int pair = 0);
+// true when the layer can run as CTA pairs (cta_group::2 MMAs, see conv_tc_kernel)
+bool tc_conv_can_pair(int Cin, int block_n, int halo);
 // Call after the output pointers / pitch / mode of L->p are final: builds the output tensor map and enables the TMA-store
 // epilogue when the layout allows it (linear tiles, 16-byte pitches); otherwise the per-thread store path stays.
 int tc_conv_bind_output(TcConvLaunch* L);

@@ -191,6 +191,72 @@ __device__ __forceinline__ void tc_commit_e(uint32_t leader, uint64_t* bar) {
                  "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
                  ::"r"(smem_u32(bar)), "r"(leader) : "memory");
 }
+// ---------------------------------------------------------------- CTA pair (cta_group::2): two SMs of one TPC, one MMA
+// The pair is a cluster of 2.  Rank 0 issues every tcgen05.mma for both SMs (M = 256: each CTA's TMEM holds its own 128 rows,
+// each CTA's shared memory holds its own A rows and HALF of the B tile); both CTAs' TMA loads complete on rank 0's barrier;
+// tcgen05.commit multicasts its arrival to the barrier at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {                                    // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {   // one warp (same warp id) in EACH CTA
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair_e(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred pe, p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_e(uint32_t leader, uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("{\n\t.reg .pred pe;\n\t.reg .b16 mask;\n\tsetp.ne.b32 pe, %1, 0;\n\tmov.b16 mask, 3;\n\t"
+                 "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mask;\n\t}\n"
+                 ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+// TMA loads of a pair: destination = this CTA's shared memory, completion bytes -> `bar_cluster` (rank 0's barrier)
+__device__ __forceinline__ void tma_load_2d_pair_e(uint32_t leader, void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_e(uint32_t leader, void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                   int c2, int c3) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %7, 0;\n\t"
+        "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair_e(uint32_t leader, void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c,
+                                                          int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %9, 0;\n\t"
+        "@pe cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}\n"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c), "r"(w), "r"(h),
+        "r"(n), "h"(off_w), "h"(off_h), "r"(leader)
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -224,10 +290,14 @@ struct SegIter {
     int dp_next, dp_tiles, stride, KB;
     long long cur, end;
     __device__ __forceinline__ void init(int dp_tiles_, int sk_ctas, long long sk_total, int KB_) {
-        dp_next = blockIdx.x; dp_tiles = dp_tiles_; stride = gridDim.x; KB = KB_;
-        if ((int)blockIdx.x < sk_ctas) {
-            cur = sk_total * blockIdx.x / sk_ctas;
-            end = sk_total * (blockIdx.x + 1) / sk_ctas;
+        init_w((int)blockIdx.x, (int)gridDim.x, dp_tiles_, sk_ctas, sk_total, KB_);
+    }
+    // worker = CTA (or CTA pair) index, nworkers = how many walk the schedule
+    __device__ __forceinline__ void init_w(int worker, int nworkers, int dp_tiles_, int sk_ctas, long long sk_total, int KB_) {
+        dp_next = worker; dp_tiles = dp_tiles_; stride = nworkers; KB = KB_;
+        if (worker < sk_ctas) {
+            cur = sk_total * worker / sk_ctas;
+            end = sk_total * (worker + 1) / sk_ctas;
         } else {
             cur = end = 0;
         }
