@@ -81,6 +81,13 @@ __device__ __forceinline__ void bulk_wait_read(int pending) {     // pending in 
     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 1-D bulk copies shared -> global: plain store, and fp32 add performed by the L2 (no read back to the SM)
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32_1d(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 
 // (x0, x1) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi); one packed convert per pair of values.
 __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -400,7 +407,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // to the previous tile, not yet collected by that tile's head).  Only this thread ever reads what it writes there, so
         // the layout is [32-column chunk][16-byte piece][row]: a warp's 32 rows form one contiguous 512 B run per access
         // instead of 32 lines 1 KiB apart (the main loop is sensitive to every extra L2 request).
-        float4* run4 = reinterpret_cast<float4*>(p.sk_run + (size_t)blockIdx.x * BLOCK_M * p.block_n) + (q * 32 + lane);
+        // Layout [32-column chunk][warp][16-byte piece][lane]: 4 KiB per (chunk, warp) = the image of one staging slab, so
+        // where slabs exist a sub-result leaves the SM as ONE bulk copy per chunk and is ADDED by the L2
+        // (cp.reduce.async.bulk .add.f32): no read-back until the chain's last sub-segment.
+        float4* run4 = reinterpret_cast<float4*>(p.sk_run + (size_t)blockIdx.x * BLOCK_M * p.block_n) + (q * 8 * 32 + lane);
+        const bool bulk_run = p.store_bufs > 0 && !(p.dbg_flags & 16);
         CapIter it;
         it.init(worker, nworkers, p.dp_tiles, p.sk_ctas, sk_total, KB, p.kcap);
         const uint32_t tempty_r0 = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u, tempty_r1 = PAIR ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u;
@@ -453,6 +464,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (lane == 0) flag_wait(p.sk_flags + h * NCTA + rank, p.epoch, 0x500u);
                 __syncwarp();
             }
+            if (bulk_run && !first_sub) {
+                // order this sub-segment's slot traffic behind the previous one's (store before add, adds in chain order;
+                // the last sub-segment reads the finished sum with ordinary loads)
+                if (lane == 0) {
+                    bulk_wait_all();
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
+                __syncwarp();
+            }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
             // Partials of the other contributors are staged through the (now idle: a head segment with contributors
             // is always this CTA's last segment) smem ring with cp.async, one 32-column chunk ahead, so the adds never
@@ -484,18 +504,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (c + 32 < p.block_n) tmem_ld_32x32b_x32(t_row + (uint32_t)(c + 32), v);   // next chunk streams in behind the math
-                float4* own = run4 + (size_t)(c >> 5) * 8 * BLOCK_M;
-                if (!first_sub && !(p.dbg_flags & 4)) {      // running sum of the earlier sub-segments (this thread wrote it)
+                float4* own = run4 + (size_t)(c >> 5) * 4 * 8 * 32;
+                if (!first_sub && (last_sub || !bulk_run) && !(p.dbg_flags & 4)) {   // running sum of the earlier sub-segments
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 t = __ldcg(own + j * BLOCK_M);
+                        const float4 t = __ldcg(own + j * 32);
                         f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
                     }
                 }
-                if (!last_sub) {                             // running sum -> this CTA's private slot
-                    if (!(p.dbg_flags & 8)) {
+                if (!last_sub) {                             // sub-result -> this CTA's private running-sum slot
+                    if (bulk_run) {
+                        const uint32_t slab = stg_base + (uint32_t)((store_seq % p.store_bufs) * 4096);
+                        if (lane == 0) bulk_wait_read(p.store_bufs - 1);   // the copy that last read this slab is done
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) __stcg(own + j * BLOCK_M, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(slab + (uint32_t)(j * 512 + lane * 16), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (first_sub) bulk_store_1d(own - lane, slab, 4096);
+                            else bulk_reduce_add_f32_1d(own - lane, slab, 4096);
+                            bulk_commit();
+                        }
+                        ++store_seq;
+                    } else if (!(p.dbg_flags & 8)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(own + j * 32, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
                     }
                     continue;
                 }
@@ -651,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (acc == 0) acc_phase ^= 1u;
         }
         if (p.dbg && et == 0) p.dbg[blockIdx.x * 4 + 3] = gtime_ns();
-        if (p.tma_store && lane == 0) bulk_wait_read(0);    // the slabs have been read out before the CTA (its smem) retires
+        if (p.store_bufs && lane == 0) bulk_wait_read(0);   // the slabs have been read out before the CTA (its smem) retires
     }
 
     tc_fence_before();
