@@ -108,3 +108,27 @@ def test_darknet_forward_pair_mode_vs_oracle(cuda, mode, classes, size, batch):
     assert _rel(out[:nref], ref.astype(np.float64)) <= TOL
     assert _rel(base[:nref], ref.astype(np.float64)) <= TOL       # (batch 32 x 416 x 80 classes is the bench configuration)
     assert _rel(out, base.astype(np.float64)) <= 5e-5           # two fp32-grade evaluations, different summation orders
+
+
+@pytest.mark.parametrize("classes,size,batch,pick", [(80, 416, 32, (0, 13, 31)), (80, 608, 16, (0, 7, 15))])
+def test_full_size_batch_independence(cuda, classes, size, batch, pick):
+    """Size-independent property at BASELINE's full sizes (no oracle needed): an image's output must not depend on the batch
+    it travels in.  The plans differ completely (tile schedule, stream-K splits, fused pools, chain lengths), so this is
+    exactly the check that exposes a batch-size-dependent error such as the truncating accumulator (1.9e-4 at B = 32 before
+    the chain cap); both evaluations are fp32-grade, so they must agree to the 1e-4 bar."""
+    import torch
+    from yolo_tf_b200 import _lib, variables
+    from yolo_tf_b200.model.yolo2 import inference
+    params = init_params(classes, 5, seed=1)
+    store = variables.reset_default_store()
+    store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(batch, size, size, 3, device="cuda", generator=g)
+    _, full = inference.darknet(x, classes, 5)
+    full = full.cpu().numpy()
+    for i in pick:
+        _, one = inference.darknet(x[i:i + 1].contiguous(), classes, 5)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().y2_check_async_errors())
+        one = one.cpu().numpy()
+        assert _rel(full[i:i + 1], one.astype(np.float64)) <= TOL, i
