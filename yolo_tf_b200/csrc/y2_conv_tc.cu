@@ -911,6 +911,8 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     Y2_REQUIRE((reinterpret_cast<uintptr_t>(in_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0,
                "tc conv: operands must be 16-byte aligned");
     memset(L, 0, sizeof(*L));
+    // no co-resident CTA pair on this device / context (cluster launch refused): the single-CTA kernel computes the same thing
+    if (pair && max_active_pairs(split3, SMEM_LIMIT) < 1) pair = 0;
     const int BK = (Cin % 64 == 0) ? 64 : 32;
     const int taps = ksize * ksize;
     const long long M = (long long)B * H * W;
