@@ -414,7 +414,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t acc_phase = 0;
         uint32_t store_seq = 0;
         const uint32_t stg_base = smem_u32(smem0) + (uint32_t)(q * p.store_bufs * 4096);
-        float* my_partial = p.sk_partial + (size_t)blockIdx.x * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n;
+        // Partial slots use the same [32-column chunk][warp][16-byte piece][lane] layout as the running sums below: the head
+        // thread that collects a partial has the writer's (warp, lane), so every access of a warp is one contiguous 512 B run.
+        auto part4 = [&](int slot) -> float4* {
+            return reinterpret_cast<float4*>(p.sk_partial + (size_t)slot * BLOCK_M * p.block_n) + (q * 8 * 32 + lane);
+        };
+        float4* my_part4 = part4((int)blockIdx.x);
         // running sum of a segment's sub-segments: a slot of its own (the partial slot may still hold this CTA's contribution
         // to the previous tile, not yet collected by that tile's head).  Only this thread ever reads what it writes there, so
         // the layout is [32-column chunk][16-byte piece][row]: a warp's 32 rows form one contiguous 512 B run per access
@@ -501,11 +506,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             };
             auto stage_issue = [&](int c, int buf) {
                 for (int hh = 0; hh < nstaged; ++hh) {
-                    const float* src = p.sk_partial + (size_t)((worker + 1 + hh) * NCTA + rank) * BLOCK_M * p.block_n + (size_t)rr * p.block_n + c;
+                    const float4* src = part4((worker + 1 + hh) * NCTA + rank) + (size_t)(c >> 5) * 4 * 8 * 32;
                     const uint32_t dst = stage_slot(buf, hh);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((j ^ (rr & 7)) << 4)), "l"(src + 4 * j) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((j ^ (rr & 7)) << 4)), "l"(src + j * 32) : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
@@ -554,10 +559,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     continue;
                 }
-                if (!is_head) {                              // raw partial -> this CTA's slot (row layout: the tile's head reads it)
-                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
+                if (!is_head) {                              // raw partial -> this CTA's slot (the tile's head collects it)
+                    float4* dst = my_part4 + (size_t)(c >> 5) * 4 * 8 * 32;
+                    if (bulk_run) {
+                        const uint32_t slab = stg_base + (uint32_t)((store_seq % p.store_bufs) * 4096);
+                        if (lane == 0) bulk_wait_read(p.store_bufs - 1);
+                        __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(slab + (uint32_t)(j * 512 + lane * 16), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store_1d(dst - lane, slab, 4096);
+                            bulk_commit();
+                        }
+                        ++store_seq;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(dst + j * 32, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    }
                     continue;
                 }
                 if (nstaged > 0) {
@@ -581,11 +603,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
                 for (int h = worker + 1 + nstaged; h <= last_contrib; ++h) {      // overflow (tiny-K corner): direct loads
-                    const float4* src = reinterpret_cast<const float4*>(
-                        p.sk_partial + (size_t)(h * NCTA + rank) * BLOCK_M * p.block_n + (size_t)(q * 32 + lane) * p.block_n + c);
+                    const float4* src = part4(h * NCTA + rank) + (size_t)(c >> 5) * 4 * 8 * 32;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 t = __ldcg(src + j);
+                        const float4 t = __ldcg(src + j * 32);
                         f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
                     }
                 }
@@ -698,6 +719,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 else mbar_arrive(&tempty[acc]);
             }
             if (!is_head && last_sub) {                      // publish the partial: all 128 rows written -> flag
+                if (bulk_run) {                              // (the bulk copies of this warp have landed)
+                    if (lane == 0) {
+                        bulk_wait_all();
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                    }
+                    __syncwarp();
+                }
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (et == 0) flag_set(p.sk_flags + blockIdx.x, p.epoch);
