@@ -221,3 +221,37 @@ def test_backward_per_layer_teacher_forced(cuda):
     worst = max(max(v.values()) for v in report.values())
     assert worst <= 2e-4, report
     assert route12 <= 1e-6 and route19 == 0.0
+
+
+@pytest.mark.parametrize("classes,size,batch", [(20, 416, 64), (20, 96, 3)])
+def test_full_size_backward_is_repeatable_and_linear(cuda, classes, size, batch):
+    """BASELINE config 3 at its full size (B = 64, 416x416, 20 classes), through size-independent properties: given one
+    forward state, the backward is a LINEAR map of the incoming gradient, so (a) calling it twice gives bit-identical
+    buckets (fixed summation order everywhere: stream-K hand-offs, chain-cap running sums, two-stage reductions) and
+    (b) doubling dL/dnet doubles every gradient bit for bit (a power-of-two scale commutes with the bf16 hi/lo split, with
+    every rounding and with the tensor core's truncating accumulator)."""
+    import torch
+    from yolo_tf_b200 import _lib, variables
+    from yolo_tf_b200.model.yolo2 import Builder, inference
+    params = init_params(classes, 5, seed=6)
+    store = variables.reset_default_store()
+    store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(batch, size, size, 3, device="cuda", generator=g)
+    cw = size // 32
+    labels = [torch.from_numpy(t).to(cuda) for t in ho.synthetic_labels(batch, classes, cw, cw, seed=6)]
+    builder = Builder.from_values([str(i) for i in range(classes)], size, size, ho.ANCHORS_VOC)
+    builder(x, training=True)
+    builder.create_objectives(labels)
+    eng = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+    dnet = builder.objectives.grad_inputs
+    f1, _ = eng.backward(dnet)
+    f1 = f1.clone()
+    f1b, _ = eng.backward(dnet)
+    f1b = f1b.clone()
+    f2, _ = eng.backward((dnet * 2.0).contiguous())
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().y2_check_async_errors())
+    assert torch.isfinite(f1).all() and float(f1.abs().max()) > 0
+    assert torch.equal(f1, f1b)
+    assert torch.equal(f2, f1 * 2.0)
