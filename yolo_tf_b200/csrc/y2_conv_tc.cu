@@ -475,14 +475,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 sb_nt = nt;
             }
 
-            mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
-            tc_fence_after();
-            // the other contributors ran at the START of their ranges: normally long done
-            if (p.dbg && et == 0 && last_contrib > worker) p.dbg[blockIdx.x * 4 + 2] = gtime_ns();   // own MMAs done, start waiting
+            // The other contributors ran at the START of their ranges and are normally long done: their flags are acquired
+            // while this CTA's own MMAs are still running, which keeps that round trip out of the exposed tail.
             for (int h = worker + 1; h <= last_contrib; ++h) {       // (pair: the contributor CTA of the same rank)
                 if (lane == 0) flag_wait(p.sk_flags + h * NCTA + rank, p.epoch, 0x500u);
                 __syncwarp();
             }
+            mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
+            tc_fence_after();
+            if (p.dbg && et == 0 && last_contrib > worker) p.dbg[blockIdx.x * 4 + 2] = gtime_ns();   // own MMAs done
             if (bulk_run && !first_sub) {
                 // order this sub-segment's slot traffic behind the previous one's (store before add, adds in chain order;
                 // the last sub-segment reads the finished sum with ordinary loads)
