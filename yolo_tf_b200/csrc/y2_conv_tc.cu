@@ -110,38 +110,6 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// Accumulation-chain cap.  The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so a long chain
-// biases the sum towards zero by ~(chain length) x 2^-24 -- measured: the 13x13 layers at batch 32 (171 k-blocks per
-// chain) carried 1.9e-4 to the network output against 4e-5 with 6-k-block chains (tools/diag_layers.py).  Segments of the
-// schedule are therefore cut into sub-segments of at most `cap` k-blocks, each accumulated from zero in the next TMEM
-// buffer; the epilogue warps (idle during the main loop) add the sub-results with round-to-nearest fp32 adds in the CTA's
-// own partial slot.  The producer never notices; the MMA warp only sees more, shorter "segments".
-struct CapIter {
-    SegIter it;
-    int cap, tile_, a, b, pos;
-    __device__ __forceinline__ void init(int worker, int nworkers, int dp_tiles, int sk_ctas, long long sk_total, int KB, int cap_) {
-        it.init_w(worker, nworkers, dp_tiles, sk_ctas, sk_total, KB);
-        cap = cap_ > 0 ? cap_ : 0x7fffffff;
-        a = b = pos = 0; tile_ = 0;
-    }
-    // [kb0, kb1) = next sub-segment of segment [seg_a, seg_b) of `tile`
-    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& seg_a, int& seg_b) {
-        if (pos >= b) {
-            if (!it.next(tile_, a, b)) return false;
-            pos = a;
-        }
-        const int len = b - pos;
-        int step = len;
-        if (len > cap) {                              // equal pieces, none longer than cap
-            const int n = (len + cap - 1) / cap;
-            step = (len + n - 1) / n;
-        }
-        tile = tile_; kb0 = pos; kb1 = pos + step; seg_a = a; seg_b = b;
-        pos = kb1;
-        return true;
-    }
-};
-
 // PAIR: the kernel runs as clusters of two CTAs (the two SMs of a TPC) that share one tcgen05.mma.cta_group::2 stream:
 // a pair owns a 256-row M tile (CTA rank r: rows r*128..), each CTA stages its own A rows and HALF of the B tile, rank 0
 // issues M = 256 MMAs whose accumulator rows live in each CTA's own TMEM.  Per k-block a CTA's shared memory then sees

@@ -328,6 +328,43 @@ struct SegIter {
     }
 };
 
+// Accumulation-chain cap.  The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so a long chain
+// biases the sum towards zero by ~(chain length) x 2^-24 -- measured: the 13x13 layers at batch 32 (171 k-blocks per
+// chain) carried 1.9e-4 to the network output against 4e-5 with 6-k-block chains (tools/diag_layers.py).  Segments of the
+// schedule are therefore cut into sub-segments of at most `cap` k-blocks, each accumulated from zero in the next TMEM
+// buffer; the epilogue warps (idle during the main loop) add the sub-results with round-to-nearest fp32 adds in the CTA's
+// own partial slot.  The producer never notices; the MMA warp only sees more, shorter "segments".
+struct CapIter {
+    SegIter it;
+    int cap, tile_, a, b, pos;
+    __device__ __forceinline__ void init(int worker, int nworkers, int dp_tiles, int sk_ctas, long long sk_total, int KB, int cap_) {
+        it.init_w(worker, nworkers, dp_tiles, sk_ctas, sk_total, KB);
+        cap = cap_ > 0 ? cap_ : 0x7fffffff;
+        a = b = pos = 0; tile_ = 0;
+    }
+    // for callers that initialise `it` themselves (SegIter::init / init_split)
+    __device__ __forceinline__ void wrap(int cap_) {
+        cap = cap_ > 0 ? cap_ : 0x7fffffff;
+        a = b = pos = 0; tile_ = 0;
+    }
+    // [kb0, kb1) = next sub-segment of segment [seg_a, seg_b) of `tile`
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& seg_a, int& seg_b) {
+        if (pos >= b) {
+            if (!it.next(tile_, a, b)) return false;
+            pos = a;
+        }
+        const int len = b - pos;
+        int step = len;
+        if (len > cap) {                              // equal pieces, none longer than cap
+            const int n = (len + cap - 1) / cap;
+            step = (len + n - 1) / n;
+        }
+        tile = tile_; kb0 = pos; kb1 = pos + step; seg_a = a; seg_b = b;
+        pos = kb1;
+        return true;
+    }
+};
+
 // Shared-memory matrix descriptor, K-major operand, rows of `row_bytes` (128 -> SWIZZLE_128B,
 // 64 -> SWIZZLE_64B); 8-row groups are `8*row_bytes` apart (SBO). Bit layout as in the PTX ISA
 // "matrix descriptor" for tcgen05 (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),

@@ -35,6 +35,8 @@ struct WgradParams {
     int dp_tiles, sk_ctas;
     float* dw;                                // [taps][Cin][Cout]
     float* sk_partial;
+    float* sk_run;                            // [grid][128][block_n] running sums of capped accumulation chains (CapIter)
+    int kcap;                                 // longest tensor-core accumulation chain in k-blocks (0 = unlimited)
     unsigned int* sk_flags;
     unsigned int epoch;
 };
@@ -126,10 +128,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t leader = elect_one() ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        SegIter it;
-        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
-        while (it.next(tile, kb0, kb1)) {
+        CapIter it;
+        if (p.split_chunks) it.it.init_split(p.split_tiles, p.split_chunks, KB); else it.it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        it.wrap(p.kcap);
+        int tile, kb0, kb1, seg_a, seg_b;
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
             const int atom0 = __shfl_sync(0xffffffffu, mt * p.apt, 0);
             const int ncol0 = __shfl_sync(0xffffffffu, nt * p.block_n, 0);
@@ -172,10 +175,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t a_kstep = (uint32_t)(16 * a_row) >> 4, b_kstep = (16u * 128u) >> 4;
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        SegIter it;
-        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
-        while (it.next(tile, kb0, kb1)) {
+        CapIter it;
+        if (p.split_chunks) it.it.init_split(p.split_tiles, p.split_chunks, KB); else it.it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        it.wrap(p.kcap);
+        int tile, kb0, kb1, seg_a, seg_b;
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {              // every sub-segment: a fresh accumulator buffer
             mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x700u + acc);
             __syncwarp();
             tc_fence_after();
@@ -210,10 +214,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         float* my_partial = p.sk_partial + (size_t)blockIdx.x * WG_M * p.block_n + (size_t)r * p.block_n;
-        SegIter it;
-        if (p.split_chunks) it.init_split(p.split_tiles, p.split_chunks, KB); else it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
-        int tile, kb0, kb1;
-        while (it.next(tile, kb0, kb1)) {
+        // running sum of this CTA's accumulation chain (see CapIter): private, [32-column chunk][warp][16-byte piece][lane]
+        float4* run4 = reinterpret_cast<float4*>(p.sk_run + (size_t)blockIdx.x * WG_M * p.block_n) + (q * 8 * 32 + lane);
+        CapIter it;
+        if (p.split_chunks) it.it.init_split(p.split_tiles, p.split_chunks, KB); else it.it.init(p.dp_tiles, p.sk_ctas, sk_total, KB);
+        it.wrap(p.kcap);
+        int tile, kb0, kb1, seg_a, seg_b;
+        while (it.next(tile, kb0, kb1, seg_a, seg_b)) {
+            const bool first_sub = (kb0 == seg_a), last_sub = (kb1 == seg_b);
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
             const int ga = mt * p.apt + r / p.atom_ch;
@@ -221,10 +229,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int tap = row_ok ? ga / p.apc : 0;
             const int cch = row_ok ? (ga - tap * p.apc) * p.atom_ch + (r % p.atom_ch) : 0;
             float* drow = p.dw + ((size_t)tap * p.Cin + cch) * p.Cout;
-            const bool is_head = (kb0 == 0);
+            const bool is_head = (seg_a == 0) && last_sub;
             // the other CTAs holding k-ranges of this tile: ids cfirst + j * cstride, j < ncontrib
             int cfirst = blockIdx.x + 1, cstride = 1, ncontrib = 0;
-            if (is_head && kb1 < KB) {
+            if (is_head && seg_b < KB) {
                 if (p.split_chunks) {
                     cfirst = blockIdx.x + p.split_tiles; cstride = p.split_tiles; ncontrib = p.split_chunks - 1;
                 } else {
@@ -237,6 +245,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase, 0xA00u + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WG_ACC);
+            if (!last_sub) {
+                // not the end of the chain: add this sub-result to the running sum (round-to-nearest fp32) and release the
+                // accumulator; the MMAs of the next sub-segment are already filling the other buffer
+                for (int c = 0; c < p.block_n; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+                    tmem_ld_wait();
+                    float4* own = run4 + (size_t)(c >> 5) * 4 * 8 * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                               __uint_as_float(v[4 * j + 3]));
+                        if (!first_sub) {
+                            const float4 o = __ldcg(own + j * 32);
+                            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+                        }
+                        __stcg(own + j * 32, t);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+                continue;
+            }
             if (p.split_chunks) {
                 // K-aligned split: cooperative hand-off.  EVERY CTA of the tile publishes its raw partial, waits for the
                 // others, then reduces its own 1/chunks slice of the tile over all partials in chunk order (fixed order =
@@ -247,10 +281,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
                     tmem_ld_wait();
                     float4* dst = reinterpret_cast<float4*>(my_partial + c);
+                    const float4* own = run4 + (size_t)(c >> 5) * 4 * 8 * 32;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    for (int j = 0; j < 8; ++j) {
+                        float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                               __uint_as_float(v[4 * j + 3]));
+                        if (!first_sub) {                  // earlier sub-segments of this chain
+                            const float4 o = __ldcg(own + j * 32);
+                            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+                        }
+                        __stcg(dst + j, t);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -329,17 +370,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
-                if (!is_head) {
-                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                    continue;
-                }
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (!first_sub) {                          // earlier sub-segments of this chain
+                    const float4* own = run4 + (size_t)(c >> 5) * 4 * 8 * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 o = __ldcg(own + j * 32);
+                        f[4 * j] += o.x; f[4 * j + 1] += o.y; f[4 * j + 2] += o.z; f[4 * j + 3] += o.w;
+                    }
+                }
+                if (!is_head) {
+                    float4* dst = reinterpret_cast<float4*>(my_partial + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    continue;
+                }
                 for (int bt = 0; bt < nbatch; ++bt, ++step) {           // ascending contributor order: deterministic sum
                     const int buf = step & 1;
                     const bool more = (bt + 1 < nbatch) || (c + 32 < p.block_n);
@@ -449,6 +496,8 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     p.dw = dw;
     p.sk_flags = static_cast<unsigned int*>(sk_ws);
     p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
+    p.sk_run = p.sk_partial + (size_t)num_sms * WG_M * 256;     // second half of tc_conv_streamk_bytes()
+    p.kcap = g_conv_kcap;
     const int stage_bytes = 2 * (WG_M * WG_KPIX * 2 + bn * WG_KPIX * 2);
     int stages = (WG_SMEM - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
