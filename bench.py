@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--precision", type=int, default=0, help="0 = split-bf16 x3 (fp32-grade parity), 1 = single bf16 pass")
     ap.add_argument("--pair", type=int, default=-1, help="CTA-pair (cta_group::2) conv mode: -1 = library default, 0 off, 1 = 3x3 N=256 layers, 2 = all eligible")
+    ap.add_argument("--conv0-tc", type=int, default=-1, help="conv0 on the tensor cores (y2_set_option conv0_tc): -1 = library default")
     ap.add_argument("--cpu-images", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-report", default="", help="write the per-layer timing table (JSON) here")
@@ -235,6 +236,8 @@ def main():
     inference.PRECISION = args.precision
     if args.pair >= 0:
         _lib.check(L.y2_set_option(inference._Engine.get(dev, C, 5).h, b"pair", args.pair))
+    if args.conv0_tc >= 0:
+        _lib.check(L.y2_set_option(inference._Engine.get(dev, C, 5).h, b"conv0_tc", args.conv0_tc))
 
     rs = np.random.RandomState(100 + rank)
     host_in = [torch.from_numpy(rs.normal(0, 1, size=(B, size, size, 3)).astype(np.float32)).pin_memory()
@@ -401,7 +404,7 @@ def main():
                 "path": "pinned host -> H2D (copy stream, double-buffered) -> Builder(x) -> model.conf/xy_min/xy_max -> non_max_suppress_device -> D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (21 tcgen05 conv launches per step, conv1..conv20 + final)",
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (21 tcgen05 conv launches per step, conv1..conv20 + final; 3x3 layers with 256-wide N tiles as CTA pairs / cta_group::2 unless --pair 0; accumulation chains capped at 32 k-blocks for fp32-grade parity)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": "profiles/" + os.path.basename(tpath) + ": dram__bytes_read+write summed over the 21 conv launches of one step (ncu --set full)" if traffic else None,
                      "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,

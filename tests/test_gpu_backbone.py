@@ -12,6 +12,7 @@ from oracle.darknet_oracle import conv_bn_leaky_oracle, darknet_oracle, init_par
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+CONV0_TC_DEFAULT = 0          # library default of y2_set_option(h, "conv0_tc", ...)
 
 
 def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, max_ctas=0):
@@ -240,3 +241,42 @@ def test_objectives_through_builder(cuda):
     assert np.abs(obj.grad_inputs.cpu().numpy() - ref_g).max() <= 1e-4 * np.abs(ref_g).max()
     with pytest.raises(AttributeError):
         model.conf                       # not built when training (model/yolo2/__init__.py:50)
+
+
+@pytest.mark.parametrize("tc_mode", [1, 2])
+@pytest.mark.parametrize("arch,classes,size,batch", [("darknet", 20, 64, 3), ("darknet", 80, 416, 2), ("darknet", 20, 608, 1),
+                                                     ("darknet", 20, 96, 32), ("tiny", 20, 416, 2)])
+def test_conv0_on_tensor_cores_vs_oracle_and_cuda_core_kernel(cuda, tc_mode, arch, classes, size, batch):
+    """conv0 as SIMT-built im2col tiles + tcgen05 (option conv0_tc; 2 = unchecked gather for interior tiles): the pooled conv0
+    activation against the oracle and against the exact-fp32 CUDA-core kernel (they differ only by the 2^-17 operand
+    split), and the network output."""
+    import torch
+    from oracle.darknet_oracle import tiny_layer_table, tiny_oracle
+    from yolo_tf_b200 import _lib, variables
+    from yolo_tf_b200.model.yolo2 import inference
+    table = tiny_layer_table(classes, 5) if arch == "tiny" else None
+    params = init_params(classes, 5, seed=9, table=table)
+    store = variables.reset_default_store()
+    store.assign({"yolo2_%s/" % arch + k: v for k, v in params.items()})
+    rs = np.random.RandomState(5)
+    x = rs.normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
+    nref = min(batch, 2)
+    taps = {}
+    ref = (tiny_oracle if arch == "tiny" else darknet_oracle)(x[:nref], params, classes, 5, taps=taps)
+    eng = inference._Engine.get(torch.device("cuda:0"), classes, 5, inference.ARCH_TINY if arch == "tiny" else inference.ARCH_DARKNET)
+    fn = inference.tiny if arch == "tiny" else inference.darknet
+    xd = torch.from_numpy(x).to(cuda)
+    c0 = taps["conv0/pool"].shape[-1]
+    got = {}
+    try:
+        for mode in (0, tc_mode):
+            _lib.check(_lib.lib().y2_set_option(eng.h, b"conv0_tc", mode))
+            _, out = fn(xd, classes, 5)
+            torch.cuda.synchronize()
+            _lib.check(_lib.lib().y2_check_async_errors())
+            got[mode] = (eng.activation(0, True, (batch, size // 2, size // 2, c0)).cpu().numpy(), out.cpu().numpy())
+    finally:
+        _lib.check(_lib.lib().y2_set_option(eng.h, b"conv0_tc", CONV0_TC_DEFAULT))
+    assert _rel(got[tc_mode][0][:nref], taps["conv0/pool"].astype(np.float64)) <= 2e-5
+    assert _rel(got[tc_mode][0], got[0][0].astype(np.float64)) <= 2e-5
+    assert _rel(got[tc_mode][1][:nref], ref.astype(np.float64)) <= TOL

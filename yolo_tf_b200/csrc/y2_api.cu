@@ -155,6 +155,7 @@ struct y2_handle {
     TrainPlan tplan;
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
+    int conv0_tc = 0;                  // y2_set_option("conv0_tc"): conv0 on the tensor cores (SIMT-built im2col tile) instead of the CUDA cores; 2 = + unchecked gather for interior tiles
     int pair = 1;                      // y2_set_option("pair"): CTA-pair (cta_group::2) convs: 0 off, 1 = 3x3 layers with 256-wide N tiles, 2 = every eligible layer
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
@@ -412,7 +413,9 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
     {
         const size_t M0 = (size_t)B * (H / 2) * (W / 2);
         Y2_REQUIRE(L0.d.cout_s == 32 && L0.d.pool == 1, "y2_darknet_forward: conv0 kernel is built for 32 stored output channels + pool");
-        if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout_s, B, H, W, s)) return -1;
+        if (h->conv0_tc && conv0_tc_applicable(H, W)) {
+            if (conv0_tc_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout_s, B, H, W, h->num_sms, s, h->conv0_tc >= 2)) return -1;
+        } else if (conv0_pool_launch(x, L0.w_f32, L0.scale, L0.bias, P.act[0], P.act[0] + M0 * L0.d.cout_s, B, H, W, s)) return -1;
     }
     if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[1], s));
     for (int i = 1; i < nl; ++i) {
@@ -501,6 +504,7 @@ int y2_set_option(y2_handle* h, const char* key, int value) {
     if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }
     if (strcmp(key, "halo") == 0) { h->halo = value; h->plan.valid = false; return 0; }
     if (strcmp(key, "pair") == 0) { h->pair = value; h->plan.valid = false; return 0; }
+    if (strcmp(key, "conv0_tc") == 0) { h->conv0_tc = value; return 0; }
     set_error("y2_set_option: unknown option '%s'", key);
     return -1;
 }
@@ -641,7 +645,8 @@ int y2_nms(float* conf, const float* xy_min, const float* xy_max, int B, int N, 
 int y2_check_async_errors(void) {
     const int a = tc_conv_check_watchdog();
     const int b = wgrad_check_watchdog();
-    return a ? a : b;
+    const int c = conv0_tc_check_watchdog();
+    return a ? a : (b ? b : c);
 }
 
 }  // extern "C"

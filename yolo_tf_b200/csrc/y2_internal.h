@@ -221,4 +221,9 @@ int transform_labels_launch(const int* ocls, const float* ocoord, const int* off
 // conv0: 3x3, Cin=3 -> Cout=32, BN+leaky+2x2 maxpool fused, fp32 in, planes out.
 int conv0_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi,
                       bf16* out_lo, int B, int H, int W, cudaStream_t s);
+// conv0 on the tensor cores (y2_conv0_tc.cu): SIMT-built im2col tiles + tcgen05, same fused BN + leaky + pool and output planes
+bool conv0_tc_applicable(int H, int W);
+int conv0_tc_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi, bf16* out_lo, int B,
+                         int H, int W, int num_sms, cudaStream_t s, int fast = 0);
+int conv0_tc_check_watchdog();
 }  // namespace y2
