@@ -12,7 +12,7 @@ from oracle.darknet_oracle import conv_bn_leaky_oracle, darknet_oracle, init_par
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-CONV0_TC_DEFAULT = 0          # library default of y2_set_option(h, "conv0_tc", ...)
+CONV0_TC_DEFAULT = 2          # library default of y2_set_option(h, "conv0_tc", ...)
 
 
 def _conv(cuda, x, w, scale, bias, leaky, precision=0, block_n=0, max_ctas=0):

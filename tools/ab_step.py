@@ -45,7 +45,7 @@ def main():
     def apply(kvs):
         for k, v in [("5", "1"), ("6", "1"), ("3", "0"), ("8", "32")]:
             L.y2_debug_set(int(k), float(v))
-        opts = {"halo": 1, "fuse_pool": 1, "pair": 1, "conv0_tc": 0}
+        opts = {"halo": 1, "fuse_pool": 1, "pair": 1, "conv0_tc": 2}
         for k, v in kvs:
             if k in opts:
                 opts[k] = int(v)

@@ -155,7 +155,7 @@ struct y2_handle {
     TrainPlan tplan;
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
-    int conv0_tc = 0;                  // y2_set_option("conv0_tc"): conv0 on the tensor cores (SIMT-built im2col tile) instead of the CUDA cores; 2 = + unchecked gather for interior tiles
+    int conv0_tc = 2;                  // y2_set_option("conv0_tc"): conv0 on the tensor cores (SIMT-built im2col tile) instead of the CUDA cores; 2 = + unchecked gather for interior tiles
     int pair = 1;                      // y2_set_option("pair"): CTA-pair (cta_group::2) convs: 0 off, 1 = 3x3 layers with 256-wide N tiles, 2 = every eligible layer
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
