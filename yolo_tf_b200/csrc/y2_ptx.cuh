@@ -293,7 +293,7 @@ struct SegIter {
         init_w((int)blockIdx.x, (int)gridDim.x, dp_tiles_, sk_ctas, sk_total, KB_);
     }
     // worker = CTA (or CTA pair) index, nworkers = how many walk the schedule
-    __device__ __forceinline__ void init_w(int worker, int nworkers, int dp_tiles_, int sk_ctas, long long sk_total, int KB_) {
+    __host__ __device__ __forceinline__ void init_w(int worker, int nworkers, int dp_tiles_, int sk_ctas, long long sk_total, int KB_) {
         dp_next = worker; dp_tiles = dp_tiles_; stride = nworkers; KB = KB_;
         if (worker < sk_ctas) {
             cur = sk_total * worker / sk_ctas;
@@ -310,7 +310,7 @@ struct SegIter {
         cur = (long long)t * KB + (long long)KB * c / chunks;
         end = (long long)t * KB + (long long)KB * (c + 1) / chunks;
     }
-    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    __host__ __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
         if (dp_next < dp_tiles) {
             tile = dp_next; kb0 = 0; kb1 = KB; dp_next += stride;
             return true;
@@ -337,18 +337,18 @@ struct SegIter {
 struct CapIter {
     SegIter it;
     int cap, tile_, a, b, pos;
-    __device__ __forceinline__ void init(int worker, int nworkers, int dp_tiles, int sk_ctas, long long sk_total, int KB, int cap_) {
+    __host__ __device__ __forceinline__ void init(int worker, int nworkers, int dp_tiles, int sk_ctas, long long sk_total, int KB, int cap_) {
         it.init_w(worker, nworkers, dp_tiles, sk_ctas, sk_total, KB);
         cap = cap_ > 0 ? cap_ : 0x7fffffff;
         a = b = pos = 0; tile_ = 0;
     }
     // for callers that initialise `it` themselves (SegIter::init / init_split)
-    __device__ __forceinline__ void wrap(int cap_) {
+    __host__ __device__ __forceinline__ void wrap(int cap_) {
         cap = cap_ > 0 ? cap_ : 0x7fffffff;
         a = b = pos = 0; tile_ = 0;
     }
     // [kb0, kb1) = next sub-segment of segment [seg_a, seg_b) of `tile`
-    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& seg_a, int& seg_b) {
+    __host__ __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, int& seg_a, int& seg_b) {
         if (pos >= b) {
             if (!it.next(tile_, a, b)) return false;
             pos = a;
