@@ -230,7 +230,10 @@ void y2_destroy(y2_handle* h) {
     delete h;
 }
 
-int y2_num_layers(const y2_handle* h) { return h ? (int)h->layers.size() : -1; }
+int y2_num_layers(const y2_handle* h) {
+    Y2_REQUIRE(h, "y2_num_layers: null handle");
+    return (int)h->layers.size();
+}
 
 int y2_layer_info(const y2_handle* h, int layer, int* ksize, int* cin, int* cout, int* has_bn) {
     Y2_REQUIRE(h && layer >= 0 && layer < (int)h->layers.size(), "y2_layer_info: bad layer %d", layer);
@@ -513,6 +516,10 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
               const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int max_ctas,
               void* stream) {
     Y2_REQUIRE(x && w_hwio && y, "y2_conv2d: null argument");
+    Y2_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "y2_conv2d: bad shape B=%d H=%d W=%d cin=%d cout=%d", B, H, W, cin, cout);
+    Y2_REQUIRE(ksize == 1 || ksize == 3, "y2_conv2d: ksize must be 1 or 3 (got %d)", ksize);
+    Y2_REQUIRE(cin % 32 == 0, "y2_conv2d: cin must be a multiple of 32 (got %d)", cin);
+    Y2_REQUIRE(block_n == 0 || (block_n % 32 == 0 && block_n >= 32 && block_n <= 256), "y2_conv2d: block_n %d invalid", block_n);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int dev = 0;
     Y2_CUDA(cudaGetDevice(&dev));
@@ -588,6 +595,8 @@ int y2_debug_cta_times(unsigned long long* out, int max_ctas, int* sched4) {
 int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* dy, int ksize, int cout, float* dw,
                     int max_ctas, void* stream) {
     Y2_REQUIRE(x && dy && dw, "y2_conv2d_wgrad: null argument");
+    Y2_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "y2_conv2d_wgrad: bad shape B=%d H=%d W=%d cin=%d cout=%d", B, H, W, cin, cout);
+    Y2_REQUIRE(ksize == 1 || ksize == 3, "y2_conv2d_wgrad: ksize must be 1 or 3 (got %d)", ksize);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int dev = 0;
     Y2_CUDA(cudaGetDevice(&dev));
