@@ -205,11 +205,16 @@ int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int
         if (s.d.from_concat) h->cat_c = s.d.cin_s;
         choose_tiles(s.d.cout_s, &s.block_n, &s.cout_pad);
         const size_t K = (size_t)s.d.ksize * s.d.ksize * s.d.cin_s;
-        if (cudaMalloc(&s.w_f32, K * s.d.cout_s * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
-        if (i > 0 && cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
-        if (cudaMalloc(&s.scale, s.d.cout_s * sizeof(float)) != cudaSuccess ||
+        if (cudaMalloc(&s.w_f32, K * s.d.cout_s * sizeof(float)) != cudaSuccess ||
+            (i > 0 && cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) ||
+            cudaMalloc(&s.scale, s.d.cout_s * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&s.bias, s.d.cout_s * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout * sizeof(float)) != cudaSuccess) { set_error("y2_create: cudaMalloc failed"); delete h; return -2; }
+            cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout * sizeof(float)) != cudaSuccess) {
+            set_error("y2_create: cudaMalloc failed at layer %zu (%s)", i, cudaGetErrorString(cudaGetLastError()));
+            h->layers.push_back(s);            // y2_destroy frees this layer's partial allocations with the earlier layers'
+            y2_destroy(h);
+            return -2;
+        }
         cudaMemset(s.scale, 0, s.d.cout_s * sizeof(float));      // padded channels: scale = bias = 0 -> exact zeros
         cudaMemset(s.bias, 0, s.d.cout_s * sizeof(float));
         s.beta = s.gamma + s.d.cout; s.mmean = s.beta + s.d.cout; s.mvar = s.mmean + s.d.cout;
