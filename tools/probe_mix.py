@@ -1,0 +1,60 @@
+"""EXPERIMENTAL mixed-kind conv (csrc/y2_conv_mix.cu, y2_conv2d_mix) against the shipped kernel, one layer shape at a time:
+  * does kind::f16 + kind::f8f6f4 accumulate correctly into one TMEM tile (error vs float64 for terms = 7, 1, 6),
+  * what the main loop costs with 1 fp16 + 2 fp8 products (terms 7) vs the fp16 product alone (1) vs the two fp8 products alone (6)
+    vs the shipped bf16x3 kernel in its data-parallel single-CTA configuration and in its default configuration.
+Written without GPU time (round 1 budget spent); first thing to run in round 2.  Writes gpurun_out/probe_mix.json."""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from yolo_tf_b200 import _lib  # noqa: E402
+
+L = _lib.lib()
+L.y2_debug_set.argtypes = [ctypes.c_int, ctypes.c_double]
+L.y2_debug_last_conv_ms.restype = ctypes.c_float
+out = []
+# one tile per SM (conv13's shape at batch 28 -> 148 tiles of 128 x 256), then conv8 / conv18 / conv20 / conv14 at the bench batch
+for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 1024, 3), (32, 13, 3072, 1024, 3), (32, 13, 1024, 512, 1)]:
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, hw, hw, cin, device="cuda", generator=g)
+    x = torch.maximum(x, 0.1 * x)
+    w = torch.randn(k, k, cin, cout, device="cuda", generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    y = torch.empty(B, hw, hw, cout, device="cuda")
+    ref = torch.zeros(B, hw, hw, cout, dtype=torch.float64, device="cuda")
+    for i0 in range(0, B, 4):
+        ref[i0:i0 + 4] = F.conv2d(x[i0:i0 + 4].double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
+    flops = 2.0 * B * hw * hw * k * k * cin * cout
+    row = {"shape": [B, hw, cin, cout, k], "kblocks": k * k * cin // 64}
+    for terms in (7, 1, 6):
+        ts = []
+        for rep in range(5):
+            y.fill_(float("nan"))
+            rc = L.y2_conv2d_mix(_lib.ptr(x), B, hw, hw, cin, _lib.ptr(w), k, cout, None, None, 0, _lib.ptr(y), terms, 0, None)
+            torch.cuda.synchronize()
+            assert rc == 0, L.y2_last_error()
+            ts.append(float(L.y2_debug_last_mix_ms()))
+        err = float((y.double() - ref).abs().max() / ref.abs().max())
+        row["mix_terms%d" % terms] = {"ms": min(ts), "algorithmic_tflops": flops / min(ts) / 1e9, "rel_err_vs_fp64": err}
+    for name, sched, pair in (("bf16x3_dp_single", 1, 0), ("bf16x3_default", 0, 1)):
+        L.y2_debug_set(0, float(sched))
+        L.y2_debug_set(7, float(pair))
+        ts = []
+        for rep in range(5):
+            rc = L.y2_conv2d(_lib.ptr(x), B, hw, hw, cin, _lib.ptr(w), k, cout, None, None, 0, _lib.ptr(y), 0, 0, 0, None)
+            torch.cuda.synchronize()
+            assert rc == 0, L.y2_last_error()
+            ts.append(float(L.y2_debug_last_conv_ms()))
+        L.y2_debug_set(0, 0.0)
+        L.y2_debug_set(7, 0.0)
+        row[name] = {"ms": min(ts), "algorithmic_tflops": flops / min(ts) / 1e9,
+                     "rel_err_vs_fp64": float((y.double() - ref).abs().max() / ref.abs().max())}
+    out.append(row)
+    print(json.dumps(row), flush=True)
+_lib.check(L.y2_check_async_errors())
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/probe_mix.json", "w"), indent=1)

@@ -1,0 +1,453 @@
+// EXPERIMENTAL (not on any product path, not used by y2_darknet_forward, never run on a GPU at the time of writing):
+// one conv as an implicit GEMM whose products cost 2 MMA-equivalents instead of the 3 bf16 MMAs of conv_tc_kernel.
+//
+//   x*w ~= X16*W16 + X8*RW8 + RX8*W8       (tests/test_numerics_candidate_fp16_fp8.py)
+//   X16 = fp16(x E16)   X8 = e4m3(x E8)   RX8 = e4m3((x E16 - X16) * 4096 E8 / E16)          (weights likewise: F16, F8)
+//
+// With E16 / E8 = 2^7 and F16 / F8 = 2^5 all three products carry the same power-of-two factor E16 * F16, so ONE fp32 TMEM
+// accumulator takes the kind::f16 MMAs of the main term and the kind::f8f6f4 MMAs (half the cycles per product) of the
+// two corrections; the epilogue multiplies by 1 / (E16 F16).  Operand bytes per k-element read from shared memory:
+// 2 + 1 + 1 on each side instead of 2 + 2 + 2.
+//
+// Scope of this file: the questions that need hardware -- do the two MMA kinds accumulate into one TMEM tile, do they
+// interleave at full rate, what does the accumulator truncation add -- behind a diagnostic entry point (y2_conv2d_mix)
+// that converts float32 operands on the fly.  Deliberately minimal: single CTA, linear 128-pixel tiles (im2col TMA),
+// whole-K data-parallel tiles, fp32 output, no stream-K / pairs / chain cap / pooled epilogue.  The conv it stands for is
+// the same slim.layers.conv2d (+ folded batch_norm + leaky_relu) of model/yolo2/inference.py:62-69,73-118.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/yolo2_b200.h"
+#include "y2_internal.h"
+#include "y2_ptx.cuh"
+
+namespace y2 {
+
+static constexpr int MX_BLOCK_M = 128;
+static constexpr int MX_BK = 64;                 // channels per k-block: 128 B of fp16 (SW128), 64 B of e4m3 (SW64)
+static constexpr int MX_THREADS = 256;
+static constexpr int MX_EPI_WARP0 = 4;
+static constexpr int MX_ACC_COLS = 256;
+static constexpr int MX_TMEM_COLS = 512;
+static constexpr int MX_SMEM_LIMIT = 227 * 1024;
+static constexpr int MX_BAR_BYTES = 256;
+static constexpr int MX_A16 = MX_BLOCK_M * MX_BK * 2;      // 16 KiB
+static constexpr int MX_A8 = MX_BLOCK_M * MX_BK;           //  8 KiB
+
+struct MixParams {
+    int M, N, Cin, ksize, B, H, W;
+    int block_n, m_tiles, n_tiles, kblocks, cout_pad, num_stages;
+    int terms;               // bit 0: X16*W16, bit 1: X8*RW8, bit 2: RX8*W8 (diagnostics: time / check the terms separately)
+    int leaky;
+    float unscale;           // 1 / (E16 * F16)
+    const float* scale;      // [N] folded BN scale (null -> 1)
+    const float* bias;       // [N] (null -> 0)
+    float* out;              // [M][ldc] float32
+    long long ldc;
+};
+
+// same operand form as tcgen05.mma kind::f16; A and B are e4m3 (format 0 / 0 in the instruction descriptor), K = 32
+__device__ __forceinline__ void tc_mma_f8_e(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred pe, p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+// D = f32, A = B = format 0 (F16 for kind::f16, E4M3 for kind::f8f6f4), both K-major
+__host__ __device__ __forceinline__ uint32_t make_idesc_fmt0(uint32_t m, uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(MX_THREADS, 1)
+conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_constant__ CUtensorMap map_a8,
+                const __grid_constant__ CUtensorMap map_ra8, const __grid_constant__ CUtensorMap map_w16,
+                const __grid_constant__ CUtensorMap map_rw8, const __grid_constant__ CUtensorMap map_w8, const MixParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int b16 = p.block_n * MX_BK * 2, b8 = p.block_n * MX_BK;
+    // stage = [A16 | A8 | RA8 | W16 | RW8 | W8]; every piece is a multiple of 1 KiB (block_n % 16 == 0)
+    const int stage_bytes = MX_A16 + 2 * MX_A8 + b16 + 2 * b8;
+    const int S = p.num_stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a16); tma_prefetch_desc(&map_a8); tma_prefetch_desc(&map_ra8);
+        tma_prefetch_desc(&map_w16); tma_prefetch_desc(&map_rw8); tma_prefetch_desc(&map_w8);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, MX_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int KB = p.kblocks;
+    const int cblocks = p.Cin / MX_BK;
+    const int pad = p.ksize / 2;
+    const int hw = p.H * p.W;
+    const int tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            const int m0 = mt * MX_BLOCK_M;
+            int img = m0 / hw;
+            const int rem = m0 - img * hw;
+            int y0 = rem / p.W;
+            int x0 = rem - y0 * p.W;
+            x0 = __shfl_sync(0xffffffffu, x0, 0); y0 = __shfl_sync(0xffffffffu, y0, 0); img = __shfl_sync(0xffffffffu, img, 0);
+            const int n0 = __shfl_sync(0xffffffffu, nt * p.block_n, 0);
+            int tap = 0, cb = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1u, 0x100u + stage);
+                __syncwarp();
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                tap = __shfl_sync(0xffffffffu, tap, 0); cb = __shfl_sync(0xffffffffu, cb, 0);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                const int c0 = cb * MX_BK;
+                const int dy = (p.ksize == 3) ? tap / 3 : 0;
+                const int dx = (p.ksize == 3) ? tap - dy * 3 : 0;
+                const int kcoord = tap * p.Cin + c0;
+                mbar_expect_tx_e(leader, &full[stage], (uint32_t)stage_bytes);
+                tma_load_im2col_4d_e(leader, st, &map_a16, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                tma_load_im2col_4d_e(leader, st + MX_A16, &map_a8, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                tma_load_im2col_4d_e(leader, st + MX_A16 + MX_A8, &map_ra8, &full[stage], c0, x0 - pad, y0 - pad, img, (uint16_t)dx, (uint16_t)dy);
+                uint8_t* sb = st + MX_A16 + 2 * MX_A8;
+                tma_load_2d_e(leader, sb, &map_w16, &full[stage], kcoord, n0);
+                tma_load_2d_e(leader, sb + b16, &map_rw8, &full[stage], kcoord, n0);
+                tma_load_2d_e(leader, sb + b16 + b8, &map_w8, &full[stage], kcoord, n0);
+                if (++cb == cblocks) { cb = 0; ++tap; }
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc = make_idesc_fmt0(MX_BLOCK_M, (uint32_t)p.block_n);
+        const uint32_t ring = smem_u32(smem);
+        const uint32_t h128 = (uint32_t)(make_kmajor_desc(0, 128) >> 32), h64 = (uint32_t)(make_kmajor_desc(0, 64) >> 32);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(acc * MX_ACC_COLS), 0);
+            uint32_t have = 0;                               // 0 until the first MMA of this tile has been issued
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[stage], phase, 0x300u + stage);
+                __syncwarp();
+                tc_fence_after();
+                stage = __shfl_sync(0xffffffffu, stage, 0);
+                const uint32_t st = ring + (uint32_t)(stage * stage_bytes);
+                const uint32_t da16 = (uint32_t)make_kmajor_desc(st, 128);
+                const uint32_t da8 = (uint32_t)make_kmajor_desc(st + MX_A16, 64);
+                const uint32_t dra8 = (uint32_t)make_kmajor_desc(st + MX_A16 + MX_A8, 64);
+                const uint32_t sb = st + MX_A16 + 2 * MX_A8;
+                const uint32_t dw16 = (uint32_t)make_kmajor_desc(sb, 128);
+                const uint32_t drw8 = (uint32_t)make_kmajor_desc(sb + (uint32_t)b16, 64);
+                const uint32_t dw8 = (uint32_t)make_kmajor_desc(sb + (uint32_t)(b16 + b8), 64);
+                if (p.terms & 1) {
+#pragma unroll
+                    for (int k = 0; k < MX_BK / 16; ++k) {   // 16 halves = 32 B per MMA
+                        tc_mma_f16_e(leader, d_tmem, da16 + (uint32_t)(k * 2), h128, dw16 + (uint32_t)(k * 2), h128, idesc, have);
+                        have = 1u;
+                    }
+                }
+                if (p.terms & 2) {
+#pragma unroll
+                    for (int k = 0; k < MX_BK / 32; ++k) {   // 32 e4m3 = 32 B per MMA
+                        tc_mma_f8_e(leader, d_tmem, da8 + (uint32_t)(k * 2), h64, drw8 + (uint32_t)(k * 2), h64, idesc, have);
+                        have = 1u;
+                    }
+                }
+                if (p.terms & 4) {
+#pragma unroll
+                    for (int k = 0; k < MX_BK / 32; ++k) {
+                        tc_mma_f8_e(leader, d_tmem, dra8 + (uint32_t)(k * 2), h64, dw8 + (uint32_t)(k * 2), h64, idesc, have);
+                        have = 1u;
+                    }
+                }
+                tc_commit_e(leader, &empty[stage]);
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit_e(leader, &tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (warp >= MX_EPI_WARP0) {
+        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        const int q = warp - MX_EPI_WARP0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            const int n0 = nt * p.block_n;
+            const long long row = (long long)mt * MX_BLOCK_M + q * 32 + lane;
+            mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MX_ACC_COLS);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+                tmem_ld_wait_dep(v);
+                if (row < p.M) {
+                    float* dst = p.out + (size_t)row * p.ldc + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c + j;
+                        if (n < p.N) {
+                            float t = __uint_as_float(v[j]) * p.unscale;
+                            t = fmaf(t, p.scale ? __ldg(p.scale + n) : 1.0f, p.bias ? __ldg(p.bias + n) : 0.0f);
+                            dst[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, MX_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+__global__ void mix_amax_kernel(const float* __restrict__ x, size_t n, unsigned int* amax_bits) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
+// x (fp32) -> X16 = fp16(x s16), X8 = e4m3(x s8), RX8 = e4m3((x s16 - X16) * rs)
+__global__ void mix_prep_act_kernel(const float* __restrict__ x, size_t n, float s16, float s8, float rs, __half* x16, uint8_t* x8,
+                                    uint8_t* rx8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const __half h = __float2half_rn(v * s16);
+        x16[i] = h;
+        x8[i] = to_e4m3(v * s8);
+        rx8[i] = to_e4m3((v * s16 - __half2float(h)) * rs);
+    }
+}
+// w HWIO (fp32) -> [cout_pad][K = tap * Cin + c] (K-major B operand, the layout pack_weights_kernel produces), rows >= cout zero
+__global__ void mix_prep_w_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cout_pad, float s16, float s8, float rs,
+                                  __half* w16, uint8_t* w8, uint8_t* rw8) {
+    const size_t K = (size_t)taps * cin, total = K * cout_pad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / K);
+        const size_t k = i - (size_t)n * K;
+        const float v = n < cout ? w[k * cout + n] : 0.f;
+        const __half h = __float2half_rn(v * s16);
+        w16[i] = h;
+        w8[i] = to_e4m3(v * s8);
+        rw8[i] = to_e4m3((v * s16 - __half2float(h)) * rs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_mx_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_mx_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_mx_encodeTiled mx_encodeTiled = nullptr;
+static PFN_mx_encodeIm2col mx_encodeIm2col = nullptr;
+static float g_mix_last_ms = 0.f;
+
+static int mx_load_entry_points() {
+    if (mx_encodeTiled && mx_encodeIm2col) return 0;
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    Y2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    Y2_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+    mx_encodeTiled = reinterpret_cast<PFN_mx_encodeTiled>(fn);
+    fn = nullptr;
+    Y2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+    Y2_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col unavailable");
+    mx_encodeIm2col = reinterpret_cast<PFN_mx_encodeIm2col>(fn);
+    return 0;
+}
+
+// im2col map over an NHWC tensor of `esize`-byte elements: 128 pixels x 64 channels per load, zero fill = SAME padding
+static int mx_map_act(CUtensorMap* m, void* base, CUtensorMapDataType dt, int esize, int B, int H, int W, int Cin, int ksize) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * esize, (cuuint64_t)W * Cin * esize, (cuuint64_t)H * W * Cin * esize};
+    const int padv = ksize / 2;
+    int lower[2] = {-padv, -padv};
+    int upper[2] = {padv - (ksize - 1), padv - (ksize - 1)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = mx_encodeIm2col(m, dt, 4, base, dims, strides, lower, upper, (cuuint32_t)MX_BK, (cuuint32_t)MX_BLOCK_M, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    Y2_REQUIRE(r == CUDA_SUCCESS, "conv mix: cuTensorMapEncodeIm2col failed (%d), element size %d", (int)r, esize);
+    int drv = 0;
+    cudaDriverGetVersion(&drv);                      // same driver workaround as tc_conv_plan (tensors below 128 KiB)
+    if (drv <= 13010 && (size_t)B * H * W * Cin * esize < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+    return 0;
+}
+static int mx_map_w(CUtensorMap* m, void* base, CUtensorMapDataType dt, int esize, size_t K, int cout_pad, int block_n) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)K * esize};
+    cuuint32_t box[2] = {(cuuint32_t)MX_BK, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = mx_encodeTiled(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                esize == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    Y2_REQUIRE(r == CUDA_SUCCESS, "conv mix: cuTensorMapEncodeTiled failed (%d), element size %d", (int)r, esize);
+    return 0;
+}
+
+static int conv_mix_check_watchdog_impl() {
+    Watchdog w;
+    Y2_CUDA(cudaMemcpyFromSymbol(&w, g_watchdog, sizeof(w)));
+    if (!w.fired) return 0;
+    Watchdog z;
+    memset(&z, 0, sizeof(z));
+    cudaMemcpyToSymbol(g_watchdog, &z, sizeof(z));
+    set_error("conv mix: barrier watchdog fired (block %u warp %u wait-site 0x%x parity %u)", w.block, w.warp, w.tag, w.parity);
+    return -3;
+}
+int conv_mix_check_watchdog() { return conv_mix_check_watchdog_impl(); }
+
+static float pow2_at_least(float v) { return exp2f(ceilf(log2f(v))); }
+
+}  // namespace y2
+
+using namespace y2;
+
+extern "C" {
+
+float y2_debug_last_mix_ms(void) { return g_mix_last_ms; }
+
+int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
+                  const float* bias, int leaky, float* y, int terms, int block_n, void* stream) {
+    Y2_REQUIRE(x && w_hwio && y, "y2_conv2d_mix: null argument");
+    Y2_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "y2_conv2d_mix: bad shape B=%d H=%d W=%d cin=%d cout=%d", B, H, W, cin, cout);
+    Y2_REQUIRE(ksize == 1 || ksize == 3, "y2_conv2d_mix: ksize must be 1 or 3 (got %d)", ksize);
+    Y2_REQUIRE(cin % MX_BK == 0, "y2_conv2d_mix: cin must be a multiple of 64 (got %d)", cin);
+    Y2_REQUIRE(terms >= 1 && terms <= 7, "y2_conv2d_mix: terms is a bit mask 1..7 (got %d)", terms);
+    Y2_REQUIRE(block_n == 0 || (block_n % 32 == 0 && block_n >= 32 && block_n <= 256), "y2_conv2d_mix: block_n %d invalid", block_n);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    Y2_CUDA(cudaGetDevice(&dev));
+    const int num_sms = device_sm_count(dev);
+    if (mx_load_entry_points()) return -1;
+    const int taps = ksize * ksize;
+    const size_t M = (size_t)B * H * W, K = (size_t)taps * cin;
+    Y2_REQUIRE(M < ((size_t)1 << 31), "y2_conv2d_mix: too many pixels");
+    int bn = block_n;
+    if (bn == 0) {                                   // widest tile that divides the padded channel count evenly (as choose_tiles)
+        const int p32 = (cout + 31) / 32 * 32, nt = (p32 + 255) / 256;
+        bn = ((p32 + nt - 1) / nt + 31) / 32 * 32;
+    }
+    const int cout_pad = (cout + bn - 1) / bn * bn;
+
+    unsigned int* amax_d = nullptr;
+    __half *x16 = nullptr, *w16 = nullptr;
+    uint8_t *x8 = nullptr, *rx8 = nullptr, *w8 = nullptr, *rw8 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&amax_d, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&x16, M * cin * 2) != cudaSuccess ||
+            cudaMalloc(&x8, M * cin) != cudaSuccess || cudaMalloc(&rx8, M * cin) != cudaSuccess ||
+            cudaMalloc(&w16, K * cout_pad * 2) != cudaSuccess || cudaMalloc(&w8, K * cout_pad) != cudaSuccess ||
+            cudaMalloc(&rw8, K * cout_pad) != cudaSuccess) { set_error("y2_conv2d_mix: cudaMalloc failed"); break; }
+        if (cudaMemsetAsync(amax_d, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) { set_error("y2_conv2d_mix: memset failed"); break; }
+        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(x, M * cin, amax_d);
+        note_launch();
+        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(w_hwio, K * cout, amax_d + 1);
+        note_launch();
+        float amax[2] = {0.f, 0.f};
+        if (cudaMemcpyAsync(amax, amax_d, sizeof(amax), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("y2_conv2d_mix: amax pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (!(amax[0] > 0.f) || !(amax[1] > 0.f) || !isfinite(amax[0]) || !isfinite(amax[1])) { set_error("y2_conv2d_mix: operands are all zero or not finite"); break; }
+        // E16 = 2^15 / ba, E8 = 2^8 / ba (ba, bw: powers of two >= amax); F16 = 2^13 / bw, F8 = 2^8 / bw.
+        // E16 F16 == E8 F8 4096: main term and both corrections share one accumulator.
+        const float ba = pow2_at_least(amax[0]), bw = pow2_at_least(amax[1]);
+        const float E16 = 32768.f / ba, E8 = 256.f / ba, F16 = 8192.f / bw, F8 = 256.f / bw;
+        mix_prep_act_kernel<<<num_sms * 8, 256, 0, s>>>(x, M * cin, E16, E8, 4096.f * E8 / E16, x16, x8, rx8);
+        note_launch();
+        mix_prep_w_kernel<<<num_sms * 8, 256, 0, s>>>(w_hwio, taps, cin, cout, cout_pad, F16, F8, 4096.f * F8 / F16, w16, w8, rw8);
+        note_launch();
+        if (cudaGetLastError() != cudaSuccess) { set_error("y2_conv2d_mix: operand preparation failed to launch"); break; }
+
+        CUtensorMap ma16, ma8, mra8, mw16, mrw8, mw8;
+        if (mx_map_act(&ma16, x16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, H, W, cin, ksize)) break;
+        if (mx_map_act(&ma8, x8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
+        if (mx_map_act(&mra8, rx8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
+        if (mx_map_w(&mw16, w16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, K, cout_pad, bn)) break;
+        if (mx_map_w(&mrw8, rw8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
+        if (mx_map_w(&mw8, w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
+
+        MixParams p;
+        memset(&p, 0, sizeof(p));
+        p.M = (int)M; p.N = cout; p.Cin = cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
+        p.block_n = bn; p.m_tiles = (int)((M + MX_BLOCK_M - 1) / MX_BLOCK_M); p.n_tiles = cout_pad / bn;
+        p.kblocks = taps * (cin / MX_BK); p.cout_pad = cout_pad;
+        p.terms = terms; p.leaky = leaky; p.unscale = 1.0f / (E16 * F16);
+        p.scale = scale; p.bias = bias; p.out = y; p.ldc = cout;
+        const int stage_bytes = MX_A16 + 2 * MX_A8 + bn * MX_BK * 4;
+        int stages = (MX_SMEM_LIMIT - 1024 - MX_BAR_BYTES) / stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) { set_error("y2_conv2d_mix: tile does not fit shared memory"); break; }
+        p.num_stages = stages;
+        const int smem_bytes = stages * stage_bytes + 1024 + MX_BAR_BYTES;
+        const long long tiles = (long long)p.m_tiles * p.n_tiles;
+        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+        if (cudaFuncSetAttribute(conv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM_LIMIT) != cudaSuccess) {
+            set_error("y2_conv2d_mix: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // warm-up / result
+        note_launch();
+        cudaEventRecord(e0, s);
+        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // timed (same output)
+        note_launch();
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d_mix: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        cudaEventElapsedTime(&g_mix_last_ms, e0, e1);
+        if (conv_mix_check_watchdog()) break;
+        rc = 0;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(amax_d); cudaFree(x16); cudaFree(x8); cudaFree(rx8); cudaFree(w16); cudaFree(w8); cudaFree(rw8);
+    return rc;
+}
+
+}  // extern "C"
