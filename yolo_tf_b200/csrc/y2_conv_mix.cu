@@ -21,6 +21,7 @@
 
 #include "../../include/yolo2_b200.h"
 #include "y2_internal.h"
+#include "y2_mix_prep.cuh"
 #include "y2_ptx.cuh"
 
 namespace y2 {
@@ -247,18 +248,11 @@ __global__ void mix_amax_kernel(const float* __restrict__ x, size_t n, unsigned 
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));      // non-negative floats order like their bit patterns
 }
-__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
-
-// x (fp32) -> X16 = fp16(x s16), X8 = e4m3(x s8), RX8 = e4m3((x s16 - X16) * rs)
+// x (fp32) -> X16, X8, RX8 (y2_mix_prep.cuh)
 __global__ void mix_prep_act_kernel(const float* __restrict__ x, size_t n, float s16, float s8, float rs, __half* x16, uint8_t* x8,
                                     uint8_t* rx8) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        const __half h = __float2half_rn(v * s16);
-        x16[i] = h;
-        x8[i] = to_e4m3(v * s8);
-        rx8[i] = to_e4m3((v * s16 - __half2float(h)) * rs);
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        mix_split(x[i], s16, s8, rs, x16 + i, x8 + i, rx8 + i);
 }
 // w HWIO (fp32) -> [cout_pad][K = tap * Cin + c] (K-major B operand, the layout pack_weights_kernel produces), rows >= cout zero
 __global__ void mix_prep_w_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cout_pad, float s16, float s8, float rs,
@@ -267,11 +261,7 @@ __global__ void mix_prep_w_kernel(const float* __restrict__ w, int taps, int cin
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int n = (int)(i / K);
         const size_t k = i - (size_t)n * K;
-        const float v = n < cout ? w[k * cout + n] : 0.f;
-        const __half h = __float2half_rn(v * s16);
-        w16[i] = h;
-        w8[i] = to_e4m3(v * s8);
-        rw8[i] = to_e4m3((v * s16 - __half2float(h)) * rs);
+        mix_split(n < cout ? w[k * cout + n] : 0.f, s16, s8, rs, w16 + i, w8 + i, rw8 + i);
     }
 }
 
@@ -341,8 +331,6 @@ static int conv_mix_check_watchdog_impl() {
 }
 int conv_mix_check_watchdog() { return conv_mix_check_watchdog_impl(); }
 
-static float pow2_at_least(float v) { return exp2f(ceilf(log2f(v))); }
-
 }  // namespace y2
 
 using namespace y2;
@@ -395,13 +383,10 @@ int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_h
             break;
         }
         if (!(amax[0] > 0.f) || !(amax[1] > 0.f) || !isfinite(amax[0]) || !isfinite(amax[1])) { set_error("y2_conv2d_mix: operands are all zero or not finite"); break; }
-        // E16 = 2^15 / ba, E8 = 2^8 / ba (ba, bw: powers of two >= amax); F16 = 2^13 / bw, F8 = 2^8 / bw.
-        // E16 F16 == E8 F8 4096: main term and both corrections share one accumulator.
-        const float ba = pow2_at_least(amax[0]), bw = pow2_at_least(amax[1]);
-        const float E16 = 32768.f / ba, E8 = 256.f / ba, F16 = 8192.f / bw, F8 = 256.f / bw;
-        mix_prep_act_kernel<<<num_sms * 8, 256, 0, s>>>(x, M * cin, E16, E8, 4096.f * E8 / E16, x16, x8, rx8);
+        const MixScales sc = mix_scales(amax[0], amax[1]);       // E16 F16 == E8 F8 4096: one accumulator for all three products
+        mix_prep_act_kernel<<<num_sms * 8, 256, 0, s>>>(x, M * cin, sc.E16, sc.E8, sc.ra, x16, x8, rx8);
         note_launch();
-        mix_prep_w_kernel<<<num_sms * 8, 256, 0, s>>>(w_hwio, taps, cin, cout, cout_pad, F16, F8, 4096.f * F8 / F16, w16, w8, rw8);
+        mix_prep_w_kernel<<<num_sms * 8, 256, 0, s>>>(w_hwio, taps, cin, cout, cout_pad, sc.F16, sc.F8, sc.rw, w16, w8, rw8);
         note_launch();
         if (cudaGetLastError() != cudaSuccess) { set_error("y2_conv2d_mix: operand preparation failed to launch"); break; }
 
@@ -418,7 +403,7 @@ int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_h
         p.M = (int)M; p.N = cout; p.Cin = cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
         p.block_n = bn; p.m_tiles = (int)((M + MX_BLOCK_M - 1) / MX_BLOCK_M); p.n_tiles = cout_pad / bn;
         p.kblocks = taps * (cin / MX_BK); p.cout_pad = cout_pad;
-        p.terms = terms; p.leaky = leaky; p.unscale = 1.0f / (E16 * F16);
+        p.terms = terms; p.leaky = leaky; p.unscale = sc.unscale;
         p.scale = scale; p.bias = bias; p.out = y; p.ldc = cout;
         const int stage_bytes = MX_A16 + 2 * MX_A8 + bn * MX_BK * 4;
         int stages = (MX_SMEM_LIMIT - 1024 - MX_BAR_BYTES) / stage_bytes;
