@@ -115,3 +115,53 @@ def test_tiny_oracle_table_pool_semantics_and_fp64():
     y64 = tiny_oracle(x, p, 20, 5, dtype=torch.float64)
     assert y32.shape == (1, 3, 3, 125)
     assert np.abs(y32 - y64).max() <= 1e-4 * np.abs(y64).max()
+
+
+def test_oracle_conv_bn_pool_follow_the_tf_definitions_written_out_as_loops():
+    """TensorFlow itself cannot run here (parity unpinned), so the oracle's primitives are at least pinned to the
+    DEFINITIONS the survey restates, spelled out as explicit loops that share no code with torch's conv:
+    tf.nn.conv2d (NHWC, HWIO, stride 1, SAME) = cross-correlation out[b,y,x,o] = sum_{dy,dx,c} in[b,y+dy-p,x+dx-p,c] w[dy,dx,c,o]
+    with zero padding p = k//2; tf.nn.batch_normalization: inv = rsqrt(var+eps)*gamma, y = x*inv + (beta - mean*inv);
+    leaky_relu = max(x, 0.1x) (model/yolo/function.py:21-24); max_pool2d 2x2 stride 2 (inference.py:69)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle.darknet_oracle import BN_EPS, _conv_same, leaky_oracle
+    rs = np.random.RandomState(9)
+    for k, cin, cout, h, w in ((3, 3, 4, 5, 6), (1, 5, 3, 4, 4), (3, 2, 2, 1, 1)):
+        x = rs.normal(size=(2, h, w, cin))
+        wt = rs.normal(size=(k, k, cin, cout))
+        want = np.zeros((2, h, w, cout))
+        p = k // 2
+        for b in range(2):
+            for y in range(h):
+                for xx in range(w):
+                    for dy in range(k):
+                        for dx in range(k):
+                            yy, xs = y + dy - p, xx + dx - p
+                            if 0 <= yy < h and 0 <= xs < w:
+                                want[b, y, xx] += x[b, yy, xs] @ wt[dy, dx]
+        got = _conv_same(torch.as_tensor(x).permute(0, 3, 1, 2), torch.as_tensor(wt)).permute(0, 2, 3, 1).numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    # one whole BN-conv layer + pool through darknet_oracle's code path, against the written-out arithmetic
+    table = [("conv0", 3, 3, 4, "pool"), ("conv", 1, 4, 6, "linear")]
+    prm = init_params(1, 1, seed=5, table=table)
+    x = rs.normal(size=(1, 4, 4, 3))
+    got = darknet_oracle(x, prm, 1, 1, dtype=torch.float64, table=table)
+    z = _conv_same(torch.as_tensor(x).permute(0, 3, 1, 2), torch.as_tensor(prm["conv0/weights"]).double()).permute(0, 2, 3, 1).numpy()
+    g, b_, m, v = (prm["conv0/BatchNorm/" + n].astype(np.float64) for n in ("gamma", "beta", "moving_mean", "moving_variance"))
+    inv = g / np.sqrt(v + BN_EPS)
+    a = z * inv + (b_ - m * inv)
+    a = np.maximum(a, 0.1 * a)
+    pooled = a.reshape(1, 2, 2, 2, 2, 4).max(axis=(2, 4))
+    want = pooled @ prm["conv/weights"].astype(np.float64)[0, 0] + prm["conv/biases"].astype(np.float64)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    # training mode: batch mean and POPULATION variance over (B, H, W) (slim.batch_norm(is_training=True))
+    got_t = darknet_oracle(np.concatenate([x, 2 * x]), prm, 1, 1, training=True, dtype=torch.float64, table=table)
+    z2 = np.concatenate([z, 2 * z])
+    mu, var = z2.mean(axis=(0, 1, 2)), z2.var(axis=(0, 1, 2))
+    inv = g / np.sqrt(var + BN_EPS)
+    a = z2 * inv + (b_ - mu * inv)
+    a = np.maximum(a, 0.1 * a)
+    want_t = a.reshape(2, 2, 2, 2, 2, 4).max(axis=(2, 4)) @ prm["conv/weights"].astype(np.float64)[0, 0] + prm["conv/biases"].astype(np.float64)
+    np.testing.assert_allclose(got_t, want_t, rtol=1e-11, atol=1e-11)
+    assert float(leaky_oracle(torch.tensor(-2.0, dtype=torch.float64))) == -0.2 and float(leaky_oracle(torch.tensor(0.0))) == 0.0
