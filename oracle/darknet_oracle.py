@@ -17,11 +17,16 @@ Restates, with torch-CPU float32 (or float64 "truth") tensors:
   2x2 **stride-1** SAME max-pool (:42): TF SAME with k=2, s=1 pads one row/column at
   the bottom/right only (pad_total = 1, pad_before = 0) and max-pool ignores padding.
 
-PARITY UNPINNED for conv/BN/pool arithmetic: TensorFlow 1.0 is not installable in
-the authoring container and the reference ships no golden vector for this part
-(SURVEY.md section 8c).  The only pinned item is the reorg self-test vector
-(function.py:32-50), checked in tests/test_oracle_golden.py.  The float64 twin is
-used to apportion error between "fp32 summation order" and "kernel error".
+PINNED TO THE REFERENCE'S SOURCE, NOT TO TENSORFLOW'S ARITHMETIC: tests/golden/backbone_reference.npz
+holds the outputs of the reference's own graph builders ``darknet()`` / ``_darknet()`` / ``tiny()`` /
+``_tiny()``, ``reorg()`` and ``leaky_relu()``, compiled from the reference files and run with a torch
+float64 stand-in for the slim / tf calls they make (tests/golden/make_backbone_golden.py); this
+oracle matches them to 1e-9 incl. training-mode statistics, and the variable names / shapes the
+graph creates are the ones the product looks up (tests/test_backbone_reference_golden.py).  The
+reorg self-test vector (function.py:32-50) and the TF definitions written out as loops are checked
+in tests/test_oracle_golden.py.  TensorFlow 1.0 itself is not installable in the authoring
+container, so its conv / BN kernel ARITHMETIC stays PARITY UNPINNED.  The
+float64 twin is used to apportion error between "fp32 summation order" and "kernel error".
 
 Variable naming follows the TF checkpoint scope the reference builds
 (inference.py:67,73,118): ``conv{i}/weights`` (HWIO), ``conv{i}/BatchNorm/{gamma,

@@ -13,9 +13,14 @@ Restates with numpy (float32 by default, float64 twin via ``dtype``):
 * ``transform_labels_oracle`` <- ``transform_labels`` utils/data/__init__.py:112-145
   (label layout the loss consumes; ``np.int`` replaced by ``int``).
 
-PARITY UNPINNED against TensorFlow itself (not installable here; the reference
-ships no golden vectors for this part).  TF semantics assumed: softmax subtracts the
-row max; ``tf.equal`` masks carry no gradient; reductions are float32 sums.
+PINNED TO THE REFERENCE'S SOURCE, NOT TO TENSORFLOW'S ARITHMETIC: tests/golden/head_reference.npz holds
+the outputs of the reference's own ``Model`` / ``Objectives`` classes (and autograd through them),
+compiled from the reference file and run with a torch stand-in for the ~20 TF ops they call
+(tests/golden/make_head_golden.py); decode, objectives and the closed-form gradient match them to
+1e-12 / 1e-10 in float64 (tests/test_head_reference_golden.py).  TensorFlow 1.0 itself is not
+installable here, so its kernel arithmetic (summation order, exp / sigmoid ulps) stays PARITY
+UNPINNED.  TF semantics assumed: softmax subtracts the row max; ``tf.equal`` masks carry no
+gradient; reductions are float32 sums.
 """
 import numpy as np
 
