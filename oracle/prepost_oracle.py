@@ -4,8 +4,9 @@
       reference's own function (tests/golden/make_preprocess_golden.py).
   detections_oracle                <- detect.py:72-87 (the loop after non_max_suppress): index = np.argmax(_conf) (first
       maximum), kept iff _conf[index] > threshold; _xy_min * scale, (_xy_max - _xy_min) * scale with
-      scale = [image_width / cell_width, image_height / cell_height].  Restated (the reference's loop sits inside a
-      function that needs a TF session and matplotlib): parity unpinned.
+      scale = [image_width / cell_width, image_height / cell_height].  PINNED: tests/golden/detect_reference.npz holds what
+      the reference's own detect() draws (the function compiled from detect.py as it lies, its own non_max_suppress, the TF
+      session and matplotlib replaced by recorders: tests/golden/make_detect_golden.py); checked in tests/test_prepost.py.
 """
 import numpy as np
 

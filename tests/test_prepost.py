@@ -75,3 +75,68 @@ def test_detections_gpu_vs_oracle(cuda, n, c):
             np.testing.assert_allclose(xywh[b, i, :2], rxy, rtol=2e-7)
             np.testing.assert_allclose(xywh[b, i, 2:], rwh, rtol=2e-7)
     assert cls[0, list(box[0, :count[0]]).index(1)] == 0 if 1 in box[0, :count[0]] else True
+
+
+DETECT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "detect_reference.npz")
+DETECT_CASES = ("voc13", "coco7", "rect", "none")
+
+
+def _reference_drawn(g, name):
+    """What the reference's own detect() drew (tests/golden/make_detect_golden.py): rows (x, y, w, h, linewidth) in pixels,
+    class per row; sorted so that the reference's NMS-list order and the oracle's box-index order compare as SETS."""
+    rect, cls = g[name + "_rect"], g[name + "_cls"]
+    rows = sorted((float(r[0]), float(r[1]), float(r[2]), float(r[3]), int(c)) for r, c in zip(rect, cls))
+    return rows
+
+
+def _assert_same_boxes(mine, want, atol):
+    """Both lists hold (x, y, w, h, class); equal as multisets within atol pixels (order-free, robust to near-equal keys)."""
+    assert len(mine) == len(want)
+    left = list(mine)
+    for w in want:
+        hit = [i for i, m in enumerate(left) if m[4] == w[4] and max(abs(m[j] - w[j]) for j in range(4)) <= atol + 1e-6 * abs(w[0])]
+        assert hit, ("the reference draws %s, not found" % (w,))
+        left.pop(hit[0])
+
+
+@pytest.mark.parametrize("name", DETECT_CASES)
+def test_detections_oracle_matches_what_the_reference_detect_draws(name):
+    """detect.py:56-88 executed as it lies (its own non_max_suppress; session / matplotlib replaced by recorders): the NMS
+    oracle reproduces the in-place zeroing, and detections_oracle on the result selects the boxes the reference draws --
+    same class (argmax, first maximum on exact ties), same pixel rectangle (scale = original image size / cells), same count."""
+    from oracle.nms_oracle import nms_oracle
+    g = np.load(DETECT_GOLD)
+    cw, ch, iw, ih = (int(v) for v in g[name + "_meta"])
+    conf = g[name + "_conf_in"].copy()
+    nms_oracle(conf, g[name + "_xy_min"], g[name + "_xy_max"], 0.3, 0.4)
+    assert np.array_equal(conf.view(np.uint32), g[name + "_conf_out"].view(np.uint32))
+    n, c = conf.shape[0] * conf.shape[1], conf.shape[2]
+    det = detections_oracle(conf.reshape(n, c), g[name + "_xy_min"].reshape(n, 2), g[name + "_xy_max"].reshape(n, 2), 0.3,
+                            [iw / cw, ih / ch])
+    mine = sorted((float(xy[0]), float(xy[1]), float(wh[0]), float(wh[1]), int(k)) for _, k, _, xy, wh in det)
+    want = _reference_drawn(g, name)
+    _assert_same_boxes(mine, want, 1e-4)
+    # the label text carries the score: '%.1f%%' of conf[index] * 100
+    scores = sorted("%.1f" % (s * 100) for _, _, s, _, _ in det)
+    assert scores == sorted(str(p) for p in g[name + "_pct"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DETECT_CASES)
+def test_nms_and_detections_gpu_vs_what_the_reference_detect_draws(cuda, name):
+    import torch
+    from yolo_tf_b200.utils.postprocess import detections_device, non_max_suppress_device
+    g = np.load(DETECT_GOLD)
+    cw, ch, iw, ih = (int(v) for v in g[name + "_meta"])
+    shp = g[name + "_conf_in"].shape
+    n, c = shp[0] * shp[1], shp[2]
+    conf = torch.from_numpy(g[name + "_conf_in"].reshape(1, n, c).copy()).to(cuda)
+    lo = torch.from_numpy(g[name + "_xy_min"].reshape(1, n, 2).copy()).to(cuda)
+    hi = torch.from_numpy(g[name + "_xy_max"].reshape(1, n, 2).copy()).to(cuda)
+    non_max_suppress_device(conf, lo, hi, 0.3, 0.4)
+    assert np.array_equal(conf.cpu().numpy().reshape(shp).view(np.uint32), g[name + "_conf_out"].view(np.uint32))
+    count, box, cls, score, xywh = detections_device(conf, lo, hi, 0.3, [iw / cw, ih / ch])
+    k = int(count[0])
+    mine = sorted((float(r[0]), float(r[1]), float(r[2]), float(r[3]), int(q)) for r, q in zip(xywh[0, :k].cpu().numpy(), cls[0, :k].cpu().numpy()))
+    want = _reference_drawn(g, name)
+    _assert_same_boxes(mine, want, 1e-3)            # float32 products on the device vs float64 in the reference's numpy
