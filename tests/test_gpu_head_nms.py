@@ -104,6 +104,45 @@ def test_loss_fwd_bwd_vs_oracle(cuda, B, hc, wc, C, anchors, seed):
     assert np.abs(g - g64).max() <= 1e-4 * np.abs(g64).max()
 
 
+@pytest.mark.parametrize("name", ["voc", "coco", "nonsquare", "ties"])
+def test_head_decode_and_loss_vs_the_reference_source_golden(cuda, name):
+    """tests/golden/head_reference.npz = the reference's own Model / Objectives classes (model/yolo2/__init__.py:27-94) run with a
+    torch stand-in for TF, float64, plus autograd through them (tests/golden/make_head_golden.py): the device decode, objectives
+    and gradient against THOSE numbers directly (the CPU suite pins the oracle to them at 1e-12)."""
+    import torch
+    from yolo_tf_b200 import _lib
+    L = _lib.lib()
+    d = np.load(os.path.join(GOLD, "head_reference.npz"))
+    net, C, anchors = d[name + "_net"], int(d[name + "_meta"][0]), d[name + "_anchors"]
+    labels = [d["%s_label_%s" % (name, n)] for n in ("mask", "prob", "coords", "offset_xy_min", "offset_xy_max", "areas")]
+    B, hc, wc, _ = net.shape
+    A, N = len(anchors), hc * wc * len(anchors)
+    x = _t(net, cuda)
+    anc = _t(np.asarray(anchors, np.float32), cuda)
+    dev = {k: torch.empty(*s, device=cuda) for k, s in {"conf": (B, N, C), "xy_min": (B, N, 2), "xy_max": (B, N, 2), "iou": (B, N),
+                                                        "prob": (B, N, C), "wh": (B, N, 2), "coords": (B, N, 4)}.items()}
+    outs = _lib.HeadOutputs(**{k: v.data_ptr() for k, v in dev.items()})
+    _lib.check(L.y2_head_decode(_lib.ptr(x), B, hc, wc, A, C, _lib.ptr(anc), ctypes.byref(outs), None))
+    for k, v in dev.items():
+        ref = d["%s_f64_model_%s" % (name, k)].reshape(v.shape)
+        assert np.abs(v.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())), k
+    lab = [_t(t.reshape(t.shape[0], t.shape[1], -1) if t.ndim > 2 else t, cuda) for t in labels]
+    objs = torch.zeros(4, device=cuda)
+    dnet = torch.full_like(x, float("nan"))
+    ws_bytes = L.y2_loss_workspace_bytes(B, hc, wc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    hp = (ctypes.c_float * 4)(1.0, 5.0, 1.0, 1.0)
+    _lib.check(L.y2_loss_fwd_bwd(_lib.ptr(x), B, hc, wc, A, C, _lib.ptr(anc), *[_lib.ptr(t) for t in lab], hp,
+                                 _lib.ptr(objs), _lib.ptr(dnet), _lib.ptr(ws), ws_bytes, None))
+    got = objs.cpu().numpy()
+    for i, k in enumerate(("prob", "iou_best", "iou_normal", "coords")):
+        want = float(d["%s_f64_obj_%s" % (name, k)])
+        assert abs(got[i] - want) <= 1e-4 * max(abs(want), 1e-6), (k, got[i], want)
+    g, g64 = dnet.cpu().numpy().astype(np.float64), d[name + "_f64_grad"]
+    assert not np.isnan(g).any()
+    assert np.abs(g - g64).max() <= 1e-4 * np.abs(g64).max()
+
+
 # ------------------------------------------------------------------ NMS (bit-exact)
 def _run_nms(cuda, conf, lo, hi, thr, thr_iou, want_order=True):
     import torch
