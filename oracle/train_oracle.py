@@ -10,7 +10,12 @@ Restates with torch autograd (float64 by default = "truth"; float32 available):
 * backward     <- what ``slim.learning.create_train_op`` (train.py:127-129) gets from tf.gradients
 * moving stats <- UPDATE_OPS of slim.batch_norm: m <- m*decay + batch*(1-decay)
 
-PARITY UNPINNED against TensorFlow (not installable here; no reference vectors).
+PINNED TO THE REFERENCE'S SOURCE, NOT TO TENSORFLOW'S ARITHMETIC: tests/golden/train_reference.npz holds one
+training step of the reference's own ``darknet(training=True)`` + ``Model`` + ``Objectives`` source run with
+torch float64 stand-ins for the slim / tf calls and autograd for tf.gradients (tests/golden/make_train_golden.py);
+loss, objectives, output, d(total)/d(net) and the gradients of all 65 trainable variables match
+(tests/test_train_reference_golden.py).  TensorFlow itself is not installable here: its kernel arithmetic stays
+PARITY UNPINNED.
 """
 import numpy as np
 import torch
