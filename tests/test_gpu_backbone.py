@@ -4,6 +4,8 @@ through the reference-shaped API vs the CPU oracle, layer by layer.
 
 Tolerance (north_star): 1e-4 relative, measured as max|a-b| / max|b| per output tensor.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -144,6 +146,32 @@ def test_darknet_forward_layer_by_layer_vs_oracle(cuda, classes, size, batch, an
         worst["output" + tag] = _rel(out.cpu().numpy(), ref.astype(np.float64))
     print("per-layer rel err:", {k: "%.1e" % v for k, v in worst.items()})
     assert max(worst.values()) <= TOL, worst
+
+
+def test_darknet_forward_vs_the_reference_graph_golden(cuda):
+    """tests/golden/backbone_reference.npz = the reference's own darknet() graph builder run with a torch float64 stand-in for
+    slim / tf (tests/golden/make_backbone_golden.py): the device forward against THOSE numbers directly (the CPU suite pins the
+    oracle to them at 1e-9), incl. the taps that feed the passthrough / concat."""
+    import torch
+    from yolo_tf_b200 import _lib
+    from yolo_tf_b200.model.yolo2 import inference
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "backbone_reference.npz"))
+    _setup_store(init_params(20, 5, seed=1))
+    x = torch.from_numpy(d["x64"]).to(cuda)
+    eng = inference._Engine.get(torch.device("cuda:0"), 20, 5)
+    _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", 0))          # keep the un-pooled tensors readable
+    try:
+        scope, out = inference.darknet(x, 20, 5)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().y2_check_async_errors())
+        assert scope == str(d["darknet_scope"]) == "yolo2_darknet"
+        assert _rel(out.cpu().numpy(), d["darknet_out"]) <= TOL
+        for i, hw, c in ((12, 4, 512), (19, 2, 1024), (20, 2, 1024)):
+            got = eng.activation(i, False, (1, hw, hw, c)).cpu().numpy()[:, :4, :4, :16]
+            # the fixture keeps a 4 x 4 x 16 corner of each tap, so the error is normalised by the corner's own (smaller) maximum
+            assert _rel(got, d["darknet_tap_conv%d" % i]) <= 3 * TOL, i
+    finally:
+        _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", 1))
 
 
 def test_fused_maxpool_epilogue_matches_separate_pool(cuda):
