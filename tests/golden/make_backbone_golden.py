@@ -184,7 +184,7 @@ def run(func, x, classes, anchors, training):
 def main():
     rs = np.random.RandomState(17)
     arrays = {"torch_version": np.array(torch.__version__)}
-    x64 = rs.normal(0, 1, size=(1, 64, 64, 3)).astype(np.float32)
+    x64 = rs.normal(0, 1, size=(3, 64, 64, 3)).astype(np.float32)       # the geometry of the GPU layer-by-layer test (20, 64, 3)
     x96 = rs.normal(0, 1, size=(2, 96, 64, 3)).astype(np.float32)          # batch 2, non-square (3 x 2 cells)
     arrays["x64"], arrays["x96"] = x64, x96
     for tag, func, x, classes, training in (("darknet", "darknet", x64, 20, False), ("darknet_rect", "darknet", x96, 20, False),
