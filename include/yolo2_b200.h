@@ -172,9 +172,10 @@ int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* d
 /* EXPERIMENTAL, diagnostic only (csrc/y2_conv_mix.cu; not used by any other entry point): the same conv as y2_conv2d with
  * every product issued as one fp16 MMA plus two e4m3 correction MMAs (2 MMA-equivalents instead of 3).
  * terms: bit mask of the products to issue (1 = fp16 x fp16, 2 = x8 * w-residual, 4 = x-residual * w8; 7 = all).
+ * kcap: longest tensor-core accumulation chain in 64-channel k-blocks (0 = the whole K in one chain; the network kernels use 32).
  * cin must be a multiple of 64.  y2_debug_last_mix_ms() = device time of the kernel in the last call. */
 int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
-                  const float* bias, int leaky, float* y, int terms, int block_n, void* stream);
+                  const float* bias, int leaky, float* y, int terms, int kcap, int block_n, void* stream);
 float y2_debug_last_mix_ms(void);
 
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.

@@ -140,11 +140,12 @@ def test_single_conv_entry_points_validate_shapes_first():
 def test_experimental_mixed_kind_conv_validates_first():
     L = _lib.lib()
     a = (P, 1, 8, 8)
-    assert L.y2_conv2d_mix(None, 1, 8, 8, 64, P, 3, 32, None, None, 0, P, 7, 0, None) == -1 and "null" in _err()
-    assert L.y2_conv2d_mix(*a, 32, P, 3, 32, None, None, 0, P, 7, 0, None) == -1 and "multiple of 64" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 5, 32, None, None, 0, P, 7, 0, None) == -1 and "ksize" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 0, 0, None) == -1 and "terms" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 7, 40, None) == -1 and "block_n" in _err()
+    assert L.y2_conv2d_mix(None, 1, 8, 8, 64, P, 3, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "null" in _err()
+    assert L.y2_conv2d_mix(*a, 32, P, 3, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "multiple of 64" in _err()
+    assert L.y2_conv2d_mix(*a, 64, P, 5, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "ksize" in _err()
+    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 0, 0, 0, None) == -1 and "terms" in _err()
+    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 7, -1, 0, None) == -1 and "kcap" in _err()
+    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 7, 0, 40, None) == -1 and "block_n" in _err()
 
 
 def test_check_raises_with_the_library_message():

@@ -4,7 +4,7 @@ This kernel is not on any product path and was written after the round's GPU bud
 B200; the test is skipped unless Y2_EXPERIMENTAL=1 so that the suite the driver runs only contains verified code.  What it
 checks once enabled: one fp16 product + two e4m3 correction products accumulated into ONE TMEM tile reproduce the conv to
 the error the CPU emulation predicts (tests/test_numerics_candidate_fp16_fp8.py); the fp16 product alone does not.
-Chains are kept <= 36 k-blocks: this kernel has no accumulation-chain cap."""
+The first tests keep chains <= 36 k-blocks; the last one runs conv20's K (432 k-blocks) with and without the chain cap."""
 import os
 
 import numpy as np
@@ -18,7 +18,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("Y2_EXPERIMENTAL") != "1", reason="experimental kernel, never run on a GPU yet: set Y2_EXPERIMENTAL=1")]
 
 
-def _run(b, hw, cin, cout, k, terms, leaky=1, block_n=0, seed=0):
+def _run(b, hw, cin, cout, k, terms, leaky=1, block_n=0, seed=0, kcap=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(b, hw, hw, cin, device="cuda", generator=g)
     x = torch.maximum(x, 0.1 * x)
@@ -27,7 +27,7 @@ def _run(b, hw, cin, cout, k, terms, leaky=1, block_n=0, seed=0):
     bi = torch.randn(cout, device="cuda", generator=g) * 0.1
     y = torch.full((b, hw, hw, cout), float("nan"), device="cuda")
     _lib.check(_lib.lib().y2_conv2d_mix(_lib.ptr(x), b, hw, hw, cin, _lib.ptr(w), k, cout, _lib.ptr(sc), _lib.ptr(bi), leaky, _lib.ptr(y),
-                                        terms, block_n, None))
+                                        terms, kcap, block_n, None))
     torch.cuda.synchronize()
     _lib.check(_lib.lib().y2_check_async_errors())
     ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
@@ -52,3 +52,12 @@ def test_fp16_product_alone_is_not_enough_and_tile_widths_agree():
 
 def test_partial_last_tile_and_linear_output():
     assert _run(1, 13, 64, 32, 3, terms=7, leaky=0) <= 2e-5        # 169 pixels: second M tile mostly out of range
+
+
+def test_long_chains_need_the_cap_here_too():
+    """conv20's K = 3 x 3 x 3072 (432 k-blocks of 64, 8 MMAs each): one uncapped chain carries the truncation bias of DESIGN 4.9;
+    chains of <= 32 k-blocks summed in fp32 by the epilogue bring the error back to the short-chain level."""
+    capped = _run(2, 13, 3072, 256, 3, terms=7, kcap=32)
+    uncapped = _run(2, 13, 3072, 256, 3, terms=7, kcap=0)
+    assert capped <= 2e-5, capped
+    assert uncapped > capped, (uncapped, capped)

@@ -1,6 +1,7 @@
 """EXPERIMENTAL mixed-kind conv (csrc/y2_conv_mix.cu, y2_conv2d_mix) against the shipped kernel, one layer shape at a time:
   * does kind::f16 + kind::f8f6f4 accumulate correctly into one TMEM tile (error vs float64 for terms = 7, 1, 6),
-  * what the main loop costs with 1 fp16 + 2 fp8 products (terms 7) vs the fp16 product alone (1) vs the two fp8 products alone (6)
+  * what the main loop costs with 1 fp16 + 2 fp8 products (terms 7; with the 32-k-block chain cap and without) vs the fp16
+    product alone (1) vs the two fp8 products alone (6)
     vs the shipped bf16x3 kernel in its data-parallel single-CTA configuration and in its default configuration.
 Written without GPU time (round 1 budget spent); first thing to run in round 2.  Writes gpurun_out/probe_mix.json."""
 import ctypes
@@ -30,16 +31,16 @@ for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32
         ref[i0:i0 + 4] = F.conv2d(x[i0:i0 + 4].double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
     flops = 2.0 * B * hw * hw * k * k * cin * cout
     row = {"shape": [B, hw, cin, cout, k], "kblocks": k * k * cin // 64}
-    for terms in (7, 1, 6):
+    for terms, kcap in ((7, 32), (7, 0), (1, 0), (6, 0)):
         ts = []
         for rep in range(5):
             y.fill_(float("nan"))
-            rc = L.y2_conv2d_mix(_lib.ptr(x), B, hw, hw, cin, _lib.ptr(w), k, cout, None, None, 0, _lib.ptr(y), terms, 0, None)
+            rc = L.y2_conv2d_mix(_lib.ptr(x), B, hw, hw, cin, _lib.ptr(w), k, cout, None, None, 0, _lib.ptr(y), terms, kcap, 0, None)
             torch.cuda.synchronize()
             assert rc == 0, L.y2_last_error()
             ts.append(float(L.y2_debug_last_mix_ms()))
         err = float((y.double() - ref).abs().max() / ref.abs().max())
-        row["mix_terms%d" % terms] = {"ms": min(ts), "algorithmic_tflops": flops / min(ts) / 1e9, "rel_err_vs_fp64": err}
+        row["mix_terms%d_kcap%d" % (terms, kcap)] = {"ms": min(ts), "algorithmic_tflops": flops / min(ts) / 1e9, "rel_err_vs_fp64": err}
     for name, sched, pair in (("bf16x3_dp_single", 1, 0), ("bf16x3_default", 0, 1)):
         L.y2_debug_set(0, float(sched))
         L.y2_debug_set(7, float(pair))

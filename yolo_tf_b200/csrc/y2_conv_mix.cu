@@ -12,7 +12,8 @@
 // Scope of this file: the questions that need hardware -- do the two MMA kinds accumulate into one TMEM tile, do they
 // interleave at full rate, what does the accumulator truncation add -- behind a diagnostic entry point (y2_conv2d_mix)
 // that converts float32 operands on the fly.  Deliberately minimal: single CTA, linear 128-pixel tiles (im2col TMA),
-// whole-K data-parallel tiles, fp32 output, no stream-K / pairs / chain cap / pooled epilogue.  The conv it stands for is
+// whole-K data-parallel tiles, fp32 output, an optional accumulation-chain cap (sub-results summed in the output tile by the
+// epilogue), no stream-K / pairs / pooled epilogue.  The conv it stands for is
 // the same slim.layers.conv2d (+ folded batch_norm + leaky_relu) of model/yolo2/inference.py:62-69,73-118.
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -41,6 +42,8 @@ struct MixParams {
     int M, N, Cin, ksize, B, H, W;
     int block_n, m_tiles, n_tiles, kblocks, cout_pad, num_stages;
     int terms;               // bit 0: X16*W16, bit 1: X8*RW8, bit 2: RX8*W8 (diagnostics: time / check the terms separately)
+    int nchunks;             // accumulation-chain cap: K is cut into nchunks equal chains, each summed from zero in its own TMEM
+                             // buffer; the epilogue adds the sub-results in fp32 (round to nearest) in the output tile itself
     int leaky;
     float unscale;           // 1 / (E16 * F16)
     const float* scale;      // [N] folded BN scale (null -> 1)
@@ -150,12 +153,14 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+          for (int ch = 0; ch < p.nchunks; ++ch) {
+            const int kb_lo = (int)((long long)KB * ch / p.nchunks), kb_hi = (int)((long long)KB * (ch + 1) / p.nchunks);
             mbar_wait(&tempty[acc], acc_phase ^ 1u, 0x200u + acc);
             __syncwarp();
             tc_fence_after();
             const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(acc * MX_ACC_COLS), 0);
-            uint32_t have = 0;                               // 0 until the first MMA of this tile has been issued
-            for (int kb = 0; kb < KB; ++kb) {
+            uint32_t have = 0;                               // 0 until the first MMA of this chain has been issued
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 mbar_wait(&full[stage], phase, 0x300u + stage);
                 __syncwarp();
                 tc_fence_after();
@@ -195,6 +200,7 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
             tc_commit_e(leader, &tfull[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
+          }
         }
     } else if (warp >= MX_EPI_WARP0) {
         // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
@@ -205,31 +211,40 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
             const long long row = (long long)mt * MX_BLOCK_M + q * 32 + lane;
-            mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MX_ACC_COLS);
-            for (int c = 0; c < p.block_n; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
-                tmem_ld_wait_dep(v);
-                if (row < p.M) {
-                    float* dst = p.out + (size_t)row * p.ldc + n0 + c;
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                const bool first = ch == 0, last = ch == p.nchunks - 1;
+                mbar_wait(&tfull[acc], acc_phase, 0x400u + acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MX_ACC_COLS);
+                for (int c = 0; c < p.block_n; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+                    tmem_ld_wait_dep(v);
+                    if (row < p.M) {
+                        // the running sum of the earlier chains lives in the output tile itself (written and read back by this
+                        // thread only); the last chain adds it, then applies scale / bias / leaky
+                        float* dst = p.out + (size_t)row * p.ldc + n0 + c;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + c + j;
-                        if (n < p.N) {
-                            float t = __uint_as_float(v[j]) * p.unscale;
-                            t = fmaf(t, p.scale ? __ldg(p.scale + n) : 1.0f, p.bias ? __ldg(p.bias + n) : 0.0f);
-                            dst[j] = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.N) {
+                                float t = __uint_as_float(v[j]) * p.unscale;      // exact: a power of two
+                                if (!first) t += dst[j];
+                                if (last) {
+                                    t = fmaf(t, p.scale ? __ldg(p.scale + n) : 1.0f, p.bias ? __ldg(p.bias + n) : 0.0f);
+                                    t = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                                }
+                                dst[j] = t;
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
         }
     }
 
@@ -342,12 +357,13 @@ extern "C" {
 float y2_debug_last_mix_ms(void) { return g_mix_last_ms; }
 
 int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
-                  const float* bias, int leaky, float* y, int terms, int block_n, void* stream) {
+                  const float* bias, int leaky, float* y, int terms, int kcap, int block_n, void* stream) {
     Y2_REQUIRE(x && w_hwio && y, "y2_conv2d_mix: null argument");
     Y2_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "y2_conv2d_mix: bad shape B=%d H=%d W=%d cin=%d cout=%d", B, H, W, cin, cout);
     Y2_REQUIRE(ksize == 1 || ksize == 3, "y2_conv2d_mix: ksize must be 1 or 3 (got %d)", ksize);
     Y2_REQUIRE(cin % MX_BK == 0, "y2_conv2d_mix: cin must be a multiple of 64 (got %d)", cin);
     Y2_REQUIRE(terms >= 1 && terms <= 7, "y2_conv2d_mix: terms is a bit mask 1..7 (got %d)", terms);
+    Y2_REQUIRE(kcap >= 0, "y2_conv2d_mix: kcap is the longest accumulation chain in k-blocks, 0 = unlimited (got %d)", kcap);
     Y2_REQUIRE(block_n == 0 || (block_n % 32 == 0 && block_n >= 32 && block_n <= 256), "y2_conv2d_mix: block_n %d invalid", block_n);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int dev = 0;
@@ -406,6 +422,7 @@ int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_h
         p.block_n = bn; p.m_tiles = (int)((M + MX_BLOCK_M - 1) / MX_BLOCK_M); p.n_tiles = cout_pad / bn;
         p.kblocks = taps * (cin / MX_BK); p.cout_pad = cout_pad;
         p.terms = terms; p.leaky = leaky; p.unscale = sc.unscale;
+        p.nchunks = kcap > 0 ? (p.kblocks + kcap - 1) / kcap : 1;
         p.scale = scale; p.bias = bias; p.out = y; p.ldc = cout;
         const int stage_bytes = MX_A16 + 2 * MX_A8 + bn * MX_BK * 4;
         int stages = (MX_SMEM_LIMIT - 1024 - MX_BAR_BYTES) / stage_bytes;
