@@ -177,6 +177,15 @@ int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* d
 int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
                   const float* bias, int leaky, float* y, int terms, int kcap, int block_n, void* stream);
 float y2_debug_last_mix_ms(void);
+/* The same with the activations already in the storage format of that mode (x16 = fp16(x E16), x8 = e4m3(x E8), rx8 = e4m3 of
+ * the fp16 residual; the two power-of-two scales follow from `in_bound` >= amax|x|), as y2_mix_split or a previous
+ * y2_conv2d_mix_pre wrote them: chains layers without leaving the format.  Optional outputs: y (float32), the split form of
+ * the result (o16 / o8 / or8, scales from `out_bound`, cout % 32 == 0) and the atomicMax of |result| (float bits) the next
+ * layer derives its bound from.  All pointers are device pointers except none; diagnostic only. */
+int y2_mix_split(const float* x, size_t n, float bound, void* x16, void* x8, void* rx8, void* stream);
+int y2_conv2d_mix_pre(const void* x16, const void* x8, const void* rx8, float in_bound, int B, int H, int W, int cin, const float* w_hwio,
+                      int ksize, int cout, const float* scale, const float* bias, int leaky, float* y, void* o16, void* o8, void* or8,
+                      float out_bound, uint32_t* amax_out, int terms, int kcap, int block_n, void* stream);
 
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.
  * out[b, y, x, (dy*stride+dx)*C + c] = in[b, stride*y+dy, stride*x+dx, c]. */

@@ -61,3 +61,52 @@ def test_long_chains_need_the_cap_here_too():
     uncapped = _run(2, 13, 3072, 256, 3, terms=7, kcap=0)
     assert capped <= 2e-5, capped
     assert uncapped > capped, (uncapped, capped)
+
+
+def test_two_layers_chained_in_the_storage_format():
+    """Layer 1 writes its result in the format layer 2 reads (fp16 + e4m3 + e4m3 residual, power-of-two scales from the
+    one-layer bound S * amax_in + T) and publishes its amax; layer 2 consumes that directly.  Checks the stored triple against
+    the float32 output it encodes, the published amax, and the two-layer result against float64."""
+    import math
+    import torch.nn.functional as F
+    L = _lib.lib()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(3)
+    b, hw, c0, c1, c2 = 2, 26, 128, 256, 128
+    x = torch.randn(b, hw, hw, c0, device=dev, generator=g)
+    x = torch.maximum(x, 0.1 * x)
+    w1 = torch.randn(3, 3, c0, c1, device=dev, generator=g) * (2.0 / (9 * c0)) ** 0.5
+    w2 = torch.randn(1, 1, c1, c2, device=dev, generator=g) * (2.0 / c1) ** 0.5
+    s1, b1 = torch.rand(c1, device=dev, generator=g) + 0.5, torch.randn(c1, device=dev, generator=g) * 0.1
+    s2, b2 = torch.rand(c2, device=dev, generator=g) + 0.5, torch.randn(c2, device=dev, generator=g) * 0.1
+    amax_x = float(x.abs().max())
+    bound1 = float((s1.abs() * w1.abs().sum(dim=(0, 1, 2))).max()) * amax_x + float(b1.abs().max())       # S * amax_in + T
+    n0, n1 = x.numel(), b * hw * hw * c1
+    x16 = torch.empty(n0, dtype=torch.float16, device=dev)
+    x8, rx8 = torch.empty(n0, dtype=torch.uint8, device=dev), torch.empty(n0, dtype=torch.uint8, device=dev)
+    _lib.check(L.y2_mix_split(_lib.ptr(x), n0, amax_x, _lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), None))
+    y1 = torch.full((b, hw, hw, c1), float("nan"), device=dev)
+    o16 = torch.empty(n1, dtype=torch.float16, device=dev)
+    o8, or8 = torch.empty(n1, dtype=torch.uint8, device=dev), torch.empty(n1, dtype=torch.uint8, device=dev)
+    amax1 = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.y2_conv2d_mix_pre(_lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), amax_x, b, hw, hw, c0, _lib.ptr(w1), 3, c1, _lib.ptr(s1), _lib.ptr(b1), 1,
+                                   _lib.ptr(y1), _lib.ptr(o16), _lib.ptr(o8), _lib.ptr(or8), bound1, _lib.ptr(amax1), 7, 32, 0, None))
+    torch.cuda.synchronize()
+    ref1 = F.conv2d(x.double().permute(0, 3, 1, 2), w1.double().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1) * s1.double() + b1.double()
+    ref1 = torch.maximum(ref1, 0.1 * ref1)
+    assert float((y1.double() - ref1).abs().max() / ref1.abs().max()) <= 2e-5
+    assert float(y1.abs().max()) <= bound1                                                # the bound is a bound
+    assert amax1.view(torch.float32).item() == float(y1.abs().max())                     # published amax = what was written
+    ba = 2.0 ** math.ceil(math.log2(bound1))
+    e16, e8 = 32768.0 / ba, 256.0 / ba
+    dec = o16.double() / e16 + or8.view(torch.float8_e4m3fn).double() / (e8 * 4096.0)
+    assert float((dec.view_as(y1) - y1.double()).abs().max()) <= 2.0 ** -15 * ba          # fp16 + 4 residual bits of the scaled range
+    assert float((o8.view(torch.float8_e4m3fn).double().view_as(y1) / e8 - y1.double()).abs().max()) <= 2.0 ** -4 * float(y1.abs().max()) + 2.0 ** -10 / e8
+    y2 = torch.full((b, hw, hw, c2), float("nan"), device=dev)
+    _lib.check(L.y2_conv2d_mix_pre(_lib.ptr(o16), _lib.ptr(o8), _lib.ptr(or8), bound1, b, hw, hw, c1, _lib.ptr(w2), 1, c2, _lib.ptr(s2), _lib.ptr(b2), 1,
+                                   _lib.ptr(y2), None, None, None, 0.0, None, 7, 32, 0, None))
+    torch.cuda.synchronize()
+    _lib.check(L.y2_check_async_errors())
+    ref2 = F.conv2d(ref1.permute(0, 3, 1, 2), w2.double().permute(3, 2, 0, 1)).permute(0, 2, 3, 1) * s2.double() + b2.double()
+    ref2 = torch.maximum(ref2, 0.1 * ref2)
+    assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) <= 3e-5

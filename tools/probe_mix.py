@@ -56,6 +56,37 @@ for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32
                      "rel_err_vs_fp64": float((y.double() - ref).abs().max() / ref.abs().max())}
     out.append(row)
     print(json.dumps(row), flush=True)
+# ---- epilogue cost of the storage format: float32 output only vs float32 + split triple + amax vs split triple only
+epi = []
+for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 512, 1)]:
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(B, hw, hw, cin, device="cuda", generator=g)
+    w = torch.randn(k, k, cin, cout, device="cuda", generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    n0, n1 = x.numel(), B * hw * hw * cout
+    amax_x = float(x.abs().max())
+    bound = float(w.abs().sum(dim=(0, 1, 2)).max()) * amax_x
+    x16 = torch.empty(n0, dtype=torch.float16, device="cuda")
+    x8, rx8 = torch.empty(n0, dtype=torch.uint8, device="cuda"), torch.empty(n0, dtype=torch.uint8, device="cuda")
+    _lib.check(L.y2_mix_split(_lib.ptr(x), n0, amax_x, _lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), None))
+    y = torch.empty(B, hw, hw, cout, device="cuda")
+    o16 = torch.empty(n1, dtype=torch.float16, device="cuda")
+    o8, or8 = torch.empty(n1, dtype=torch.uint8, device="cuda"), torch.empty(n1, dtype=torch.uint8, device="cuda")
+    amax = torch.zeros(1, dtype=torch.int32, device="cuda")
+    row = {"shape": [B, hw, cin, cout, k]}
+    for name, yy, split in (("f32_only", y, False), ("f32_and_split", y, True), ("split_only", None, True)):
+        ts = []
+        for rep in range(5):
+            rc = L.y2_conv2d_mix_pre(_lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), amax_x, B, hw, hw, cin, _lib.ptr(w), k, cout, None, None, 1,
+                                     _lib.ptr(yy), _lib.ptr(o16) if split else None, _lib.ptr(o8) if split else None, _lib.ptr(or8) if split else None,
+                                     bound if split else 0.0, _lib.ptr(amax) if split else None, 7, 0, 0, None)
+            torch.cuda.synchronize()
+            assert rc == 0, L.y2_last_error()
+            ts.append(float(L.y2_debug_last_mix_ms()))
+        row[name + "_ms"] = min(ts)
+    row["bound_over_amax"] = bound / float(y.abs().max())
+    epi.append(row)
+    print(json.dumps(row), flush=True)
 _lib.check(L.y2_check_async_errors())
 os.makedirs("gpurun_out", exist_ok=True)
+json.dump(epi, open("gpurun_out/probe_mix_epilogue.json", "w"), indent=1)
 json.dump(out, open("gpurun_out/probe_mix.json", "w"), indent=1)

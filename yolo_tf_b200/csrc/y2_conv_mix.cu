@@ -48,8 +48,14 @@ struct MixParams {
     float unscale;           // 1 / (E16 * F16)
     const float* scale;      // [N] folded BN scale (null -> 1)
     const float* bias;       // [N] (null -> 0)
-    float* out;              // [M][ldc] float32
+    float* out;              // [M][ldc] float32 (nullable when nchunks == 1 and the split outputs are written)
     long long ldc;
+    // optional second output: the result in the storage format the NEXT mixed-kind conv reads (N % 32 == 0, row pitch N)
+    __half* o16;             // fp16(y oE16)
+    uint8_t* o8;             // e4m3(y oE8)
+    uint8_t* or8;            // e4m3((y oE16 - o16) * ora)
+    float oE16, oE8, ora;
+    unsigned int* amax_out;  // atomicMax of |y| as float bits: what the next layer derives its bound from
 };
 
 // same operand form as tcgen05.mma kind::f16; A and B are e4m3 (format 0 / 0 in the instruction descriptor), K = 32
@@ -207,6 +213,7 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
         const int q = warp - MX_EPI_WARP0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        float amax_local = 0.f;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
             const int n0 = nt * p.block_n;
@@ -223,19 +230,45 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
                     if (row < p.M) {
                         // the running sum of the earlier chains lives in the output tile itself (written and read back by this
                         // thread only); the last chain adds it, then applies scale / bias / leaky
-                        float* dst = p.out + (size_t)row * p.ldc + n0 + c;
+                        float* dst = p.out ? p.out + (size_t)row * p.ldc + n0 + c : nullptr;
+                        float t[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n = n0 + c + j;
+                            t[j] = 0.f;
                             if (n < p.N) {
-                                float t = __uint_as_float(v[j]) * p.unscale;      // exact: a power of two
-                                if (!first) t += dst[j];
+                                float a = __uint_as_float(v[j]) * p.unscale;      // exact: a power of two
+                                if (!first) a += dst[j];
                                 if (last) {
-                                    t = fmaf(t, p.scale ? __ldg(p.scale + n) : 1.0f, p.bias ? __ldg(p.bias + n) : 0.0f);
-                                    t = p.leaky ? fmaxf(t, 0.1f * t) : t;
+                                    a = fmaf(a, p.scale ? __ldg(p.scale + n) : 1.0f, p.bias ? __ldg(p.bias + n) : 0.0f);
+                                    a = p.leaky ? fmaxf(a, 0.1f * a) : a;
                                 }
-                                dst[j] = t;
+                                if (dst) dst[j] = a;
+                                t[j] = a;
                             }
+                        }
+                        if (last && p.o16) {                     // (N % 32 == 0: whole chunks only) 64 + 32 + 32 bytes per row
+                            uint32_t h[16], q8[8], r8[8];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float a0 = t[2 * j] * p.oE16, a1 = t[2 * j + 1] * p.oE16;
+                                const __half2 hh = __floats2half2_rn(a0, a1);
+                                const float2 back = __half22float2(hh);
+                                h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                                const uint32_t qq = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(t[2 * j] * p.oE8, t[2 * j + 1] * p.oE8), __NV_SATFINITE, __NV_E4M3);
+                                const uint32_t rr = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((a0 - back.x) * p.ora, (a1 - back.y) * p.ora), __NV_SATFINITE, __NV_E4M3);
+                                if (j & 1) { q8[j >> 1] |= qq << 16; r8[j >> 1] |= rr << 16; }
+                                else { q8[j >> 1] = qq; r8[j >> 1] = rr; }
+                                amax_local = fmaxf(amax_local, fmaxf(fabsf(t[2 * j]), fabsf(t[2 * j + 1])));
+                            }
+                            const size_t off = (size_t)row * p.N + n0 + c;
+                            uint4* d16 = reinterpret_cast<uint4*>(p.o16 + off);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) d16[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                            uint4* d8 = reinterpret_cast<uint4*>(p.o8 + off);
+                            uint4* dr = reinterpret_cast<uint4*>(p.or8 + off);
+                            d8[0] = make_uint4(q8[0], q8[1], q8[2], q8[3]); d8[1] = make_uint4(q8[4], q8[5], q8[6], q8[7]);
+                            dr[0] = make_uint4(r8[0], r8[1], r8[2], r8[3]); dr[1] = make_uint4(r8[4], r8[5], r8[6], r8[7]);
                         }
                     }
                 }
@@ -245,6 +278,10 @@ conv_mix_kernel(const __grid_constant__ CUtensorMap map_a16, const __grid_consta
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
+        }
+        if (p.amax_out) {                                    // one atomic per warp per kernel, not per tile
+            for (int o = 16; o > 0; o >>= 1) amax_local = fmaxf(amax_local, __shfl_xor_sync(0xffffffffu, amax_local, o));
+            if (lane == 0) atomicMax(p.amax_out, __float_as_uint(amax_local));
         }
     }
 
@@ -352,9 +389,133 @@ int conv_mix_check_watchdog() { return conv_mix_check_watchdog_impl(); }
 
 using namespace y2;
 
+// Shared body: activations already in the storage format (scales fixed by `in_bound` >= their amax), weights converted here.
+static int mix_run(const char* who, const __half* x16, const uint8_t* x8, const uint8_t* rx8, float in_bound, int B, int H, int W, int cin,
+                   const float* w_hwio, int ksize, int cout, const float* scale, const float* bias, int leaky, float* y, __half* o16,
+                   uint8_t* o8, uint8_t* or8, float out_bound, unsigned int* amax_out, int terms, int kcap, int block_n, cudaStream_t s) {
+    Y2_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "%s: bad shape B=%d H=%d W=%d cin=%d cout=%d", who, B, H, W, cin, cout);
+    Y2_REQUIRE(ksize == 1 || ksize == 3, "%s: ksize must be 1 or 3 (got %d)", who, ksize);
+    Y2_REQUIRE(cin % MX_BK == 0, "%s: cin must be a multiple of 64 (got %d)", who, cin);
+    Y2_REQUIRE(terms >= 1 && terms <= 7, "%s: terms is a bit mask 1..7 (got %d)", who, terms);
+    Y2_REQUIRE(kcap >= 0, "%s: kcap is the longest accumulation chain in k-blocks, 0 = unlimited (got %d)", who, kcap);
+    Y2_REQUIRE(block_n == 0 || (block_n % 32 == 0 && block_n >= 32 && block_n <= 256), "%s: block_n %d invalid", who, block_n);
+    Y2_REQUIRE(in_bound > 0.f && isfinite(in_bound), "%s: the activations' bound must be positive and finite", who);
+    Y2_REQUIRE(!o16 || (o8 && or8 && cout % 32 == 0 && out_bound > 0.f && isfinite(out_bound)),
+               "%s: split outputs need all three arrays, cout %% 32 == 0 and a positive finite output bound", who);
+    const int taps = ksize * ksize;
+    const size_t M = (size_t)B * H * W, K = (size_t)taps * cin;
+    Y2_REQUIRE(M < ((size_t)1 << 31), "%s: too many pixels", who);
+    int bn = block_n;
+    if (bn == 0) {                                   // widest tile that divides the padded channel count evenly (as choose_tiles)
+        const int p32 = (cout + 31) / 32 * 32, nt = (p32 + 255) / 256;
+        bn = ((p32 + nt - 1) / nt + 31) / 32 * 32;
+    }
+    const int cout_pad = (cout + bn - 1) / bn * bn;
+    const int kblocks = taps * (cin / MX_BK);
+    const int nchunks = kcap > 0 ? (kblocks + kcap - 1) / kcap : 1;
+    Y2_REQUIRE(y || (o16 && nchunks == 1), "%s: the float32 output may only be omitted with split outputs and a single accumulation chain", who);
+    int dev = 0;
+    Y2_CUDA(cudaGetDevice(&dev));
+    const int num_sms = device_sm_count(dev);
+    if (mx_load_entry_points()) return -1;
+
+    unsigned int* amax_d = nullptr;
+    __half* w16 = nullptr;
+    uint8_t *w8 = nullptr, *rw8 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&amax_d, sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&w16, K * cout_pad * 2) != cudaSuccess ||
+            cudaMalloc(&w8, K * cout_pad) != cudaSuccess || cudaMalloc(&rw8, K * cout_pad) != cudaSuccess) { set_error("%s: cudaMalloc failed", who); break; }
+        if (cudaMemsetAsync(amax_d, 0, sizeof(unsigned int), s) != cudaSuccess) { set_error("%s: memset failed", who); break; }
+        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(w_hwio, K * cout, amax_d);
+        note_launch();
+        float amax_w = 0.f;
+        if (cudaMemcpyAsync(&amax_w, amax_d, sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("%s: amax pass failed: %s", who, cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (!(amax_w > 0.f) || !isfinite(amax_w)) { set_error("%s: weights are all zero or not finite", who); break; }
+        const MixScales sc = mix_scales(in_bound, amax_w);        // E16 F16 == E8 F8 4096: one accumulator for all three products
+        mix_prep_w_kernel<<<num_sms * 8, 256, 0, s>>>(w_hwio, taps, cin, cout, cout_pad, sc.F16, sc.F8, sc.rw, w16, w8, rw8);
+        note_launch();
+        if (cudaGetLastError() != cudaSuccess) { set_error("%s: operand preparation failed to launch", who); break; }
+
+        CUtensorMap ma16, ma8, mra8, mw16, mrw8, mw8;
+        if (mx_map_act(&ma16, const_cast<__half*>(x16), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, H, W, cin, ksize)) break;
+        if (mx_map_act(&ma8, const_cast<uint8_t*>(x8), CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
+        if (mx_map_act(&mra8, const_cast<uint8_t*>(rx8), CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
+        if (mx_map_w(&mw16, w16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, K, cout_pad, bn)) break;
+        if (mx_map_w(&mrw8, rw8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
+        if (mx_map_w(&mw8, w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
+
+        MixParams p;
+        memset(&p, 0, sizeof(p));
+        p.M = (int)M; p.N = cout; p.Cin = cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
+        p.block_n = bn; p.m_tiles = (int)((M + MX_BLOCK_M - 1) / MX_BLOCK_M); p.n_tiles = cout_pad / bn;
+        p.kblocks = kblocks; p.cout_pad = cout_pad;
+        p.terms = terms; p.leaky = leaky; p.unscale = sc.unscale; p.nchunks = nchunks;
+        p.scale = scale; p.bias = bias; p.out = y; p.ldc = cout;
+        if (o16) {
+            const MixScales so = mix_scales(out_bound, 1.0f);     // only the activation half is used
+            p.o16 = o16; p.o8 = o8; p.or8 = or8; p.oE16 = so.E16; p.oE8 = so.E8; p.ora = so.ra; p.amax_out = amax_out;
+        }
+        const int stage_bytes = MX_A16 + 2 * MX_A8 + bn * MX_BK * 4;
+        int stages = (MX_SMEM_LIMIT - 1024 - MX_BAR_BYTES) / stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) { set_error("%s: tile does not fit shared memory", who); break; }
+        p.num_stages = stages;
+        const int smem_bytes = stages * stage_bytes + 1024 + MX_BAR_BYTES;
+        const long long tiles = (long long)p.m_tiles * p.n_tiles;
+        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+        if (cudaFuncSetAttribute(conv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM_LIMIT) != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        g_mix_used = true;
+        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // warm-up / result
+        note_launch();
+        cudaEventRecord(e0, s);
+        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // timed (same output)
+        note_launch();
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("%s: kernel failed: %s", who, cudaGetErrorString(cudaGetLastError())); break; }
+        cudaEventElapsedTime(&g_mix_last_ms, e0, e1);
+        if (conv_mix_check_watchdog()) break;
+        rc = 0;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(amax_d); cudaFree(w16); cudaFree(w8); cudaFree(rw8);
+    return rc;
+}
+
 extern "C" {
 
 float y2_debug_last_mix_ms(void) { return g_mix_last_ms; }
+
+int y2_mix_split(const float* x, size_t n, float bound, void* x16, void* x8, void* rx8, void* stream) {
+    Y2_REQUIRE(x && x16 && x8 && rx8 && n > 0, "y2_mix_split: null argument");
+    Y2_REQUIRE(bound > 0.f && isfinite(bound), "y2_mix_split: the bound must be positive and finite");
+    int dev = 0;
+    Y2_CUDA(cudaGetDevice(&dev));
+    const MixScales sc = mix_scales(bound, 1.0f);
+    mix_prep_act_kernel<<<device_sm_count(dev) * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, sc.E16, sc.E8, sc.ra, static_cast<__half*>(x16),
+                                                                                               static_cast<uint8_t*>(x8), static_cast<uint8_t*>(rx8));
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int y2_conv2d_mix_pre(const void* x16, const void* x8, const void* rx8, float in_bound, int B, int H, int W, int cin, const float* w_hwio,
+                      int ksize, int cout, const float* scale, const float* bias, int leaky, float* y, void* o16, void* o8, void* or8,
+                      float out_bound, uint32_t* amax_out, int terms, int kcap, int block_n, void* stream) {
+    Y2_REQUIRE(x16 && x8 && rx8 && w_hwio, "y2_conv2d_mix_pre: null argument");
+    return mix_run("y2_conv2d_mix_pre", static_cast<const __half*>(x16), static_cast<const uint8_t*>(x8), static_cast<const uint8_t*>(rx8), in_bound,
+                   B, H, W, cin, w_hwio, ksize, cout, scale, bias, leaky, y, static_cast<__half*>(o16), static_cast<uint8_t*>(o8),
+                   static_cast<uint8_t*>(or8), out_bound, amax_out, terms, kcap, block_n, static_cast<cudaStream_t>(stream));
+}
 
 int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
                   const float* bias, int leaky, float* y, int terms, int kcap, int block_n, void* stream) {
@@ -369,89 +530,28 @@ int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_h
     int dev = 0;
     Y2_CUDA(cudaGetDevice(&dev));
     const int num_sms = device_sm_count(dev);
-    if (mx_load_entry_points()) return -1;
-    const int taps = ksize * ksize;
-    const size_t M = (size_t)B * H * W, K = (size_t)taps * cin;
-    Y2_REQUIRE(M < ((size_t)1 << 31), "y2_conv2d_mix: too many pixels");
-    int bn = block_n;
-    if (bn == 0) {                                   // widest tile that divides the padded channel count evenly (as choose_tiles)
-        const int p32 = (cout + 31) / 32 * 32, nt = (p32 + 255) / 256;
-        bn = ((p32 + nt - 1) / nt + 31) / 32 * 32;
-    }
-    const int cout_pad = (cout + bn - 1) / bn * bn;
-
+    const size_t n = (size_t)B * H * W * cin;
     unsigned int* amax_d = nullptr;
-    __half *x16 = nullptr, *w16 = nullptr;
-    uint8_t *x8 = nullptr, *rx8 = nullptr, *w8 = nullptr, *rw8 = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    __half* x16 = nullptr;
+    uint8_t *x8 = nullptr, *rx8 = nullptr;
     int rc = -1;
     do {
-        if (cudaMalloc(&amax_d, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&x16, M * cin * 2) != cudaSuccess ||
-            cudaMalloc(&x8, M * cin) != cudaSuccess || cudaMalloc(&rx8, M * cin) != cudaSuccess ||
-            cudaMalloc(&w16, K * cout_pad * 2) != cudaSuccess || cudaMalloc(&w8, K * cout_pad) != cudaSuccess ||
-            cudaMalloc(&rw8, K * cout_pad) != cudaSuccess) { set_error("y2_conv2d_mix: cudaMalloc failed"); break; }
-        if (cudaMemsetAsync(amax_d, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) { set_error("y2_conv2d_mix: memset failed"); break; }
-        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(x, M * cin, amax_d);
+        if (cudaMalloc(&amax_d, sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&x16, n * 2) != cudaSuccess || cudaMalloc(&x8, n) != cudaSuccess ||
+            cudaMalloc(&rx8, n) != cudaSuccess) { set_error("y2_conv2d_mix: cudaMalloc failed"); break; }
+        if (cudaMemsetAsync(amax_d, 0, sizeof(unsigned int), s) != cudaSuccess) { set_error("y2_conv2d_mix: memset failed"); break; }
+        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(x, n, amax_d);
         note_launch();
-        mix_amax_kernel<<<num_sms * 4, 256, 0, s>>>(w_hwio, K * cout, amax_d + 1);
-        note_launch();
-        float amax[2] = {0.f, 0.f};
-        if (cudaMemcpyAsync(amax, amax_d, sizeof(amax), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        float amax_x = 0.f;
+        if (cudaMemcpyAsync(&amax_x, amax_d, sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
             set_error("y2_conv2d_mix: amax pass failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        if (!(amax[0] > 0.f) || !(amax[1] > 0.f) || !isfinite(amax[0]) || !isfinite(amax[1])) { set_error("y2_conv2d_mix: operands are all zero or not finite"); break; }
-        const MixScales sc = mix_scales(amax[0], amax[1]);       // E16 F16 == E8 F8 4096: one accumulator for all three products
-        mix_prep_act_kernel<<<num_sms * 8, 256, 0, s>>>(x, M * cin, sc.E16, sc.E8, sc.ra, x16, x8, rx8);
-        note_launch();
-        mix_prep_w_kernel<<<num_sms * 8, 256, 0, s>>>(w_hwio, taps, cin, cout, cout_pad, sc.F16, sc.F8, sc.rw, w16, w8, rw8);
-        note_launch();
-        if (cudaGetLastError() != cudaSuccess) { set_error("y2_conv2d_mix: operand preparation failed to launch"); break; }
-
-        CUtensorMap ma16, ma8, mra8, mw16, mrw8, mw8;
-        if (mx_map_act(&ma16, x16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, H, W, cin, ksize)) break;
-        if (mx_map_act(&ma8, x8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
-        if (mx_map_act(&mra8, rx8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, H, W, cin, ksize)) break;
-        if (mx_map_w(&mw16, w16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, K, cout_pad, bn)) break;
-        if (mx_map_w(&mrw8, rw8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
-        if (mx_map_w(&mw8, w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, K, cout_pad, bn)) break;
-
-        MixParams p;
-        memset(&p, 0, sizeof(p));
-        p.M = (int)M; p.N = cout; p.Cin = cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
-        p.block_n = bn; p.m_tiles = (int)((M + MX_BLOCK_M - 1) / MX_BLOCK_M); p.n_tiles = cout_pad / bn;
-        p.kblocks = taps * (cin / MX_BK); p.cout_pad = cout_pad;
-        p.terms = terms; p.leaky = leaky; p.unscale = sc.unscale;
-        p.nchunks = kcap > 0 ? (p.kblocks + kcap - 1) / kcap : 1;
-        p.scale = scale; p.bias = bias; p.out = y; p.ldc = cout;
-        const int stage_bytes = MX_A16 + 2 * MX_A8 + bn * MX_BK * 4;
-        int stages = (MX_SMEM_LIMIT - 1024 - MX_BAR_BYTES) / stage_bytes;
-        if (stages > 8) stages = 8;
-        if (stages < 2) { set_error("y2_conv2d_mix: tile does not fit shared memory"); break; }
-        p.num_stages = stages;
-        const int smem_bytes = stages * stage_bytes + 1024 + MX_BAR_BYTES;
-        const long long tiles = (long long)p.m_tiles * p.n_tiles;
-        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-        if (cudaFuncSetAttribute(conv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM_LIMIT) != cudaSuccess) {
-            set_error("y2_conv2d_mix: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-            break;
-        }
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        g_mix_used = true;
-        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // warm-up / result
-        note_launch();
-        cudaEventRecord(e0, s);
-        conv_mix_kernel<<<grid, MX_THREADS, smem_bytes, s>>>(ma16, ma8, mra8, mw16, mrw8, mw8, p);      // timed (same output)
-        note_launch();
-        cudaEventRecord(e1, s);
-        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d_mix: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-        cudaEventElapsedTime(&g_mix_last_ms, e0, e1);
-        if (conv_mix_check_watchdog()) break;
-        rc = 0;
+        if (!(amax_x > 0.f) || !isfinite(amax_x)) { set_error("y2_conv2d_mix: activations are all zero or not finite"); break; }
+        if (y2_mix_split(x, n, amax_x, x16, x8, rx8, stream)) break;
+        rc = mix_run("y2_conv2d_mix", x16, x8, rx8, amax_x, B, H, W, cin, w_hwio, ksize, cout, scale, bias, leaky, y, nullptr, nullptr, nullptr,
+                     0.f, nullptr, terms, kcap, block_n, s);
     } while (0);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    cudaFree(amax_d); cudaFree(x16); cudaFree(x8); cudaFree(rx8); cudaFree(w16); cudaFree(w8); cudaFree(rw8);
+    cudaFree(amax_d); cudaFree(x16); cudaFree(x8); cudaFree(rx8);
     return rc;
 }
 
