@@ -33,7 +33,8 @@ class VariableStore(object):
         """values: dict name -> ndarray / tensor (like a checkpoint restore)."""
         import torch
         for name, val in values.items():
-            t = torch.as_tensor(np.asarray(val, dtype=np.float32) if not torch.is_tensor(val) else val).float()
+            # (a tensor is copied: the store must not alias a buffer the caller may overwrite without a version bump)
+            t = val.detach().clone().float() if torch.is_tensor(val) else torch.as_tensor(np.asarray(val, dtype=np.float32))
             if name in self._vars:
                 if tuple(self._vars[name].shape) != tuple(t.shape):
                     raise ValueError("checkpoint shape mismatch for %s" % name)
