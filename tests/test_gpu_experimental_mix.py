@@ -7,7 +7,6 @@ the error the CPU emulation predicts (tests/test_numerics_candidate_fp16_fp8.py)
 The first tests keep chains <= 36 k-blocks; the last one runs conv20's K (432 k-blocks) with and without the chain cap."""
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
