@@ -89,7 +89,10 @@ def make_slim(tf, g):
         cin = x.shape[-1]
         assert float(num_outputs) == int(num_outputs)             # `channels / 2` is a float under Python 3 (inference.py:80)
         w = g.var(scope + "/weights", (kh, kw_, cin, int(num_outputs)))
-        y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=(kh // 2, kw_ // 2)).permute(0, 2, 3, 1)
+        if getattr(g, "skip_compute", False):                     # graph construction only (make_darknet_walk_golden.py)
+            y = torch.zeros(tuple(x.shape[:3]) + (int(num_outputs),), dtype=torch.float64)
+        else:
+            y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=(kh // 2, kw_ // 2)).permute(0, 2, 3, 1)
         norm = kw.get("normalizer_fn", None)
         prev, g.scope = g.scope, scope
         if norm is not None:

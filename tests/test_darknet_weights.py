@@ -87,3 +87,45 @@ def test_load_into_store_and_run(cuda, tmp_path):
     _, out = inference.darknet(x, classes, 5)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_file_walk_matches_the_reference_importer_run_end_to_end(tmp_path):
+    """tests/golden/darknet_walk_reference.npz = what the reference's own `main()` (parse_darknet_yolo2.py:58-116) assigned to
+    every variable when run on a synthetic `.weights` stream (graph built by its own darknet(), TF session / variables replaced by
+    a holder of numpy values: tests/golden/make_darknet_walk_golden.py).  The stream is regenerated from its seed; the product
+    reader and the oracle reader must give the same 107 variables (shape, sum, leading entries, random projection), the same
+    header and the same count of left-over bytes."""
+    import struct
+    from yolo_tf_b200.parse_darknet_yolo2 import read
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "darknet_walk_reference.npz"))
+    classes, anchors, seed, nfloats, extra = (int(v) for v in g["meta"])
+    path = str(tmp_path / "synthetic.weights")
+    rs = np.random.RandomState(seed)
+    with open(path, "wb") as f:
+        f.write(struct.pack("4i", 0, 1, 0, 32013312))
+        left = nfloats + extra
+        while left > 0:
+            n = min(left, 1 << 22)
+            f.write(rs.standard_normal(n).astype("<f4").tobytes())
+            left -= n
+
+    def summary(v):
+        flat = np.asarray(v, dtype=np.float64).reshape(-1)
+        probe = np.random.RandomState(flat.size % (2 ** 31)).normal(size=flat.size)
+        return np.concatenate([[flat.sum()], flat[:8] if flat.size >= 8 else np.pad(flat, (0, 8 - flat.size)), [flat @ probe]])
+
+    header, values = read(path, classes, anchors)
+    oheader, ovalues, oremaining = read_darknet_oracle(path, classes, anchors)
+    ovalues = {"yolo2_darknet/" + k: v for k, v in ovalues.items()}                      # the oracle names variables without the scope
+    assert (header["major"], header["minor"], header["revision"], header["seen"]) == (0, 1, 0, 32013312)
+    assert header["remaining"] == oremaining == 4 * extra
+    assert "%d bytes remaining" % (4 * extra) in str(g["log_remaining"][0])
+    names = [str(n) for n in g["names"]]
+    assert set(names) == set(values) == set(ovalues) and len(names) == 107
+    for n, shp, want in zip(names, g["shapes"], g["summary"]):
+        shape = tuple(int(s) for s in str(shp).split("x"))
+        for got in (values[n], ovalues[n]):
+            assert tuple(got.shape) == shape and got.dtype == np.float32, n
+            np.testing.assert_allclose(summary(got), want, rtol=1e-12, atol=1e-9, err_msg=n)
+    assert np.array_equal(values["yolo2_darknet/conv/biases"], g["final_biases"])           # incl. the per-anchor re-ordering
+    assert np.array_equal(values["yolo2_darknet/conv0/weights"], g["conv0_weights"])        # Darknet [O,I,kh,kw] -> HWIO
