@@ -112,3 +112,27 @@ def test_label_encoder_has_no_cpu_path():
     from yolo_tf_b200.utils import data
     with pytest.raises(_lib.Y2Error):
         data.transform_labels_batch([np.array([1])], [np.zeros((1, 4), np.float32)], 20, 13, 13, device="cpu")
+
+
+def test_builder_constructor_reads_names_size_anchors_and_inference_like_the_reference(tmp_path):
+    """model/yolo2/__init__.py:97-107: names from <cachedir>/names, width / height / anchors (TSV with a header row,
+    config/yolo2/anchors/*.tsv) and the string-dispatched inference function from the [yolo2] section."""
+    import configparser
+    from yolo_tf_b200.model.yolo2 import Builder, inference
+    base = tmp_path / "base"
+    (base / "cache" / "20").mkdir(parents=True)
+    (base / "cache" / "20" / "names").write_text("\n".join("class%d" % i for i in range(20)) + "\n")
+    tsv = tmp_path / "voc.tsv"
+    tsv.write_text("width\theight\n1.08\t1.19\n3.42\t4.41\n6.63\t11.38\n9.42\t5.11\n16.62\t10.52\n")
+    cfg = configparser.ConfigParser()
+    cfg.read_dict({"config": {"basedir": str(base), "model": "yolo2"}, "cache": {"names": "config/names/20"},
+                   "yolo2": {"width": "416", "height": "608", "anchors": str(tsv), "inference": "tiny"},
+                   "yolo2_hparam": {"prob": "1", "iou_best": "5", "iou_normal": "1", "coords": "1"}})
+    b = Builder(None, cfg)
+    assert b.names == ["class%d" % i for i in range(20)] and (b.width, b.height) == (416, 608)
+    assert b.anchors.shape == (5, 2) and b.anchors.dtype == np.float64 and b.anchors[2].tolist() == [6.63, 11.38]
+    assert b.func is inference.tiny
+    cfg.set("yolo2", "inference", "darknet")
+    assert Builder(None, cfg).func is inference.darknet
+    v = Builder.from_values(b.names, 416, 608, b.anchors)
+    assert v.func is inference.darknet and v.config.getfloat("yolo2_hparam", "iou_best") == 5.0    # config.ini:98-102 defaults
