@@ -119,6 +119,15 @@ size_t y2_standardize_workspace_bytes(int B, size_t n_per_image);
 int y2_per_image_standardization(const void* x, int elem_bytes, int B, size_t n_per_image, float* out, void* ws,
                                  size_t ws_bytes, void* stream);
 
+/* detect.py:65 `_image.resize((width, height))`: Pillow's Image.resize on 8-bit channels, bit for bit -- resample 3 = BICUBIC
+ * (Pillow's default since 7.0: a = -0.5, antialiased when shrinking, 22-bit fixed-point weights, horizontal pass into an 8-bit
+ * intermediate then vertical) or 0 = NEAREST (its default before).  src [in_h][in_w][channels], dst [out_h][out_w][channels],
+ * uint8 device pointers.  The algorithm is Pillow's (third-party, unpinned by the reference); the restatement is verified
+ * against Pillow itself on the CPU.  NOT YET RUN ON A GPU (written after the round-1 GPU budget was spent). */
+size_t y2_resize_workspace_bytes(int in_h, int in_w, int out_h, int out_w, int channels, int resample);
+int y2_resize_u8(const uint8_t* src, int in_h, int in_w, int channels, uint8_t* dst, int out_h, int out_w, int resample, void* ws,
+                 size_t ws_bytes, void* stream);
+
 /* detect.py:72-87 after non_max_suppress: per box index = argmax_c conf (first maximum), kept iff conf[index] > threshold;
  * kept boxes are appended in box-index order: box[b][i], cls[b][i], score[b][i], xywh[b][i] = (xy_min*scale,
  * (xy_max-xy_min)*scale) with scale = image size / cells (detect.py:72), count[b] = number kept.  All device, [B][N]. */

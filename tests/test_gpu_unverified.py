@@ -48,3 +48,30 @@ def test_tiny_forward_non_square_vs_the_reference_graph_golden(cuda):
     _lib.check(_lib.lib().y2_check_async_errors())
     assert scope == "yolo2_tiny" and tuple(out.shape) == (2, 3, 2, 125)
     assert _rel(out.cpu().numpy(), d["tiny_out"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["shrink", "enlarge", "mixed", "same_w", "tiny", "strong"])
+def test_resize_on_the_device_reproduces_pillow_bit_for_bit(cuda, name):
+    """csrc/y2_resize.cu against Pillow's own outputs (tests/golden/resize.npz); the same per-element code passes on the CPU
+    (tests/test_resize.py), so what this adds is the kernels' launch geometry and table upload."""
+    import torch
+    from yolo_tf_b200.utils import preprocess
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize.npz"))
+    oh, ow = (int(v) for v in g[name + "_size"])
+    x = torch.from_numpy(g[name + "_in"]).to(cuda)
+    for flt, key in ((preprocess.BICUBIC, "_bicubic"), (preprocess.NEAREST, "_nearest")):
+        got = preprocess.resize(x, ow, oh, flt).cpu().numpy()
+        assert np.array_equal(got, g[name + key]), (name, flt, int((got != g[name + key]).sum()))
+
+
+def test_resize_then_standardize_is_the_detect_preprocessing(cuda):
+    """detect.py:65: uint8 image -> resize -> float32 -> per_image_standardization, all on the device from one uint8 upload."""
+    import torch
+    from oracle.prepost_oracle import per_image_standardization_oracle
+    from oracle.resize_oracle import resize_oracle
+    from yolo_tf_b200.utils import preprocess
+    rs = np.random.RandomState(8)
+    img = rs.randint(0, 256, size=(375, 500, 3)).astype(np.uint8)
+    dev = preprocess.per_image_standardization(preprocess.resize(torch.from_numpy(img).to(cuda), 416, 416)).cpu().numpy()
+    ref = np.asarray(per_image_standardization_oracle(resize_oracle(img, 416, 416).astype(np.float32)), dtype=np.float64)
+    assert dev.shape == (416, 416, 3) and np.abs(dev - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1.0)

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "y2_adam_workspace_bytes": (c_sz, [c_p]),
     "y2_standardize_workspace_bytes": (c_sz, [c_i, c_sz]),
     "y2_per_image_standardization": (c_i, [c_p, c_i, c_i, c_sz, c_p, c_p, c_sz, c_p]),
+    "y2_resize_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i]),
+    "y2_resize_u8": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_sz, c_p]),
     "y2_detections": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
     "y2_transform_labels": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "y2_adam_step": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_f, c_f, c_f, c_f, ctypes.c_longlong, c_f, c_p, c_sz, c_p]),
