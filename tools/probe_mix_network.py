@@ -18,9 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_tf_b200 import _lib  # noqa: E402
 from yolo_tf_b200.model.yolo2.inference import layer_geometry  # noqa: E402
 
-L = _lib.lib()
-dev = "cuda"
-B, SIZE, C, A = 2, 416, 80, 5
+DRY = os.environ.get("Y2_PROBE_DRYRUN") == "1"       # CPU dry run of the harness glue (shapes, bounds, concat): no library calls
+L = None if DRY else _lib.lib()
+dev = "cpu" if DRY else "cuda"
+B, SIZE, C, A = (1, 64, 20, 5) if DRY else (2, 416, 80, 5)
 rs = np.random.RandomState(1)
 layers = []
 for name, k, cin, cout, has_bn, pool in layer_geometry(C, A):
@@ -49,6 +50,8 @@ def conv_ref(x, w, scale, bias, leaky, dtype):
 
 
 def conv_bf16x3(x, w, scale, bias, leaky):
+    if DRY:
+        return conv_ref(x, w, scale, bias, leaky, torch.float32)
     b, h, wd, cin = x.shape
     y = torch.empty(b, h, wd, w.shape[3], device=dev)
     _lib.check(L.y2_conv2d(_lib.ptr(x.contiguous()), b, h, wd, cin, _lib.ptr(w), w.shape[0], w.shape[3], _lib.ptr(scale), _lib.ptr(bias), int(leaky),
@@ -66,6 +69,12 @@ def make_conv_mix(kcap, stats):
         x8, rx8 = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
         # the scales a producer would have used for this tensor: from ITS one-layer bound, carried along by the caller
         bound = stats.get("bound", amax_in)
+        assert bound >= amax_in * (1 - 1e-6), (bound, amax_in)                     # the bound is a bound
+        if DRY:
+            y = conv_ref(x, w, scale, bias, leaky, torch.float32)
+            stats["bound"] = float((scale.abs() * w.abs().sum(dim=(0, 1, 2))).max()) * amax_in + float(bias.abs().max())
+            stats.setdefault("looseness", []).append(stats["bound"] / float(y.abs().max()))
+            return y
         _lib.check(L.y2_mix_split(_lib.ptr(x), n, bound, _lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), None))
         y = torch.empty(b, h, wd, w.shape[3], device=dev)
         _lib.check(L.y2_conv2d_mix_pre(_lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), bound, b, h, wd, cin, _lib.ptr(w), w.shape[0], w.shape[3], _lib.ptr(scale),
@@ -97,7 +106,8 @@ def run(conv, dtype_glue=torch.float32, stats=None):
                 stats["tap_bound"] = stats["bound"]
         if pool:
             x = F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
-    torch.cuda.synchronize()
+    if not DRY:
+        torch.cuda.synchronize()
     return x
 
 
@@ -110,7 +120,8 @@ for kcap in (32, 16, 0):
     st = {}
     out["mix_kcap%d" % kcap] = rel(run(make_conv_mix(kcap, st), stats=st))
     out["mix_kcap%d_looseness_log2_max" % kcap] = math.log2(max(st["looseness"]))
-_lib.check(L.y2_check_async_errors())
+if not DRY:
+    _lib.check(L.y2_check_async_errors())
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/probe_mix_network.json", "w"), indent=1)
