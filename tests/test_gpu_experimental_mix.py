@@ -40,17 +40,19 @@ def _run(b, hw, cin, cout, k, terms, leaky=1, block_n=0, seed=0, kcap=0):
 @pytest.mark.parametrize("shape", [(2, 26, 256, 512, 3), (2, 13, 128, 1024, 3), (3, 13, 1024, 425, 1), (1, 52, 128, 64, 1), (2, 26, 64, 96, 3)])
 def test_mixed_kind_conv_matches_fp64(shape):
     err = _run(*shape, terms=7)
-    assert err <= 2e-5, err                      # emulation: 3e-6 .. 6e-6 per layer; shipped bf16x3 kernel: 4.5e-6
+    # exact-accumulation emulation of these shapes: 0.9e-5 .. 1.4e-5 (shipped bf16x3 kernel: 4.5e-6 measured); the fp16 term alone
+    # gives 2.8e-4 and a wrong descriptor / format garbage, so 3e-5 separates "works" from "does not" with room for the accumulator
+    assert err <= 3e-5, err
 
 
 def test_fp16_product_alone_is_not_enough_and_tile_widths_agree():
     assert 5e-5 < _run(2, 26, 256, 512, 3, terms=1) < 3e-3
     a = _run(2, 26, 256, 512, 3, terms=7, block_n=128)
-    assert a <= 2e-5, a
+    assert a <= 3e-5, a
 
 
 def test_partial_last_tile_and_linear_output():
-    assert _run(1, 13, 64, 32, 3, terms=7, leaky=0) <= 2e-5        # 169 pixels: second M tile mostly out of range
+    assert _run(1, 13, 64, 32, 3, terms=7, leaky=0) <= 3e-5        # 169 pixels: second M tile mostly out of range
 
 
 def test_long_chains_need_the_cap_here_too():
@@ -58,7 +60,7 @@ def test_long_chains_need_the_cap_here_too():
     chains of <= 32 k-blocks summed in fp32 by the epilogue bring the error back to the short-chain level."""
     capped = _run(2, 13, 3072, 256, 3, terms=7, kcap=32)
     uncapped = _run(2, 13, 3072, 256, 3, terms=7, kcap=0)
-    assert capped <= 2e-5, capped
+    assert capped <= 3e-5, capped                 # ~1e-5 from the operand formats + ~0.6e-5 of truncation bias per 32-k-block chain
     assert uncapped > capped, (uncapped, capped)
 
 
@@ -93,7 +95,7 @@ def test_two_layers_chained_in_the_storage_format():
     torch.cuda.synchronize()
     ref1 = F.conv2d(x.double().permute(0, 3, 1, 2), w1.double().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1) * s1.double() + b1.double()
     ref1 = torch.maximum(ref1, 0.1 * ref1)
-    assert float((y1.double() - ref1).abs().max() / ref1.abs().max()) <= 2e-5
+    assert float((y1.double() - ref1).abs().max() / ref1.abs().max()) <= 3e-5        # emulation: 1.0e-5
     assert float(y1.abs().max()) <= bound1                                                # the bound is a bound
     assert amax1.view(torch.float32).item() == float(y1.abs().max())                     # published amax = what was written
     ba = 2.0 ** math.ceil(math.log2(bound1))
@@ -108,4 +110,4 @@ def test_two_layers_chained_in_the_storage_format():
     _lib.check(L.y2_check_async_errors())
     ref2 = F.conv2d(ref1.permute(0, 3, 1, 2), w2.double().permute(3, 2, 0, 1)).permute(0, 2, 3, 1) * s2.double() + b2.double()
     ref2 = torch.maximum(ref2, 0.1 * ref2)
-    assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) <= 3e-5
+    assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) <= 4e-5        # emulation: 1.1e-5
