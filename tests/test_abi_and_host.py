@@ -136,3 +136,84 @@ def test_builder_constructor_reads_names_size_anchors_and_inference_like_the_ref
     assert Builder(None, cfg).func is inference.darknet
     v = Builder.from_values(b.names, 416, 608, b.anchors)
     assert v.func is inference.darknet and v.config.getfloat("yolo2_hparam", "iou_best") == 5.0    # config.ini:98-102 defaults
+
+
+def test_integration_md_ctypes_stub_matches_the_binding():
+    """INTEGRATION.md section 2 is the binding a maintainer of the reference would paste: execute that code block as written and
+    compare every argtypes / restype it sets with yolo_tf_b200/_lib.py (which the GPU suite exercises)."""
+    import ctypes
+    from yolo_tf_b200 import _lib
+    _lib.lib()
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if "ctypes.CDLL" in b]
+    assert len(stub) == 1
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(stub[0], "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    L = ns["L"]
+    checked = 0
+    for name, (res, args) in _lib._SIGNATURES.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        got = list(fn.argtypes)
+        assert len(got) == len(args), (name, len(got), len(args))
+        for a, b in zip(got, args):
+            # c_void_p vs POINTER(struct) are both pointers; scalars must agree exactly
+            pa, pb = (a is ctypes.c_void_p or hasattr(a, "contents")), (b is ctypes.c_void_p or b is ctypes.c_char_p or hasattr(b, "contents"))
+            assert (pa and pb) or a is b, (name, a, b)
+        if fn.restype is not ctypes.c_int:                      # ctypes' default restype is c_int
+            assert fn.restype is res, (name, fn.restype, res)
+        checked += 1
+    assert checked >= 18
+
+
+def test_binding_argument_counts_and_kinds_match_the_header():
+    """A ctypes signature that disagrees with the C prototype corrupts the call silently: parse include/yolo2_b200.h and compare
+    every function's parameter list (count; pointer / integer / float / size_t kind) and return type with yolo_tf_b200/_lib.py."""
+    import ctypes
+    from yolo_tf_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "yolo2_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef struct y2_head_outputs \{.*?\} y2_head_outputs;", "", src, flags=re.S)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(y2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) == len(_lib._SIGNATURES), (len(protos), len(_lib._SIGNATURES))
+
+    def kind_of_c(decl):                 # (on LP64 ctypes aliases c_size_t / c_ulonglong / c_ulong: 64-bit integers form one kind)
+        d = " ".join(decl.split())
+        if "*" in d or "[" in d:
+            return "ptr"
+        if d.startswith("size_t") or d.startswith("long long") or d.startswith("unsigned long long"):
+            return "i64"
+        if d.startswith("float"):
+            return "float"
+        if d.startswith("int") or d.startswith("uint32_t"):
+            return "i32"
+        raise AssertionError("unparsed parameter: %r" % d)
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents"):
+            return "ptr"
+        if t is ctypes.c_float:
+            return "float"
+        assert t in (ctypes.c_int, ctypes.c_size_t, ctypes.c_longlong, ctypes.c_ulonglong), t
+        return "i32" if ctypes.sizeof(t) == 4 else "i64"
+
+    for ret, name, params in protos:
+        res, args = _lib._SIGNATURES[name]
+        plist = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        assert len(plist) == len(args), (name, plist, args)
+        for decl, t in zip(plist, args):
+            assert kind_of_c(decl) == kind_of_ctypes(t), (name, decl, t)
+        r = " ".join(ret.split())
+        if r == "void":
+            assert res is None, name
+        elif "*" in r:
+            assert res in (ctypes.c_char_p, ctypes.c_void_p), name
+        else:
+            assert kind_of_c(r + " x") == kind_of_ctypes(res), (name, r, res)
