@@ -86,3 +86,30 @@ def test_device_encoder_errors_like_the_reference(cuda):
         transform_labels(np.array([20]), np.array([[0.1, 0.1, 0.2, 0.2]], np.float32), 20, 13, 13)
     with pytest.raises(AssertionError):                       # xmax < xmin (:142)
         transform_labels(np.array([0]), np.array([[0.5, 0.1, 0.2, 0.2]], np.float32), 20, 13, 13)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/data/__init__.py"), reason="the reference checkout only exists in the authoring container")
+def test_label_oracle_against_the_live_reference_on_random_cases():
+    """Beyond the committed goldens: 60 fresh random object lists per run through the reference's own transform_labels (its source
+    compiled from the file, tests/golden/make_labels_golden.py) -- crowded cells, square and non-square grids, 1 .. 80 classes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    try:
+        from make_labels_golden import load_reference_transform_labels
+    finally:
+        sys.path.pop(0)
+    from oracle.head_oracle import transform_labels_oracle
+    tl = load_reference_transform_labels()
+    rs = np.random.RandomState(99)
+    for case in range(60):
+        classes, cw, ch = int(rs.choice([1, 3, 20, 80])), int(rs.randint(1, 20)), int(rs.randint(1, 20))
+        n = int(rs.randint(0, 40))
+        cx, cy = rs.uniform(0, 1, n), rs.uniform(0, 1, n)
+        w, h = rs.uniform(0.01, 0.7, n), rs.uniform(0.01, 0.7, n)
+        coord = np.stack([np.clip(cx - w / 2, 0, 1 - 1e-6), np.clip(cy - h / 2, 0, 1 - 1e-6), np.clip(cx + w / 2, 0, 1 - 1e-6),
+                          np.clip(cy + h / 2, 0, 1 - 1e-6)], 1).astype(np.float32).reshape(n, 4)
+        cls = rs.randint(0, classes, n)
+        want = tl(cls, coord, classes, cw, ch)
+        got = transform_labels_oracle(cls, coord, classes, cw, ch)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32)), case

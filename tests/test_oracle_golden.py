@@ -165,3 +165,46 @@ def test_oracle_conv_bn_pool_follow_the_tf_definitions_written_out_as_loops():
     want_t = a.reshape(2, 2, 2, 2, 2, 4).max(axis=(2, 4)) @ prm["conv/weights"].astype(np.float64)[0, 0] + prm["conv/biases"].astype(np.float64)
     np.testing.assert_allclose(got_t, want_t, rtol=1e-11, atol=1e-11)
     assert float(leaky_oracle(torch.tensor(-2.0, dtype=torch.float64))) == -0.2 and float(leaky_oracle(torch.tensor(0.0))) == 0.0
+
+
+REF_NMS = "/root/reference/utils/postprocess.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_NMS), reason="the reference checkout only exists in the authoring container")
+def test_nms_oracles_against_the_live_reference_on_random_cases():
+    """Beyond the 9 committed goldens: 40 fresh random cases per run against the reference's own non_max_suppress loaded by path
+    (pure numpy / Python, so it runs here) -- heavy score ties (quantised scores), duplicate boxes, thresholds hit exactly,
+    1 .. 6 classes -- for the numpy oracle and its C twin, bit for bit in the zeroed matrix and in the returned order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_postprocess_live", REF_NMS)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rs = np.random.RandomState(20260117)
+    for case in range(40):
+        cells, a, c = rs.randint(1, 10), rs.randint(1, 4), rs.randint(1, 7)
+        n = cells * a
+        centre = rs.uniform(0, 4, size=(cells, a, 2))
+        wh = rs.uniform(0.5, 3, size=(cells, a, 2))
+        lo, hi = (centre - wh / 2).astype(np.float32), (centre + wh / 2).astype(np.float32)
+        if case % 4 == 0 and n > 2:                                   # duplicate boxes
+            lo[-1, -1], hi[-1, -1] = lo[0, 0], hi[0, 0]
+        conf = rs.uniform(0, 1, size=(cells, a, c)).astype(np.float32)
+        if case % 2 == 0:
+            conf = (np.round(conf * 4) / 4).astype(np.float32)        # ties, and values exactly on a threshold of 0.25 / 0.5
+        thr, thr_iou = [(0.3, 0.4), (0.25, 0.5), (0.5, 0.25)][case % 3]
+        want = conf.copy()
+        boxes = ref.non_max_suppress(want, lo, hi, thr, thr_iou)
+        flat_lo = lo.reshape(n, 2)
+        want_order = []
+        for row, b_lo, _ in boxes:                                    # rows are views into `want`: recover each one's box index
+            off = (row.__array_interface__["data"][0] - want.__array_interface__["data"][0]) // (4 * c)
+            want_order.append(off)
+            assert np.array_equal(b_lo, flat_lo[off])
+        got = conf.copy()
+        order = nms_oracle(got, lo, hi, thr, thr_iou)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), case
+        assert list(order) == want_order, case
+        got_c = conf.copy().reshape(1, n, c)
+        order_c = nms_c_batch(got_c, lo.reshape(1, n, 2), hi.reshape(1, n, 2), thr, thr_iou)
+        assert np.array_equal(got_c.reshape(cells, a, c).view(np.uint32), want.view(np.uint32)), case
+        assert list(order_c[0]) == want_order, case
