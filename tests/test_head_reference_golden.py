@@ -63,3 +63,39 @@ def test_ties_case_really_has_tied_best_boxes_and_the_empty_image_none():
     assert (mb.sum(-1) == 2).any()              # two anchors share the maximum IoU in some object cell: both count (tf.equal)
     d, net, classes, anchors, labels = _load("voc")
     assert labels[0][1].sum() == 0 and labels[0][0].sum() > 0          # second image of the batch has no object
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/model/yolo2/__init__.py"), reason="the reference checkout only exists in the authoring container")
+def test_head_oracle_against_the_live_reference_source_on_random_cases():
+    """Beyond the 4 committed cases: 12 fresh random heads per run through the reference's own Model / Objectives source (the
+    generator's stand-in for TF, float64): grids 1 x 1 .. 9 x 9 incl. non-square, 1 .. 6 anchors, 1 .. 30 classes, 0 .. 12 objects."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    try:
+        import make_head_golden as mh
+        from make_labels_golden import load_reference_transform_labels
+    finally:
+        sys.path.pop(0)
+    import torch
+    tl = load_reference_transform_labels()
+    rs = np.random.RandomState(123)
+    for case in range(12):
+        b, hc, wc, a, c = int(rs.randint(1, 4)), int(rs.randint(1, 10)), int(rs.randint(1, 10)), int(rs.randint(1, 7)), int(rs.randint(1, 31))
+        anchors = rs.uniform(0.5, 8.0, size=(a, 2))
+        net = rs.normal(0, 1.2, size=(b, hc, wc, a * (5 + c))).astype(np.float32)
+        per = []
+        for _ in range(b):
+            n = int(rs.randint(0, 13))
+            cx, cy, w, h = rs.uniform(0, 1, n), rs.uniform(0, 1, n), rs.uniform(0.05, 0.6, n), rs.uniform(0.05, 0.6, n)
+            coord = np.stack([np.clip(cx - w / 2, 0, 1 - 1e-6), np.clip(cy - h / 2, 0, 1 - 1e-6), np.clip(cx + w / 2, 0, 1 - 1e-6),
+                              np.clip(cy + h / 2, 0, 1 - 1e-6)], 1).astype(np.float32).reshape(n, 4)
+            per.append(tl(rs.randint(0, c, n), coord, c, wc, hc))
+        labels = tuple(np.stack([p[i] for p in per], 0) for i in range(6))
+        attrs, obj, grad = mh.run_reference(net, c, anchors, labels, torch.float64)
+        m = ho.decode_oracle(net, c, anchors, dtype=np.float64)
+        for k in ATTRS:
+            np.testing.assert_allclose(m[k], attrs[k], rtol=1e-12, atol=1e-13, err_msg="%d %s" % (case, k))
+        o, g = ho.loss_grad_oracle(net, c, anchors, labels, hparam=HPARAM, dtype=np.float64)
+        for k in HPARAM:
+            np.testing.assert_allclose(float(o[k]), float(obj[k]), rtol=1e-11, atol=1e-18, err_msg="%d %s" % (case, k))
+        np.testing.assert_allclose(g, grad, rtol=1e-9, atol=1e-15, err_msg=str(case))
