@@ -15,18 +15,34 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_tf_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
-L.y2_debug_set.argtypes = [ctypes.c_int, ctypes.c_double]
-L.y2_debug_last_conv_ms.restype = ctypes.c_float
+DRY = os.environ.get("Y2_PROBE_DRYRUN") == "1"       # CPU dry run of this script's own control flow: no library, no CUDA
+if DRY:
+    class _Fake(object):
+        def __getattr__(self, name):
+            return (lambda *a: 1.0) if name.endswith("_ms") else (lambda *a: 0)
+    L = _Fake()
+    _lib.ptr = lambda t, dtype=None: None
+    _lib.check = lambda rc: None
+    _cuda_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda: None
+    DEV = "cpu"
+else:
+    L = _lib.lib()
+    L.y2_debug_set.argtypes = [ctypes.c_int, ctypes.c_double]
+    L.y2_debug_last_conv_ms.restype = ctypes.c_float
+    DEV = "cuda"
 out = []
 # one tile per SM (conv13's shape at batch 28 -> 148 tiles of 128 x 256), then conv8 / conv18 / conv20 / conv14 at the bench batch
-for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 1024, 3), (32, 13, 3072, 1024, 3), (32, 13, 1024, 512, 1)]:
-    g = torch.Generator(device="cuda").manual_seed(1)
-    x = torch.randn(B, hw, hw, cin, device="cuda", generator=g)
+SHAPES = [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 1024, 3), (32, 13, 3072, 1024, 3), (32, 13, 1024, 512, 1)]
+if DRY:
+    SHAPES = [(1, 13, 64, 64, 3), (1, 13, 64, 32, 1)]
+for (B, hw, cin, cout, k) in SHAPES:
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(B, hw, hw, cin, device=DEV, generator=g)
     x = torch.maximum(x, 0.1 * x)
-    w = torch.randn(k, k, cin, cout, device="cuda", generator=g) * (2.0 / (k * k * cin)) ** 0.5
-    y = torch.empty(B, hw, hw, cout, device="cuda")
-    ref = torch.zeros(B, hw, hw, cout, dtype=torch.float64, device="cuda")
+    w = torch.randn(k, k, cin, cout, device=DEV, generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    y = torch.empty(B, hw, hw, cout, device=DEV)
+    ref = torch.zeros(B, hw, hw, cout, dtype=torch.float64, device=DEV)
     for i0 in range(0, B, 4):
         ref[i0:i0 + 4] = F.conv2d(x[i0:i0 + 4].double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
     flops = 2.0 * B * hw * hw * k * k * cin * cout
@@ -58,20 +74,20 @@ for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32
     print(json.dumps(row), flush=True)
 # ---- epilogue cost of the storage format: float32 output only vs float32 + split triple + amax vs split triple only
 epi = []
-for (B, hw, cin, cout, k) in [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 512, 1)]:
-    g = torch.Generator(device="cuda").manual_seed(2)
-    x = torch.randn(B, hw, hw, cin, device="cuda", generator=g)
-    w = torch.randn(k, k, cin, cout, device="cuda", generator=g) * (2.0 / (k * k * cin)) ** 0.5
+for (B, hw, cin, cout, k) in (SHAPES[:1] if DRY else [(28, 13, 512, 1024, 3), (32, 26, 256, 512, 3), (32, 13, 1024, 512, 1)]):
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(B, hw, hw, cin, device=DEV, generator=g)
+    w = torch.randn(k, k, cin, cout, device=DEV, generator=g) * (2.0 / (k * k * cin)) ** 0.5
     n0, n1 = x.numel(), B * hw * hw * cout
     amax_x = float(x.abs().max())
     bound = float(w.abs().sum(dim=(0, 1, 2)).max()) * amax_x
-    x16 = torch.empty(n0, dtype=torch.float16, device="cuda")
-    x8, rx8 = torch.empty(n0, dtype=torch.uint8, device="cuda"), torch.empty(n0, dtype=torch.uint8, device="cuda")
+    x16 = torch.empty(n0, dtype=torch.float16, device=DEV)
+    x8, rx8 = torch.empty(n0, dtype=torch.uint8, device=DEV), torch.empty(n0, dtype=torch.uint8, device=DEV)
     _lib.check(L.y2_mix_split(_lib.ptr(x), n0, amax_x, _lib.ptr(x16), _lib.ptr(x8), _lib.ptr(rx8), None))
-    y = torch.empty(B, hw, hw, cout, device="cuda")
-    o16 = torch.empty(n1, dtype=torch.float16, device="cuda")
-    o8, or8 = torch.empty(n1, dtype=torch.uint8, device="cuda"), torch.empty(n1, dtype=torch.uint8, device="cuda")
-    amax = torch.zeros(1, dtype=torch.int32, device="cuda")
+    y = torch.empty(B, hw, hw, cout, device=DEV)
+    o16 = torch.empty(n1, dtype=torch.float16, device=DEV)
+    o8, or8 = torch.empty(n1, dtype=torch.uint8, device=DEV), torch.empty(n1, dtype=torch.uint8, device=DEV)
+    amax = torch.zeros(1, dtype=torch.int32, device=DEV)
     row = {"shape": [B, hw, cin, cout, k]}
     for name, yy, split in (("f32_only", y, False), ("f32_and_split", y, True), ("split_only", None, True)):
         ts = []
