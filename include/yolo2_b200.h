@@ -178,24 +178,6 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
 int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* dy, int ksize, int cout, float* dw,
                     int max_ctas, void* stream);
 
-/* EXPERIMENTAL, diagnostic only (csrc/y2_conv_mix.cu; not used by any other entry point): the same conv as y2_conv2d with
- * every product issued as one fp16 MMA plus two e4m3 correction MMAs (2 MMA-equivalents instead of 3).
- * terms: bit mask of the products to issue (1 = fp16 x fp16, 2 = x8 * w-residual, 4 = x-residual * w8; 7 = all).
- * kcap: longest tensor-core accumulation chain in 64-channel k-blocks (0 = the whole K in one chain; the network kernels use 32).
- * cin must be a multiple of 64.  y2_debug_last_mix_ms() = device time of the kernel in the last call. */
-int y2_conv2d_mix(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout, const float* scale,
-                  const float* bias, int leaky, float* y, int terms, int kcap, int block_n, void* stream);
-float y2_debug_last_mix_ms(void);
-/* The same with the activations already in the storage format of that mode (x16 = fp16(x E16), x8 = e4m3(x E8), rx8 = e4m3 of
- * the fp16 residual; the two power-of-two scales follow from `in_bound` >= amax|x|), as y2_mix_split or a previous
- * y2_conv2d_mix_pre wrote them: chains layers without leaving the format.  Optional outputs: y (float32), the split form of
- * the result (o16 / o8 / or8, scales from `out_bound`, cout % 32 == 0) and the atomicMax of |result| (float bits) the next
- * layer derives its bound from.  All pointers are device pointers except none; diagnostic only. */
-int y2_mix_split(const float* x, size_t n, float bound, void* x16, void* x8, void* rx8, void* stream);
-int y2_conv2d_mix_pre(const void* x16, const void* x8, const void* rx8, float in_bound, int B, int H, int W, int cin, const float* w_hwio,
-                      int ksize, int cout, const float* scale, const float* bias, int leaky, float* y, void* o16, void* o8, void* or8,
-                      float out_bound, uint32_t* amax_out, int terms, int kcap, int block_n, void* stream);
-
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.
  * out[b, y, x, (dy*stride+dx)*C + c] = in[b, stride*y+dy, stride*x+dx, c]. */
 int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream);

@@ -26,13 +26,16 @@ from .darknet_oracle import BN_EPS, LEAKY_ALPHA, layer_table
 BN_DECAY = 0.999
 
 
-def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=torch.float64, taps=None):
+def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=torch.float64, taps=None, device="cpu", taps_numpy=True):
     """Returns dict(objectives, total, grads {variable name -> ndarray}, net, new_moving {name -> ndarray},
-    dnet = d total / d net).  Variable names as in oracle/darknet_oracle.py (no scope prefix)."""
+    dnet = d total / d net).  Variable names as in oracle/darknet_oracle.py (no scope prefix).
+    ``device``: where torch evaluates this same restatement.  "cpu" is the oracle of record; "cuda" (float64,
+    TF32 off) is used by the -m gpu tests only for BASELINE config 3 at its full size (B = 64, 416 x 416), where the
+    float64 step is ~7 TFLOP and tens of GB -- minutes on the host cores, seconds on the device."""
     anchors = np.asarray(anchors, dtype=np.float64)
     A = len(anchors)
-    P = {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=("moving" not in k)) for k, v in params.items()}
-    x = torch.tensor(np.ascontiguousarray(x_nhwc), dtype=dtype).permute(0, 3, 1, 2)
+    P = {k: torch.tensor(np.asarray(v), dtype=dtype, device=device, requires_grad=("moving" not in k)) for k, v in params.items()}
+    x = torch.tensor(np.ascontiguousarray(x_nhwc), dtype=dtype, device=device).permute(0, 3, 1, 2)
     new_moving = {}
     passthrough = None
     for name, k, cin, cout, then in layer_table(classes, A):
@@ -51,10 +54,10 @@ def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=to
             inv = torch.rsqrt(var + BN_EPS) * P[name + "/BatchNorm/gamma"]
             x = x * inv.view(1, -1, 1, 1) + (P[name + "/BatchNorm/beta"] - mean * inv).view(1, -1, 1, 1)
             x = torch.maximum(x, LEAKY_ALPHA * x)
-            new_moving[name + "/BatchNorm/moving_mean"] = (P[name + "/BatchNorm/moving_mean"] * BN_DECAY + mean.detach() * (1 - BN_DECAY)).numpy()
-            new_moving[name + "/BatchNorm/moving_variance"] = (P[name + "/BatchNorm/moving_variance"] * BN_DECAY + var.detach() * (1 - BN_DECAY)).numpy()
+            new_moving[name + "/BatchNorm/moving_mean"] = (P[name + "/BatchNorm/moving_mean"] * BN_DECAY + mean.detach() * (1 - BN_DECAY)).cpu().numpy()
+            new_moving[name + "/BatchNorm/moving_variance"] = (P[name + "/BatchNorm/moving_variance"] * BN_DECAY + var.detach() * (1 - BN_DECAY)).cpu().numpy()
         if taps is not None:
-            taps[name] = x.detach().permute(0, 2, 3, 1).contiguous().numpy()
+            taps[name] = x.detach().permute(0, 2, 3, 1).contiguous().cpu().numpy() if taps_numpy else x.detach().permute(0, 2, 3, 1)
         if then == "passthrough+pool":
             passthrough = x
         if then in ("pool", "passthrough+pool"):
@@ -64,16 +67,16 @@ def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=to
     b, hc, wc, _ = net.shape
     cells = hc * wc
     inp = net.reshape(b, cells, A, 5 + classes)
-    anc = torch.tensor(anchors, dtype=dtype)
+    anc = torch.tensor(anchors, dtype=dtype, device=device)
     sig = torch.sigmoid(inp[..., :3])
     iou_p, oxy = sig[..., 0], sig[..., 1:3]
     wh = torch.exp(inp[..., 3:5]) * anc.reshape(1, 1, A, 2)
     prob_p = torch.softmax(inp[..., 5:], -1)
     areas_p = wh[..., 0] * wh[..., 1]
     omin, omax = oxy - wh / 2, oxy + wh / 2
-    wh01s = torch.sqrt(wh / torch.tensor([wc, hc], dtype=dtype).reshape(1, 1, 1, 2))
+    wh01s = torch.sqrt(wh / torch.tensor([wc, hc], dtype=dtype, device=device).reshape(1, 1, 1, 2))
     coords_p = torch.cat([oxy, wh01s], -1)
-    mask, prob, coords, tmin, tmax, areas = [torch.tensor(np.asarray(t), dtype=dtype) for t in labels]
+    mask, prob, coords, tmin, tmax, areas = [torch.tensor(np.asarray(t), dtype=dtype, device=device) for t in labels]
     lo, hi = torch.maximum(omin, tmin), torch.minimum(omax, tmax)
     iwh = torch.clamp(hi - lo, min=0.0)
     inter = iwh[..., 0] * iwh[..., 1]
@@ -90,6 +93,6 @@ def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=to
     }
     total = sum(obj[k] * float(hparam[k]) for k in obj)
     total.backward()
-    grads = {k: v.grad.numpy() for k, v in P.items() if v.requires_grad and v.grad is not None}
+    grads = {k: v.grad.cpu().numpy() for k, v in P.items() if v.requires_grad and v.grad is not None}
     return {"objectives": {k: float(v.detach()) for k, v in obj.items()}, "total": float(total.detach()),
-            "grads": grads, "net": net.detach().numpy(), "dnet": net.grad.numpy(), "new_moving": new_moving}
+            "grads": grads, "net": net.detach().cpu().numpy(), "dnet": net.grad.cpu().numpy(), "new_moving": new_moving}

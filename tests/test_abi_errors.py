@@ -137,31 +137,6 @@ def test_single_conv_entry_points_validate_shapes_first():
     assert L.y2_conv2d_wgrad(P, 1, 0, 8, 32, P, 3, 32, P, 0, None) == -1 and "bad shape" in _err()
 
 
-def test_experimental_mixed_kind_conv_validates_first():
-    L = _lib.lib()
-    a = (P, 1, 8, 8)
-    assert L.y2_conv2d_mix(None, 1, 8, 8, 64, P, 3, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "null" in _err()
-    assert L.y2_conv2d_mix(*a, 32, P, 3, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "multiple of 64" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 5, 32, None, None, 0, P, 7, 0, 0, None) == -1 and "ksize" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 0, 0, 0, None) == -1 and "terms" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 7, -1, 0, None) == -1 and "kcap" in _err()
-    assert L.y2_conv2d_mix(*a, 64, P, 3, 32, None, None, 0, P, 7, 0, 40, None) == -1 and "block_n" in _err()
-
-
-def test_experimental_storage_format_entry_points_validate_first():
-    L = _lib.lib()
-    assert L.y2_mix_split(None, 10, 1.0, P, P, P, None) == -1 and "null" in _err()
-    assert L.y2_mix_split(P, 10, 0.0, P, P, P, None) == -1 and "bound" in _err()
-    assert L.y2_mix_split(P, 10, float("inf"), P, P, P, None) == -1
-    pre = lambda **k: L.y2_conv2d_mix_pre(k.get("x16", P), P, P, k.get("in_bound", 1.0), 1, 8, 8, k.get("cin", 64), P, 3, k.get("cout", 64), None, None, 0,
-                                          k.get("y", P), k.get("o16", None), k.get("o8", None), None, k.get("out_bound", 0.0), None, 7, k.get("kcap", 0), 0, None)
-    assert pre(x16=None) == -1 and "null" in _err()
-    assert pre(in_bound=-1.0) == -1 and "bound" in _err()
-    assert pre(cin=96) == -1 and "multiple of 64" in _err()
-    assert pre(o16=P, o8=P) == -1 and "split outputs" in _err()                  # all three arrays or none
-    assert pre(y=None) == -1 and "float32 output" in _err()                       # y may only be dropped with split outputs, one chain
-
-
 def test_check_raises_with_the_library_message():
     L = _lib.lib()
     rc = L.y2_reorg(P, 1, 5, 4, 4, 2, P, None)

@@ -148,7 +148,6 @@ def test_darknet_forward_layer_by_layer_vs_oracle(cuda, classes, size, batch, an
     assert max(worst.values()) <= TOL, worst
 
 
-@pytest.mark.skipif(os.environ.get("Y2_EXPERIMENTAL") != "1", reason="written after the round-1 GPU budget was spent, not yet run on a GPU: set Y2_EXPERIMENTAL=1")
 def test_darknet_forward_vs_the_reference_graph_golden(cuda):
     """tests/golden/backbone_reference.npz = the reference's own darknet() graph builder run with a torch float64 stand-in for
     slim / tf (tests/golden/make_backbone_golden.py): the device forward against THOSE numbers directly (the CPU suite pins the

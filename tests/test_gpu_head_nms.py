@@ -104,7 +104,6 @@ def test_loss_fwd_bwd_vs_oracle(cuda, B, hc, wc, C, anchors, seed):
     assert np.abs(g - g64).max() <= 1e-4 * np.abs(g64).max()
 
 
-@pytest.mark.skipif(os.environ.get("Y2_EXPERIMENTAL") != "1", reason="written after the round-1 GPU budget was spent, not yet run on a GPU: set Y2_EXPERIMENTAL=1")
 @pytest.mark.parametrize("name", ["voc", "coco", "nonsquare", "ties"])
 def test_head_decode_and_loss_vs_the_reference_source_golden(cuda, name):
     """tests/golden/head_reference.npz = the reference's own Model / Objectives classes (model/yolo2/__init__.py:27-94) run with a

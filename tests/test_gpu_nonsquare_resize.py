@@ -1,9 +1,8 @@
-"""GPU, opt-in (Y2_EXPERIMENTAL=1): checks of SHIPPED code paths that no GPU run has exercised yet (written after the round's GPU
-budget was spent).  Skipped by default so that the suite the driver runs only contains verified expectations; the first GPU
-call of the next round runs them (tools/round2_first.sh) and the ones that pass move into the regular files.
+"""-m gpu: non-square inputs and the device image resize (first executed on a B200 at the start of round 2: 18 / 18 green).
 
 * non-square input: the reference takes width and height separately (config [yolo2] width / height, utils/__init__.py:52-56);
-  the library's entry points do too, but every GPU test so far used square images."""
+  the library's entry points do too: darknet / tiny at 96 x 64 against the reference's own graph builder (golden fixture).
+* `resize` (detect.py:65): device bicubic / nearest against Pillow's own outputs (tests/golden/resize.npz), bit for bit."""
 import os
 
 import numpy as np
@@ -11,8 +10,7 @@ import pytest
 
 from oracle.darknet_oracle import init_params, tiny_layer_table
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("Y2_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set Y2_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "backbone_reference.npz")
 
 

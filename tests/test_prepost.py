@@ -121,7 +121,6 @@ def test_detections_oracle_matches_what_the_reference_detect_draws(name):
     assert scores == sorted(str(p) for p in g[name + "_pct"])
 
 
-@pytest.mark.skipif(os.environ.get("Y2_EXPERIMENTAL") != "1", reason="written after the round-1 GPU budget was spent, not yet run on a GPU: set Y2_EXPERIMENTAL=1")
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", DETECT_CASES)
 def test_nms_and_detections_gpu_vs_what_the_reference_detect_draws(cuda, name):

@@ -26,18 +26,3 @@ def test_schedule_and_chain_cap_cover_every_kblock_once(tmp_path):
     assert "tiles=172 KB=432 workers=148 cap=32 -> dp_tiles=148 sk_workers=148" in out.stdout     # conv20: hybrid
     assert "tiles=86 KB=72 workers=74 cap=32 -> dp_tiles=0 sk_workers=74" in out.stdout            # conv13 as CTA pairs: stream-K
     assert "tiles=338 KB=18 workers=74 cap=32 -> dp_tiles=338 sk_workers=0" in out.stdout          # conv5 as CTA pairs: data-parallel
-
-
-def test_mixed_kind_operand_arithmetic_on_the_host(tmp_path):
-    """EXPERIMENTAL kernel (csrc/y2_conv_mix.cu): the scale / residual arithmetic its prep kernels run (csrc/y2_mix_prep.cuh),
-    compiled for the host -- consistent scales (one accumulator for the three products), no saturation over 24 binades of
-    amax, and the three stored forms reproduce dot products to the planned budget while the fp16 term alone does not."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    exe = str(tmp_path / "mix_prep_harness")
-    src = os.path.join(ROOT, "tests", "host", "mix_prep_harness.cu")
-    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe, src])
-    out = subprocess.run([exe], capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout[-2000:]
-    assert "MIX PREP CHECK OK" in out.stdout

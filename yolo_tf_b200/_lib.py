@@ -33,10 +33,6 @@ _SIGNATURES = {
     "y2_darknet_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_i, c_p]),
     "y2_get_activation": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "y2_conv2d": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
-    "y2_conv2d_mix": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
-    "y2_debug_last_mix_ms": (c_f, []),
-    "y2_mix_split": (c_i, [c_p, c_sz, c_f, c_p, c_p, c_p, c_p]),
-    "y2_conv2d_mix_pre": (c_i, [c_p, c_p, c_p, c_f, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_p]),
     "y2_reorg": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "y2_head_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, ctypes.POINTER(HeadOutputs), c_p]),
     "y2_loss_workspace_bytes": (c_sz, [c_i, c_i, c_i]),

@@ -660,8 +660,7 @@ int y2_check_async_errors(void) {
     const int a = tc_conv_check_watchdog();
     const int b = wgrad_check_watchdog();
     const int c = conv0_tc_check_watchdog();
-    const int d = conv_mix_check_watchdog();
-    return a ? a : (b ? b : (c ? c : d));
+    return a ? a : (b ? b : c);
 }
 
 }  // extern "C"

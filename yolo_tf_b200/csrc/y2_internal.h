@@ -226,6 +226,4 @@ bool conv0_tc_applicable(int H, int W);
 int conv0_tc_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi, bf16* out_lo, int B,
                          int H, int W, int num_sms, cudaStream_t s, int fast = 0);
 int conv0_tc_check_watchdog();
-// experimental mixed-kind conv (y2_conv_mix.cu, diagnostic entry point only)
-int conv_mix_check_watchdog();
 }  // namespace y2
