@@ -5,7 +5,11 @@ Reference: train.py:70-72 (`get_optimizer` -> tf.train.AdamOptimizer(lr, beta1, 
 (`slim.learning.create_train_op(total_loss, optimizer, global_step, clip_gradient_norm=args.gradient_clip)`),
 config.ini [optimizer_adam] / [exponential_decay].
 
-The arithmetic lives in TensorFlow 1.0 (absent here: PARITY UNPINNED).  Restated from TF-1.0's published kernels:
+The arithmetic lives in TensorFlow 1.0 (not installable here).  PINNED to tests/golden/adam_reference.npz: the documented
+TF-1.0 update evaluated two independent ways that agree to 1e-12 -- scalar float64 loops of the published formulas and
+torch.optim.Adam (external implementation) with its epsilon re-mapped to TF's placement -- over 3 steps with extreme epsilon,
+active / inactive / tiny clip norms and an all-zero gradient tensor (tests/golden/make_adam_golden.py,
+tests/test_optimizer_oracle.py).  TF's own float32 kernel rounding stays unobservable.  Restated from TF-1.0's published kernels:
   * training_ops ApplyAdam functor:  alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
         m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  var -= (m * alpha) / (sqrt(v) + epsilon)
   * clip_ops.clip_by_norm (per tensor, as slim.learning.clip_gradient_norms applies it):
@@ -46,3 +50,16 @@ def adam_oracle(params, grads, m, v, learning_rate, beta1, beta2, epsilon, t, cl
         p = (p - (mi * alpha) / (np.sqrt(vi) + eps)).astype(np.float32)
         out_p.append(p); out_m.append(mi); out_v.append(vi)
     return out_p, out_m, out_v
+
+
+def adam_golden_cases(path):
+    """tests/golden/adam_reference.npz -> iterator of (name, (lr, beta1, beta2, eps, clip), p0[], g_steps[3][], p3[], m3[], v3[])."""
+    g = np.load(path)
+    n = len(g["shapes"])
+    for name in g["case_names"]:
+        name = str(name)
+        lr, b1, b2, eps, clip = (float(x) for x in g[name + "_hyper"])
+        yield (name, (lr, b1, b2, eps, clip), [g["%s_p0_%d" % (name, k)] for k in range(n)],
+               [[g["%s_g%d_%d" % (name, t, k)] for k in range(n)] for t in range(3)],
+               [g["%s_p3_%d" % (name, k)] for k in range(n)], [g["%s_m3_%d" % (name, k)] for k in range(n)],
+               [g["%s_v3_%d" % (name, k)] for k in range(n)])

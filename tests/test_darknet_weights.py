@@ -48,6 +48,18 @@ def test_read_synthetic_file_roundtrip(weights_file):
         assert np.array_equal(ovalues[k], v), k               # and both readers agree
 
 
+def test_read_center_false_assigns_the_first_block_to_biases(weights_file):
+    """`_darknet` / `_tiny` graphs (inference.py:62-66): no BatchNorm/beta, a `<conv>/biases` variable instead, and the reference's
+    walk order `['biases', 'beta', 'gamma', ...]` (parse_darknet_yolo2.py:85) hands it the file's first per-layer block."""
+    from yolo_tf_b200.parse_darknet_yolo2 import read
+    path, params = weights_file
+    _, values = read(path, 20, 5, center=False)
+    assert not any(k.endswith("BatchNorm/beta") for k in values)
+    assert set(values) == {"yolo2_darknet/" + k.replace("BatchNorm/beta", "biases") for k in params}
+    for k, v in params.items():
+        assert np.array_equal(values["yolo2_darknet/" + k.replace("BatchNorm/beta", "biases")], v), k
+
+
 def test_read_reports_trailing_bytes_and_truncation(weights_file):
     from yolo_tf_b200.parse_darknet_yolo2 import read
     path, _ = weights_file                                   # runs after the round-trip test (file order): may modify the file

@@ -174,6 +174,38 @@ def test_darknet_forward_vs_the_reference_graph_golden(cuda):
         _lib.check(_lib.lib().y2_set_option(eng.h, b"fuse_pool", 1))
 
 
+def test_center_false_variants_read_biases_and_resync(cuda):
+    """`_darknet` (inference.py:125-126): BN without beta + a separate `<conv>/biases` variable.  The engine must read the shift
+    from `biases` (not from a zero-initialised beta), re-sync when the same store is used through the other variant, and name the
+    training gradients after the variables that graph has (round-1 advisor finding)."""
+    import torch
+    from yolo_tf_b200 import _lib, variables
+    from yolo_tf_b200.model.yolo2 import Builder, inference
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "backbone_reference.npz"))
+    params = init_params(20, 5, seed=1)
+    store = variables.reset_default_store()
+    store.assign({"yolo2_darknet/" + k.replace("BatchNorm/beta", "biases"): v for k, v in params.items()})
+    x = torch.from_numpy(d["x64"]).to(cuda)
+    _, out = inference._darknet(x, 20, 5)
+    assert _rel(out.cpu().numpy(), d["darknet_nocenter_out"]) <= TOL
+    # the same store through `darknet` (center=True): beta does not exist -> created as zeros -> a different function
+    _, other = inference.darknet(x, 20, 5)
+    assert _rel(other.cpu().numpy(), d["darknet_nocenter_out"]) > 1e-3
+    _, again = inference._darknet(x, 20, 5)                     # ... and back: the freshness key includes (scope, center)
+    assert torch.equal(again, out)
+    # training through the center=False graph: gradients are named after `biases`
+    builder = Builder.from_values([str(i) for i in range(20)], 64, 64, ho.ANCHORS_VOC, inference_name="_darknet")
+    builder(x, training=True)
+    builder.create_objectives(ho.synthetic_labels(x.shape[0], 20, 2, 2, seed=1))
+    flat, views = builder.backward(allreduce=False)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().y2_check_async_errors())
+    assert "yolo2_darknet/conv3/biases" in views and not any(k.endswith("BatchNorm/beta") for k in views)
+    from yolo_tf_b200.optimizer import AdamOptimizer, create_train_op
+    create_train_op(builder, AdamOptimizer(1e-3)).apply_gradients(flat, views)       # round 1: KeyError here
+    torch.cuda.synchronize()
+
+
 def test_fused_maxpool_epilogue_matches_separate_pool(cuda):
     """Batch 32 admits the spatial tiling (16x8x1, 8x8x2, 4x4x8, 2x2x32 pixel blocks) that lets the 2x2 max-pool run
     inside the conv epilogue (warp shuffles).  Fused and separate paths must agree bit for bit, and with the oracle."""

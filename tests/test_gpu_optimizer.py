@@ -70,6 +70,50 @@ def test_adam_step_vs_oracle(cuda, clip):
         v = [gv[sum(sizes[:i]):sum(sizes[:i + 1])].copy() for i in range(len(sizes))]
 
 
+def test_adam_step_vs_the_external_golden(cuda):
+    """tests/golden/adam_reference.npz (the documented TF-1.0 update evaluated by scalar float64 loops AND by torch.optim.Adam,
+    tests/golden/make_adam_golden.py) embedded in the real 65-tensor bucket: golden tensor k occupies the head of bucket tensor
+    k, the rest of that tensor is zero (zero gradient, zero moments: it neither moves nor changes the tensor's clip norm)."""
+    import torch
+    import os
+    from oracle.optimizer_oracle import adam_golden_cases
+    from yolo_tf_b200 import _lib
+    L = _lib.lib()
+    eng = _engine(20)
+    sizes = _tensor_sizes(eng)
+    n = sum(sizes)
+    need = L.y2_adam_workspace_bytes(eng.h)
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=cuda)
+    off = (-ws.data_ptr()) % 256
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for name, (lr, b1, b2, eps, clip), p0, g_steps, p3, m3, v3 in adam_golden_cases(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adam_reference.npz")):
+        slots = [0, 1, 2, 3, 4]                                   # conv0 weights / gamma / beta, conv1 weights / gamma
+        assert all(p0[k].size <= sizes[slots[k]] for k in range(len(p0)))
+        dp = [torch.zeros(s, device=cuda) for s in sizes]
+        for k, sl in enumerate(slots):
+            dp[sl][:p0[k].size] = torch.from_numpy(p0[k].ravel()).to(cuda)
+        dm, dv = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+        ptrs = (ctypes.c_void_p * len(dp))(*[t.data_ptr() for t in dp])
+        for t in (1, 2, 3):
+            flat = torch.zeros(n, device=cuda)
+            for k, sl in enumerate(slots):
+                flat[offs[sl]:offs[sl] + p0[k].size] = torch.from_numpy(g_steps[t - 1][k].ravel()).to(cuda)
+            _lib.check(L.y2_adam_step(eng.h, _lib.ptr(flat), _lib.ptr(dm), _lib.ptr(dv), ptrs, len(dp), lr, b1, b2, eps, t, clip,
+                                      ctypes.c_void_p(ws.data_ptr() + off), need, None))
+        torch.cuda.synchronize()
+        for k, sl in enumerate(slots):
+            sz = p0[k].size
+            got = dp[sl][:sz].cpu().numpy().astype(np.float64)
+            upd, ref = got - p0[k].ravel(), (p3[k] - p0[k]).ravel()
+            assert np.abs(upd - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-30) + 2.5e-7 * max(1.0, np.abs(p0[k]).max()), (name, k)
+            gm = dm[offs[sl]:offs[sl] + sz].cpu().numpy()
+            assert np.abs(gm - m3[k].ravel()).max() <= 1e-5 * max(np.abs(m3[k]).max(), 1e-300), (name, "m", k)
+            # float32(1 - beta2) is 1.3e-5 off the ideal 0.001 (TF computes it in float32 too): v sits that far from the float64 golden
+            gv = dv[offs[sl]:offs[sl] + sz].cpu().numpy()
+            assert np.abs(gv - v3[k].ravel()).max() <= 3e-5 * max(np.abs(v3[k]).max(), 1e-300), (name, "v", k)
+            assert float(dp[sl][sz:].abs().max()) == 0.0 if sz < sizes[sl] else True
+
+
 def test_train_op_applies_adam_to_the_store(cuda):
     """create_train_op(...)(data, labels): the variables of the store move by exactly the Adam step of the gradients the
     same call produced (tensor order, clip, schedule, global_step), and the next forward uses the new weights."""

@@ -30,6 +30,10 @@ def main():
     seed = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    if os.environ.get("Y2_KCAP"):                                  # accumulation-chain cap in k-blocks (default 32)
+        import ctypes
+        _lib.lib().y2_debug_set.argtypes = [ctypes.c_int, ctypes.c_double]
+        _lib.lib().y2_debug_set(8, float(os.environ["Y2_KCAP"]))
     anchors = ho.ANCHORS_VOC if classes == 20 else ho.ANCHORS_COCO
     params = init_params(classes, 5, seed=seed)
     store = variables.reset_default_store()

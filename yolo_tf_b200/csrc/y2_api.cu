@@ -534,14 +534,27 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
     if (block_n > 0) { bn = block_n; cpad = (int)align_up((size_t)cout, (size_t)bn); }
     const size_t M = (size_t)B * H * W, K = (size_t)ksize * ksize * cin;
     bf16 *xp = nullptr, *wp = nullptr;
+    float* wsc = nullptr;
     void* sk = nullptr;
     int rc = -1;
     do {
         if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&wp, 2 * (size_t)cpad * K * sizeof(bf16)) != cudaSuccess ||
             cudaMalloc(&sk, tc_conv_streamk_bytes(num_sms)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
         if (cudaMemsetAsync(sk, 0, 4096, s) != cudaSuccess) { set_error("y2_conv2d: memset failed"); break; }
-        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
-        if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s)) break;
+        // precision 0 / 1: bf16 planes.  2: fp16 planes (activations as they are, weights pre-scaled by a power of two that the
+        // epilogue scale undoes).  3 / 4 (diagnostics of the mixed-format MMAs the training step relies on): 3 = bf16
+        // activation planes x fp16 weight planes (dgrad), 4 = fp16 activation planes x bf16 weight planes.
+        const int x16 = (precision == 2 || precision == 4) ? 1 : 0, w16 = (precision == 2 || precision == 3) ? 1 : 0;
+        if (w16) {
+            if (cudaMalloc(&wsc, (2 + (size_t)cout) * sizeof(float)) != cudaSuccess) { set_error("y2_conv2d: cudaMalloc failed"); break; }
+            if (pow2_scale_launch(w_hwio, K * cout, wsc, s)) break;
+            if (fold_scale_launch(scale, wsc + 1, wsc + 2, cout, s)) break;
+            scale = wsc + 2;
+        }
+        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s, x16)) break;
+        if (pack_weights_launch(w_hwio, wp, ksize, cin, cout, cpad, s, w16, w16 ? wsc : nullptr)) break;
+        g_conv_fmt = (x16 ? (FMT_A_HI | FMT_A_LO) : 0) | (w16 ? (FMT_B_HI | FMT_B_LO) : 0);
+        if (precision >= 2) precision = 0;
         TcConvLaunch T;
         const int halo = (g_conv_force_halo && tc_conv_can_halo(B, H, W, cin, ksize, cpad, bn, precision == 0)) ? g_conv_force_halo : 0;
         const int pair = (g_conv_force_pair && tc_conv_can_pair(cin, bn, halo)) ? 1 : 0;
@@ -569,7 +582,8 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
         if (tc_conv_check_watchdog()) break;
         rc = 0;
     } while (0);
-    cudaFree(xp); cudaFree(wp); cudaFree(sk);
+    g_conv_fmt = 0;
+    cudaFree(xp); cudaFree(wp); cudaFree(sk); cudaFree(wsc);
     return rc;
 }
 
@@ -579,6 +593,8 @@ int y2_debug_set(int key, double value) {
     else if (key == 1) g_sched_handoff_kb = value;
     else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
     else if (key == 4) g_conv_force_halo = (int)value;
+    else if (key == 9) g_conv_fmt = (int)value;             // FMT_* bits of the convs planned from now on (y2_conv2d sets them itself)
+    else if (key == 10) g_wgrad_fmt = (int)value;           // FMT_* bits of y2_conv2d_wgrad: 3 = x planes in fp16
     else if (key == 8) g_conv_kcap = (int)value;            // longest tensor-core accumulation chain in k-blocks (0 = unlimited; default 32)
     else if (key == 7) g_conv_force_pair = (int)value;      // y2_conv2d: CTA-pair mode where applicable
     else if (key == 6) g_conv_tma_store = (int)value;       // TMA-store epilogue (default 1)
@@ -615,7 +631,7 @@ int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* d
         if (cudaMalloc(&xp, 2 * M * cin * sizeof(bf16)) != cudaSuccess || cudaMalloc(&dp, 2 * M * dpitch * sizeof(bf16)) != cudaSuccess ||
             cudaMalloc(&sk, tc_conv_streamk_bytes(num_sms)) != cudaSuccess) { set_error("y2_conv2d_wgrad: cudaMalloc failed"); break; }
         if (cudaMemsetAsync(sk, 0, 4096, s) != cudaSuccess) { set_error("y2_conv2d_wgrad: memset failed"); break; }
-        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s)) break;
+        if (split_planes_launch(x, xp, xp + M * cin, M * cin, s, (g_wgrad_fmt & FMT_A_HI) ? 1 : 0)) break;     // y2_debug_set(10, 3): x planes in fp16
         if (split_planes_pad_launch(dy, cout, dp, dp + M * dpitch, M, cout, dpitch, s)) break;
         if (wgrad_tc_run(xp, B, H, W, cin, ksize, dp, cout, dpitch, dw, max_ctas, num_sms, sk, s)) break;
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("y2_conv2d_wgrad: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }

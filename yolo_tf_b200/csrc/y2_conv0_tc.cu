@@ -259,11 +259,10 @@ bool conv0_tc_applicable(int H, int W) { return H % 8 == 0 && W % 16 == 0; }
 int conv0_tc_pool_launch(const float* x, const float* w_hwio, const float* scale, const float* bias, bf16* out_hi, bf16* out_lo, int B,
                          int H, int W, int num_sms, cudaStream_t s, int fast) {
     Y2_REQUIRE(conv0_tc_applicable(H, W), "conv0 (tensor cores): H %% 8 and W %% 16 must be 0");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_current_device(attr_seen)) {
         Y2_CUDA(cudaFuncSetAttribute(conv0_tc_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
         Y2_CUDA(cudaFuncSetAttribute(conv0_tc_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
-        attr_set = true;
     }
     const long long ntiles = (long long)(W / 16) * (H / 8) * B;
     Y2_REQUIRE(ntiles < (1ll << 31), "conv0 (tensor cores): too many tiles");

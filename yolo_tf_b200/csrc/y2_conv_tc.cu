@@ -281,7 +281,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues; pair: rank 0 only) ==========
         const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t idesc = make_idesc_bf16(BLOCK_M * NCTA, (uint32_t)p.block_n);
+        // three products per k-step: hi*hi, hi*lo, lo*hi -- each with the element formats of ITS two planes
+        const uint32_t idesc = make_idesc_16(BLOCK_M * NCTA, (uint32_t)p.block_n, p.fmt & FMT_A_HI, p.fmt & FMT_B_HI);
+        const uint32_t idesc_hl = make_idesc_16(BLOCK_M * NCTA, (uint32_t)p.block_n, p.fmt & FMT_A_HI, p.fmt & FMT_B_LO);
+        const uint32_t idesc_lh = make_idesc_16(BLOCK_M * NCTA, (uint32_t)p.block_n, p.fmt & FMT_A_LO, p.fmt & FMT_B_HI);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -330,8 +333,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 const uint32_t w_off = (uint32_t)tap * wstep + (uint32_t)(k * 2);
                                 tc_mma_f16_e(leader, d_tmem, dh_hi + a_off, ha, dw_hi + w_off, hb, idesc, (tap > 0 || k > 0) ? 1u : 0u);
                                 if (SPLIT3) {
-                                    tc_mma_f16_e(leader, d_tmem, dh_hi + a_off, ha, dw_lo + w_off, hb, idesc, 1u);
-                                    tc_mma_f16_e(leader, d_tmem, dh_lo + a_off, ha, dw_hi + w_off, hb, idesc, 1u);
+                                    tc_mma_f16_e(leader, d_tmem, dh_hi + a_off, ha, dw_lo + w_off, hb, idesc_hl, 1u);
+                                    tc_mma_f16_e(leader, d_tmem, dh_lo + a_off, ha, dw_hi + w_off, hb, idesc_lh, 1u);
                                 }
                             }
                         }
@@ -349,14 +352,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (PAIR) {
                                 tc_mma_f16_pair_e(leader, d_tmem, da_hi + koff, hd, db_hi + koff, hd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                                 if (SPLIT3) {
-                                    tc_mma_f16_pair_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc, 1u);
-                                    tc_mma_f16_pair_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc, 1u);
+                                    tc_mma_f16_pair_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc_hl, 1u);
+                                    tc_mma_f16_pair_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc_lh, 1u);
                                 }
                             } else {
                             tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_hi + koff, hd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                             if (SPLIT3) {
-                                tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc, 1u);
-                                tc_mma_f16_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc, 1u);
+                                tc_mma_f16_e(leader, d_tmem, da_hi + koff, hd, db_lo + koff, hd, idesc_hl, 1u);
+                                tc_mma_f16_e(leader, d_tmem, da_lo + koff, hd, db_hi + koff, hd, idesc_lh, 1u);
                             }
                             }
                         }
@@ -745,11 +748,9 @@ static int load_driver_entry_points() {
 template <int BK, bool SPLIT3, bool PAIR>
 static int launch_inst(const TcConvLaunch& L, cudaStream_t stream) {
     auto kern = conv_tc_kernel<BK, SPLIT3, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_set = true;
-    }
     if (g_conv_pdl || PAIR) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -794,8 +795,12 @@ int tc_conv_launch(const TcConvLaunch& Lc, cudaStream_t stream) {
 // CTA pairs that can be co-resident (every worker of the persistent schedule must be: stream-K heads spin on the flags of
 // later workers).  Queried once per kernel instantiation with the real shared-memory size.
 static int max_active_pairs(int split3, int smem_bytes) {
-    static int cached[2] = {-1, -1};
-    if (cached[split3 ? 1 : 0] >= 0) return cached[split3 ? 1 : 0];
+    static int cached[64][2];
+    static unsigned long long seen[2] = {0, 0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (!first_use_on_current_device(seen[split3 ? 1 : 0])) return cached[dev][split3 ? 1 : 0];
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes;
@@ -813,7 +818,7 @@ static int max_active_pairs(int split3, int smem_bytes) {
         e = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<64, false, true>, &cfg);
     }
     if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
-    cached[split3 ? 1 : 0] = n;
+    cached[dev][split3 ? 1 : 0] = n;
     return n;
 }
 
@@ -882,6 +887,7 @@ int tc_conv_bind_output(TcConvLaunch* L) {
 }
 
 int g_conv_dbg_flags = 0, g_conv_force_halo = 0, g_conv_pdl = 1, g_conv_tma_store = 1, g_conv_force_pair = 0, g_conv_kcap = 32;
+int g_conv_fmt = 0, g_wgrad_fmt = 0;
 
 // CTA-pair mode: 64-channel k-blocks (SW128 operands), an even split of the N tile in 8-row swizzle groups, N a multiple of
 // 16 (the cta_group::2 MMA shape rule); halo mode keeps the single-CTA kernel.
@@ -917,6 +923,7 @@ int tc_conv_plan(TcConvLaunch* L, const bf16* in_planes, int B, int H, int W, in
     ConvParams& p = L->p;
     p.M = (int)M; p.N = cout; p.Cin = Cin; p.ksize = ksize; p.B = B; p.H = H; p.W = W;
     p.block_n = block_n;
+    p.fmt = g_conv_fmt;
     p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
     if (fuse_pool && !halo) {
         Y2_REQUIRE(pool_tiling(B, H, W, &p.tx, &p.ty, &p.tb), "tc conv: no spatial tiling for the fused max-pool at B=%d H=%d W=%d", B, H, W);

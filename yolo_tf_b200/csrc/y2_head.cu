@@ -5,6 +5,7 @@
 //              Builder.create_objectives :114-119; backward is the closed form of d(total)/d(inputs).
 //
 // Layout: net [B, Hc, Wc, A*(5+C)] float32 viewed as inputs[B, cells, A, 5+C] (k: 0=iou 1=x 2=y 3=w 4=h 5..=class).
+#include <algorithm>
 #include "y2_internal.h"
 #include "../../include/yolo2_b200.h"
 
@@ -67,31 +68,56 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             const long long gi = g0 + g;
             const int n = (int)(gi % ((long long)a.cells * a.A));
             const int cell = n / a.A, an = n - cell * a.A;
-            // softmax over classes (max-subtracted, as tf.nn.softmax)
+            // softmax over classes (max-subtracted, as tf.nn.softmax); up to 4 classes per lane stay in registers
             float mx = -INFINITY;
-            for (int c = lane; c < a.C; c += 32) mx = fmaxf(mx, in[5 + c]);
+            float ev[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c = lane + 32 * t;
+                ev[t] = (c < a.C) ? in[5 + c] : -INFINITY;
+                mx = fmaxf(mx, ev[t]);
+            }
+            for (int c = lane + 128; c < a.C; c += 32) mx = fmaxf(mx, in[5 + c]);
             mx = warp_max(mx);
             float se = 0.f;
-            for (int c = lane; c < a.C; c += 32) se += expf(in[5 + c] - mx);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                ev[t] = (lane + 32 * t < a.C) ? expf(ev[t] - mx) : 0.f;
+                se += ev[t];
+            }
+            for (int c = lane + 128; c < a.C; c += 32) se += expf(in[5 + c] - mx);
             se = warp_sum(se);
-            const float iou = sigmoidf_(in[0]);
-            for (int c = lane; c < a.C; c += 32) {
+            // the five box logits in parallel: lanes 0..2 sigmoid (iou, x, y), lanes 3..4 exp * anchor (w, h)
+            float bv = 0.f;
+            if (lane < 3) bv = sigmoidf_(in[lane]);
+            else if (lane < 5) bv = expf(in[lane]) * __ldg(a.anchors + 2 * an + (lane - 3));
+            const float iou = __shfl_sync(0xffffffffu, bv, 0);
+            const float sx = __shfl_sync(0xffffffffu, bv, 1), sy = __shfl_sync(0xffffffffu, bv, 2);
+            const float w = __shfl_sync(0xffffffffu, bv, 3), h = __shfl_sync(0xffffffffu, bv, 4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c = lane + 32 * t;
+                if (c < a.C) {
+                    const float pr = ev[t] / se;
+                    s_conf[(size_t)g * a.C + c] = iou * pr;
+                    if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
+                }
+            }
+            for (int c = lane + 128; c < a.C; c += 32) {
                 const float pr = expf(in[5 + c] - mx) / se;
                 s_conf[(size_t)g * a.C + c] = iou * pr;
                 if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
             }
             if (lane == 0) {
-                const float sx = sigmoidf_(in[1]), sy = sigmoidf_(in[2]);
-                const float w = expf(in[3]) * __ldg(a.anchors + 2 * an), h = expf(in[4]) * __ldg(a.anchors + 2 * an + 1);
                 const float hw = w / 2.0f, hh = h / 2.0f;
                 const float oxmin = sx - hw, oymin = sy - hh, oxmax = sx + hw, oymax = sy + hh;
                 const float cx = (float)(cell % a.Wc), cy = (float)(cell / a.Wc);
-                float* bx = s_box + (size_t)g * 24;
-                bx[0] = cx + oxmin; bx[1] = cy + oymin; bx[2] = cx + oxmax; bx[3] = cy + oymax;
-                bx[4] = iou; bx[5] = w; bx[6] = h; bx[7] = w * h;
-                bx[8] = cx + sx; bx[9] = cy + sy; bx[10] = oxmin; bx[11] = oymin;
-                bx[12] = oxmax; bx[13] = oymax; bx[14] = sqrtf(w / (float)a.Wc); bx[15] = sqrtf(h / (float)a.Hc);
-                bx[16] = sx; bx[17] = sy; bx[18] = w / (float)a.Wc; bx[19] = h / (float)a.Hc;
+                float4* bx = reinterpret_cast<float4*>(s_box + (size_t)g * 24);
+                bx[0] = make_float4(cx + oxmin, cy + oymin, cx + oxmax, cy + oymax);
+                bx[1] = make_float4(iou, w, h, w * h);
+                bx[2] = make_float4(cx + sx, cy + sy, oxmin, oymin);
+                bx[3] = make_float4(oxmax, oymax, sqrtf(w / (float)a.Wc), sqrtf(h / (float)a.Hc));
+                bx[4] = make_float4(sx, sy, w / (float)a.Wc, h / (float)a.Hc);
             }
         }
         __syncthreads();
@@ -128,18 +154,18 @@ int head_decode_launch(const float* net, int B, int Hc, int Wc, int A, int C, co
     a.o = *outs;
     if (a.boxes == 0) return 0;
     const int D = 5 + C;
-    int G = 64;
+    // boxes per CTA: enough CTAs to fill the machine at small batches (B = 32: 27 k boxes -> ~1 k CTAs of 28 boxes),
+    // at most 64 boxes, a multiple of 4 (16-byte aligned chunks)
+    int G = (int)std::min<long long>(64, std::max<long long>(8, (a.boxes / (148 * 6)) & ~3LL));
     while (G > 4 && (size_t)G * (D + C + 24) * 4 > 96 * 1024) G -= 4;
     Y2_REQUIRE((size_t)G * (D + C + 24) * 4 <= 200 * 1024, "head_decode: too many classes (%d)", C);
     a.G = G;
     const size_t smem = (size_t)G * (D + C + 24) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
     long long blocks = (a.boxes + G - 1) / G;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;
     decode_kernel<<<(int)blocks, 256, smem, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();

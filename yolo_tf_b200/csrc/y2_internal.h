@@ -28,6 +28,15 @@ const char* last_error();
     } while (0)
 
 int device_sm_count(int device);
+// cudaFuncSetAttribute / occupancy results are PER DEVICE: one bit per device ordinal of the current device; true the first
+// time it is asked on that device (ordinals >= 64: always true, i.e. the setup is simply repeated)
+static inline bool first_use_on_current_device(unsigned long long& seen) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (seen & (1ull << d)) return false;
+    seen |= 1ull << d;
+    return true;
+}
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 void note_launch();
 
@@ -36,6 +45,30 @@ void note_launch();
 // lo = bf16(T - hi), plane p at base + p*M*ld (ld = row pitch in elements). hi+lo carries 16
 // significand bits; the tcgen05 conv multiplies planes pairwise (hi*hi + hi*lo + lo*hi).
 typedef __nv_bfloat16 bf16;
+
+// Plane formats of a GEMM's operands, one bit each (1 = fp16, 0 = bf16)
+enum : int { FMT_A_HI = 1, FMT_A_LO = 2, FMT_B_HI = 4, FMT_B_LO = 8 };
+
+// ---- plane element formats ----
+// The planes of a tensor are 16-bit elements, bf16 (range-safe: float32's exponent; hi + lo = 16 significand bits) or fp16
+// (hi + lo = 22 significand bits; range 6e-8 .. 65504: used where the producer bounds the range -- batch-normalised
+// activations of the training forward, and weights pre-scaled by a per-layer power of two).  Storage type stays `bf16*`
+// (16-bit slots); `f16` says how the bits are read.
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+__device__ __forceinline__ unsigned short plane_enc(float v, int f16) {
+    if (f16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)));   // saturate, never inf
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float plane_dec(unsigned short u, int f16) {
+    return f16 ? __half2float(__ushort_as_half(u)) : __uint_as_float((uint32_t)u << 16);
+}
+__device__ __forceinline__ void plane_split(float v, int f16, unsigned short& hi, unsigned short& lo) {
+    hi = plane_enc(v, f16);
+    lo = plane_enc(v - plane_dec(hi, f16), f16);
+}
+__device__ __forceinline__ uint32_t plane_pack2(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
+#endif
 
 // ---- tcgen05 implicit-GEMM conv (y2_conv_tc.cu) ----
 enum EpilogueMode : int {
@@ -77,8 +110,10 @@ struct ConvParams {
     // CTA-pair mode (cta_group::2): m_tiles counts 256-row pair tiles, m_tiles128 the 128-row tiles that exist
     int pair, m_tiles128;
     int kcap;                // longest accumulation chain in k-blocks (0 = unlimited), see CapIter
+    int fmt;                 // FMT_* bits (y2_ptx.cuh): element format of the A (activation) and B (weight) hi / lo planes; 0 = all bf16
 };
 extern int g_conv_tma_store;   // 1 = TMA-store epilogue where the layout allows it
+extern int g_conv_fmt, g_wgrad_fmt;   // FMT_* bits of the GEMMs planned from now on (diagnostic entry points; the network sets them per launch)
 extern int g_conv_kcap;        // ConvParams::kcap of the convs planned from now on (default 32)
 extern int g_conv_force_pair;  // y2_conv2d: run eligible convs as CTA pairs (diagnostics / tests)
 extern int g_conv_dbg_flags, g_conv_force_halo, g_conv_pdl;   // g_conv_pdl: launch convs with programmatic stream serialization
@@ -153,11 +188,16 @@ int tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 int tc_conv_check_watchdog();
 
 // ---- elementwise / layout kernels (y2_layout.cu) ----
-int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s);
+int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s, int f16 = 0);
+// amax of a device array -> out[0] = 2^k, out[1] = 2^-k with amax * 2^k in [2^13, 2^14) (k = 0 for an all-zero array)
+int pow2_scale_launch(const float* src, size_t n, float* out2, cudaStream_t s);
+// out[i] = (scale ? scale[i] : 1) * factor[0]   (folds the 2^-k of pre-scaled fp16 weight planes into the epilogue scale)
+int fold_scale_launch(const float* scale, const float* factor, float* out, int n, cudaStream_t s);
 int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows, int cols, long long ld,
-                        cudaStream_t s);
+                        cudaStream_t s, int f16 = 0);
+// f16 = 1: fp16 planes of w * wscale[0] (wscale: device pointer to the power of two pow2_scale_launch chose; null = 1)
 int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad,
-                        cudaStream_t s);
+                        cudaStream_t s, int f16 = 0, const float* wscale = nullptr);
 int bn_fold_launch(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                    float* scale, float* bias, int n, cudaStream_t s);
 int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,

@@ -22,20 +22,68 @@ __device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(
 
 // ---------------------------------------------------------------- split fp32 -> planes
 __global__ void split_planes_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
-                                    size_t n4) {
+                                    size_t n4, int f16) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(src + i);
-        const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
-        const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
-        hi[i] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-        lo[i] = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+        unsigned short h[4], l[4];
+        plane_split(v.x, f16, h[0], l[0]); plane_split(v.y, f16, h[1], l[1]);
+        plane_split(v.z, f16, h[2], l[2]); plane_split(v.w, f16, h[3], l[3]);
+        hi[i] = make_uint2(plane_pack2(h[0], h[1]), plane_pack2(h[2], h[3]));
+        lo[i] = make_uint2(plane_pack2(l[0], l[1]), plane_pack2(l[2], l[3]));
     }
 }
-int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s) {
+int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, cudaStream_t s, int f16) {
     Y2_REQUIRE(n % 4 == 0, "split_planes: element count must be a multiple of 4");
     split_planes_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(src),
                                                            reinterpret_cast<uint2*>(dst_hi),
-                                                           reinterpret_cast<uint2*>(dst_lo), n / 4);
+                                                           reinterpret_cast<uint2*>(dst_lo), n / 4, f16);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------- power-of-two scale of a weight tensor (fp16 planes)
+// amax over the tensor (positive floats order like their bit patterns -> atomicMax on the bits), then k with
+// amax * 2^k in [2^13, 2^14): the hi plane keeps 11 significand bits for every weight above amax * 2^-27 and the lo plane
+// (the fp16 of the residual) 11 more for every weight above amax * 2^-16; nothing can overflow.
+__global__ void amax_bits_kernel(const float* __restrict__ src, size_t n, unsigned int* __restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(__ldg(src + i));
+        if (v < INFINITY) m = fmaxf(m, v);                   // NaN / inf weights do not steer the scale
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+__global__ void pow2_from_amax_kernel(float* out2) {
+    const float amax = __uint_as_float(reinterpret_cast<unsigned int*>(out2)[0]);
+    int k = 0;
+    if (amax > 0.f) {
+        int e;
+        frexpf(amax, &e);                                     // amax = f * 2^e, f in [0.5, 1)
+        k = 14 - e;                                           // amax * 2^k in [2^13, 2^14)
+        k = max(-100, min(100, k));
+    }
+    out2[0] = exp2f((float)k);
+    out2[1] = exp2f((float)-k);
+}
+int pow2_scale_launch(const float* src, size_t n, float* out2, cudaStream_t s) {
+    Y2_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), s));
+    amax_bits_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, n, reinterpret_cast<unsigned int*>(out2));
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    pow2_from_amax_kernel<<<1, 1, 0, s>>>(out2);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+__global__ void fold_scale_kernel(const float* scale, const float* factor, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fmul_rn(scale ? scale[i] : 1.0f, factor[0]);          // a power of two: exact
+}
+int fold_scale_launch(const float* scale, const float* factor, float* out, int n, cudaStream_t s) {
+    fold_scale_kernel<<<(n + 127) / 128, 128, 0, s>>>(scale, factor, out, n);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -43,7 +91,7 @@ int split_planes_launch(const float* src, bf16* dst_hi, bf16* dst_lo, size_t n, 
 
 // ---------------------------------------------------------------- merge planes -> fp32
 __global__ void merge_planes_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ dst,
-                                    size_t rows, int cols, long long ld) {
+                                    size_t rows, int cols, long long ld, int f16) {
     const int c4 = cols / 4;
     const size_t total = rows * (size_t)c4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -52,17 +100,17 @@ __global__ void merge_planes_kernel(const bf16* __restrict__ hi, const bf16* __r
         const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + r * ld + c));
         const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + r * ld + c));
         float4 o;
-        o.x = bf16_lo_f(h.x) + bf16_lo_f(l.x);
-        o.y = bf16_hi_f(h.x) + bf16_hi_f(l.x);
-        o.z = bf16_lo_f(h.y) + bf16_lo_f(l.y);
-        o.w = bf16_hi_f(h.y) + bf16_hi_f(l.y);
+        o.x = plane_dec((unsigned short)h.x, f16) + plane_dec((unsigned short)l.x, f16);
+        o.y = plane_dec((unsigned short)(h.x >> 16), f16) + plane_dec((unsigned short)(l.x >> 16), f16);
+        o.z = plane_dec((unsigned short)h.y, f16) + plane_dec((unsigned short)l.y, f16);
+        o.w = plane_dec((unsigned short)(h.y >> 16), f16) + plane_dec((unsigned short)(l.y >> 16), f16);
         *reinterpret_cast<float4*>(dst + r * (size_t)cols + c) = o;
     }
 }
 int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows, int cols, long long ld,
-                        cudaStream_t s) {
+                        cudaStream_t s, int f16) {
     Y2_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "merge_planes: cols and pitch must be multiples of 4");
-    merge_planes_kernel<<<grid_for(rows * (size_t)(cols / 4), 256), 256, 0, s>>>(hi, lo, dst, rows, cols, ld);
+    merge_planes_kernel<<<grid_for(rows * (size_t)(cols / 4), 256), 256, 0, s>>>(hi, lo, dst, rows, cols, ld, f16);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -70,17 +118,17 @@ int merge_planes_launch(const bf16* hi, const bf16* lo, float* dst, size_t rows,
 
 // ---------------------------------------------------------------- weights HWIO fp32 -> [2][cout_pad][tap*Cin] bf16
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int taps, int cin, int cout,
-                                    int cout_pad) {
+                                    int cout_pad, int f16, const float* __restrict__ wscale) {
+    const float ws = wscale ? __ldg(wscale) : 1.0f;
+    unsigned short* o16 = reinterpret_cast<unsigned short*>(out);
     const size_t K = (size_t)taps * cin;
     const size_t total = (size_t)cout_pad * K;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t n = i / K;
         const size_t k = i - n * K;            // k = tap*cin + c ; HWIO index = (tap*cin + c)*cout + n
         float v = 0.f;
-        if (n < (size_t)cout) v = __ldg(w + k * cout + n);
-        const bf16 h = __float2bfloat16_rn(v);
-        out[i] = h;
-        out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (n < (size_t)cout) v = __fmul_rn(__ldg(w + k * cout + n), ws);
+        plane_split(v, f16, o16[i], o16[total + i]);
     }
 }
 // HWIO [taps][cin][cout] -> HWIO [taps][cin_s][cout_s], zero-filled where the stored channel count is padded
@@ -103,9 +151,10 @@ int pad_weights_launch(const float* w_hwio, float* out, int ksize, int cin, int 
     note_launch();
     return 0;
 }
-int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad, cudaStream_t s) {
+int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, int cout, int cout_pad, cudaStream_t s, int f16,
+                        const float* wscale) {
     const size_t total = (size_t)cout_pad * ksize * ksize * cin;
-    pack_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, wpack, ksize * ksize, cin, cout, cout_pad);
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, wpack, ksize * ksize, cin, cout, cout_pad, f16, wscale);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -7,26 +7,33 @@
 //     ORIGINAL scores;
 //   * a box whose class score is > threshold when reached ("live") zeroes the class score of EVERY
 //     later box - candidate or not - whose IoU with it is >= threshold_iou; zeroed boxes never act;
-//   * IoU uses the float32 operation order of iou() with no FMA contraction (explicit _rn intrinsics).
+//   * IoU uses the float32 operation order of iou() with no FMA contraction (explicit _rn intrinsics; the
+//     translation unit is also compiled with -fmad=false).
 //
 // Three kernels, no host round trip:
-//   select : a CTA owns 32 classes of one image.  Candidates (> threshold) are compacted with coalesced reads
-//            (a warp reads 32 consecutive classes of one box = 128 bytes; lane = class; slots from a shared-memory
-//            counter).  Then one warp per class rank-sorts its candidates with the lexicographic comparator (ties
-//            descend into earlier class columns, still unmodified because nothing is written here) and runs the
-//            sequential greedy sweep with a shared-memory alive bitmask -> list of KEPT boxes.
+//   select : a CTA owns 32 classes of one image.  Candidates (> threshold) are compacted with coalesced 128-bit reads
+//            (a lane reads 4 consecutive classes of one box, a warp 4 boxes x 32 classes) into per-class shared-memory
+//            lists.  Then one warp per class: (value, index) keys of its candidates are staged in shared memory and
+//            sorted by a bitonic network (O(K log^2 K) shared-memory compare-exchanges); runs of EQUAL values -- the only
+//            place the lexicographic comparator has to look at earlier class columns, still unmodified because nothing is
+//            written here -- are re-ranked exactly.  The candidates' boxes are staged in sorted order and the sequential
+//            greedy sweep runs entirely out of shared memory (alive bitmask walked with ffs, lanes = later candidates,
+//            the IEEE divide skipped for pairs a conservative bound already rejects).  Outputs: the list of KEPT boxes
+//            and a bitmask of the SUPPRESSED candidates per (image, class).  Classes with more than SEL_CAP candidates
+//            take the general path (lists in global memory, rank sort).
 //   order  : (optional) final permutation of the N boxes = the order of the list the reference returns.
-//   apply  : a CTA owns a [64 boxes][32 classes] tile (coalesced 128-byte rows through shared memory); warps walk
-//            class columns with lanes = boxes, the class's kept boxes broadcast from shared memory.  A candidate is
-//            zeroed iff it is not kept; a non-candidate (it sorts after every candidate) is zeroed iff any kept box
-//            overlaps it >= threshold_iou (disjoint pairs are rejected before the divide when threshold_iou > 0).
+//   apply  : a CTA owns a [128 boxes][32 classes] tile (coalesced 128-bit loads through shared memory); warps walk
+//            class columns with lanes = boxes (4 per lane), the class's kept boxes broadcast from shared memory.  A
+//            candidate is zeroed iff its bit in the suppressed mask is set; a non-candidate (it sorts after every
+//            candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
 // Scores are read once by select and once by apply, both coalesced; only tiles that change are written back.
 #include "y2_internal.h"
 
 namespace y2 {
 
 static constexpr int NMS_WARPS = 8;
-static constexpr int NMS_MAX_N = 8192;     // alive bitmask: 256 words per warp
+static constexpr int NMS_MAX_N = 8192;     // bitmasks: 256 words per warp
+static constexpr int SEL_CAP = 256;        // candidates per class handled out of shared memory
 
 __device__ __forceinline__ float iou_ref(float4 a, float4 b) {   // (xmin, ymin, xmax, ymax)
     const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
@@ -36,6 +43,19 @@ __device__ __forceinline__ float iou_ref(float4 a, float4 b) {   // (xmin, ymin,
     const float inter = __fmul_rn(iw, ih);
     const float den = fmaxf(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-10f);
     return __fdiv_rn(inter, den);
+}
+__device__ __forceinline__ float box_area(float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
+// iou_ref(a, b) >= thr with the areas precomputed.  Same float32 operations as iou_ref up to the divide (bit-identical
+// inter and den), then a conservative filter when thr > 0 (quick): rn(inter/den) >= thr needs inter >= thr*(1-2^-24)*den,
+// so anything below 0.999*thr*den is certainly no hit and skips the IEEE division; disjoint pairs (inter == 0) fall out
+// here too.  NaNs fail the '<' and take the exact path.
+__device__ __forceinline__ bool iou_hit(float4 a, float aa, float4 b, float ba, float thr, float thr_lo, bool quick) {
+    const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float den = fmaxf(__fsub_rn(__fadd_rn(aa, ba), inter), 1e-10f);
+    if (quick && inter < __fmul_rn(thr_lo, den)) return false;
+    return __fdiv_rn(inter, den) >= thr;
 }
 __device__ __forceinline__ float4 load_box(const float* __restrict__ xy_min, const float* __restrict__ xy_max,
                                            size_t i) {
@@ -55,62 +75,44 @@ __device__ __forceinline__ bool precedes(const float* __restrict__ conf_img, int
     }
     return i < j;
 }
+// order-preserving map float -> uint32 (a > b  <=>  ford(a) > ford(b) for non-NaN a, b; -0 is canonicalised to +0 first)
+__device__ __forceinline__ uint32_t ford(float v) {
+    const uint32_t u = __float_as_uint(v + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 struct NmsArgs {
     float* conf;
     const float* xy_min;
     const float* xy_max;
-    int B, N, C;
+    int B, N, C, W;      // W = ceil(N / 32) mask words per (image, class)
     float thr, thr_iou;
-    uint16_t* cand;      // [B][C][N] candidates in index order, overwritten with the kept list
-    uint16_t* sorted;    // [B][C][N] scratch: candidates in visiting order
+    uint16_t* cand;      // [B][C][N] kept list (general path: candidates in index order first)
+    uint16_t* sorted;    // [B][C][N] scratch of the general path: candidates in visiting order
+    uint32_t* supp;      // [B][C][W] bit n = candidate n of this class was suppressed (written for classes with candidates)
     int* kept_cnt;       // [B][C]
     int* status;         // [B] nullable: 1 = a reference assert (NaN / xy_min > xy_max) would fire
     int* order_out;      // [B][N] nullable
 };
 
-__global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
-    __shared__ uint32_t alive_sm[NMS_WARPS][NMS_MAX_N / 32];
-    __shared__ int cnt_sm[32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c0 = blockIdx.x * 32;                     // this CTA: 32 classes of image b
-    const int b = blockIdx.y;
+// General path for one (image, class), one warp: any number of candidates, lists in global memory, rank sort.
+// alive / supp: per-warp shared-memory bitmasks of NMS_MAX_N bits.
+__device__ void select_class_general(const NmsArgs& a, int b, int c, uint32_t* alive, uint32_t* supp, int lane) {
     const float* conf_img = a.conf + (size_t)b * a.N * a.C;
     const float* bmin = a.xy_min + (size_t)b * a.N * 2;
     const float* bmax = a.xy_max + (size_t)b * a.N * 2;
-    uint32_t* alive = alive_sm[warp];
-
-    // 1. compact candidates with COALESCED reads: a warp reads 32 consecutive classes of one box (128 bytes);
-    //    lane = class.  List order is arbitrary (slots from a shared-memory counter); step 2 sorts with a total order.
-    if (threadIdx.x < 32) cnt_sm[threadIdx.x] = 0;
-    __syncthreads();
-    if (c0 + lane < a.C) {
-        uint16_t* my_cand = a.cand + ((size_t)b * a.C + c0 + lane) * a.N;
-        for (int n = warp; n < a.N; n += NMS_WARPS) {
-            if (__ldg(conf_img + (size_t)n * a.C + c0 + lane) > a.thr) my_cand[atomicAdd(&cnt_sm[lane], 1)] = (uint16_t)n;
-        }
-    }
-    __syncthreads();
-    for (int cl = warp; cl < 32; cl += NMS_WARPS) {     // one warp per class from here on
-    const int c = c0 + cl;
-    if (c >= a.C) break;
     uint16_t* cand = a.cand + ((size_t)b * a.C + c) * a.N;
     uint16_t* sorted = a.sorted + ((size_t)b * a.C + c) * a.N;
-    const int K = cnt_sm[cl];
-    if (K == 0) {
-        if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = 0;
-        continue;
+    // compaction in index order (ballot)
+    int K = 0;
+    for (int n0 = 0; n0 < a.N; n0 += 32) {
+        const int n = n0 + lane;
+        const bool is = n < a.N && __ldg(conf_img + (size_t)n * a.C + c) > a.thr;
+        const uint32_t m = __ballot_sync(0xffffffffu, is);
+        if (is) cand[K + __popc(m & ((1u << lane) - 1u))] = (uint16_t)n;
+        K += __popc(m);
     }
-    // reference asserts fire as soon as one live box is compared with the rest: every box is checked
-    if (a.status && a.N >= 2) {
-        bool bad = false;
-        for (int n = lane; n < a.N; n += 32) {
-            const float4 q = load_box(bmin, bmax, n);
-            bad |= !(q.x <= q.z) || !(q.y <= q.w);        // also true for NaN
-        }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(a.status + b, 1);
-    }
-    // 2. rank sort into visiting order
+    __syncwarp();
     for (int j0 = 0; j0 < K; j0 += 32) {
         const int jj = j0 + lane;
         const int j = (jj < K) ? cand[jj] : 0;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
         if (jj < K) sorted[rank] = (uint16_t)j;
     }
     for (int w = lane; w < (K + 31) / 32; w += 32) alive[w] = 0xffffffffu;
+    for (int w = lane; w < a.W; w += 32) supp[w] = 0u;
     __syncwarp();
-    // 3. greedy sweep in visiting order
     int kept = 0;
     for (int r = 0; r < K; ++r) {
         if (!((alive[r >> 5] >> (r & 31)) & 1u)) continue;           // warp-uniform
@@ -136,17 +138,216 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a) {
         for (int j0 = (r + 1) & ~31; j0 < K; j0 += 32) {
             const int jj = j0 + lane;
             bool kill = false;
+            int j = 0;
             if (jj > r && jj < K && ((alive[jj >> 5] >> (jj & 31)) & 1u)) {
-                const float4 bj = load_box(bmin, bmax, sorted[jj]);
-                kill = iou_ref(bi, bj) >= a.thr_iou;
+                j = sorted[jj];
+                kill = iou_ref(bi, load_box(bmin, bmax, j)) >= a.thr_iou;
             }
             const uint32_t km = __ballot_sync(0xffffffffu, kill);
+            if (kill) atomicOr(&supp[j >> 5], 1u << (j & 31));
             if (km && lane == 0) alive[j0 >> 5] &= ~km;
             __syncwarp();
         }
     }
+    uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
+    for (int w = lane; w < a.W; w += 32) supp_out[w] = supp[w];
     if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
     __syncwarp();
+}
+
+// dynamic shared memory of nms_select_kernel: per warp {key[SEL_CAP] u64, box[SEL_CAP] float4, supp[Wp] u32, alive[Wp] u32},
+// then list[32][SEL_CAP] u16 and cnt[33]; Wp = W rounded up to a multiple of 4
+//   key  : (ford(value) << 32) | (0xffff - index): descending key = visiting order up to ties
+//   box  : boxes in visiting order (also the scratch of the tie fix)
+//   supp : suppressed candidates, by box index;  alive : alive candidates, by rank (general path: up to N ranks)
+//   list : per class: candidates as found, later the kept list
+__host__ __device__ inline size_t sel_warp_bytes(int W) { return (size_t)SEL_CAP * 24 + 2 * (size_t)((W + 3) & ~3) * 4; }
+static size_t sel_smem_bytes(int W) { return NMS_WARPS * sel_warp_bytes(W) + 32 * SEL_CAP * sizeof(uint16_t) + 33 * sizeof(int); }
+
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, int vec4) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Wp = (a.W + 3) & ~3;
+    unsigned char* wbase = sel_smem + warp * sel_warp_bytes(a.W);
+    unsigned long long* w_key = reinterpret_cast<unsigned long long*>(wbase);
+    float4* w_box = reinterpret_cast<float4*>(wbase + SEL_CAP * 8);
+    uint32_t* w_supp = reinterpret_cast<uint32_t*>(wbase + SEL_CAP * 24);
+    uint32_t* w_alive = w_supp + Wp;
+    uint16_t (*s_list)[SEL_CAP] = reinterpret_cast<uint16_t (*)[SEL_CAP]>(sel_smem + NMS_WARPS * sel_warp_bytes(a.W));
+    int* s_cnt = reinterpret_cast<int*>(sel_smem + NMS_WARPS * sel_warp_bytes(a.W) + 32 * SEL_CAP * sizeof(uint16_t));
+    const int c0 = blockIdx.x * 32;                     // this CTA: 32 classes of image b
+    const int b = blockIdx.y;
+    const float* conf_img = a.conf + (size_t)b * a.N * a.C;
+    const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+    const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+
+    // 1. compact candidates with COALESCED reads into the per-class shared-memory lists (arbitrary order: step 2 sorts
+    //    with a total order).  Counters keep counting past SEL_CAP: such classes take the general path.
+    if (threadIdx.x <= 32) s_cnt[threadIdx.x] = 0;        // [32] = next class to hand out
+    __syncthreads();
+    if (vec4) {                                          // C % 4 == 0, 16-byte aligned rows: lane = (box, 4 classes)
+        const int q = lane & 7, cl = 4 * q;
+        if (c0 + cl < a.C) {
+            for (int n = warp * 4 + (lane >> 3); n < a.N; n += NMS_WARPS * 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + cl));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (vv[t] > a.thr) {
+                        const int slot = atomicAdd(&s_cnt[cl + t], 1);
+                        if (slot < SEL_CAP) s_list[cl + t][slot] = (uint16_t)n;
+                    }
+            }
+        }
+    } else if (c0 + lane < a.C) {                        // lane = class, a warp reads 32 consecutive classes of one box
+        for (int n = warp; n < a.N; n += NMS_WARPS) {
+            if (__ldg(conf_img + (size_t)n * a.C + c0 + lane) > a.thr) {
+                const int slot = atomicAdd(&s_cnt[lane], 1);
+                if (slot < SEL_CAP) s_list[lane][slot] = (uint16_t)n;
+            }
+        }
+    }
+    __syncthreads();
+    // reference asserts fire as soon as one live box is compared with the rest: with any candidate in this CTA's classes
+    // every box of the image is checked (once per CTA)
+    if (a.status && a.N >= 2) {
+        bool any = false;
+        for (int cl = 0; cl < 32; ++cl) any |= s_cnt[cl] > 0;
+        if (any) {
+            bool bad = false;
+            for (int n = threadIdx.x; n < a.N; n += NMS_WARPS * 32) {
+                const float4 q = load_box(bmin, bmax, n);
+                bad |= !(q.x <= q.z) || !(q.y <= q.w);        // also true for NaN
+            }
+            if (bad) atomicExch(a.status + b, 1);
+        }
+    }
+    const bool quick = a.thr_iou > 0.0f;
+    const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
+    // one warp per class from here on; classes are handed out dynamically (the candidate counts of real score matrices
+    // are very uneven: a few classes hold most of an image's candidates)
+    for (;;) {
+        int cl = 0;
+        if (lane == 0) cl = atomicAdd(&s_cnt[32], 1);
+        cl = __shfl_sync(0xffffffffu, cl, 0);
+        if (cl >= 32) break;
+        const int c = c0 + cl;
+        if (c >= a.C) continue;
+        const int K = s_cnt[cl];
+        if (K == 0) {
+            if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = 0;
+            continue;
+        }
+        if (K > SEL_CAP) {
+            select_class_general(a, b, c, w_alive, w_supp, lane);
+            continue;
+        }
+        // 2. keys -> shared memory, bitonic sort (descending), exact re-ranking of equal-value runs
+        uint16_t* list = s_list[cl];
+        int n2 = 32;
+        while (n2 < K) n2 <<= 1;
+        for (int p = lane; p < n2; p += 32) {
+            unsigned long long key = 0ull;                            // padding sorts last (every real key is > 0)
+            if (p < K) {
+                const int idx = list[p];
+                key = ((unsigned long long)ford(__ldg(conf_img + (size_t)idx * a.C + c)) << 32) | (unsigned long long)(0xffffu - idx);
+            }
+            w_key[p] = key;
+        }
+        for (int w = lane; w < a.W; w += 32) w_supp[w] = 0u;
+        __syncwarp();
+        for (int size = 2; size <= n2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = lane; t < (n2 >> 1); t += 32) {
+                    const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));      // lower index of the t-th pair
+                    const int hi = lo + stride;
+                    const bool desc = (lo & size) == 0;
+                    const unsigned long long x = w_key[lo], y = w_key[hi];
+                    if ((x < y) == desc) { w_key[lo] = y; w_key[hi] = x; }
+                }
+                __syncwarp();
+            }
+        }
+        if (c > 0) {                                                  // ties descend into earlier class columns
+            bool tie = false;
+            for (int p = lane; p < K; p += 32) {
+                const uint32_t v = (uint32_t)(w_key[p] >> 32);
+                tie |= (p > 0 && (uint32_t)(w_key[p - 1] >> 32) == v) || (p + 1 < K && (uint32_t)(w_key[p + 1] >> 32) == v);
+            }
+            if (__any_sync(0xffffffffu, tie)) {
+                unsigned long long* tmp = reinterpret_cast<unsigned long long*>(w_box);
+                for (int p = lane; p < K; p += 32) {
+                    const unsigned long long kp = w_key[p];
+                    const uint32_t v = (uint32_t)(kp >> 32);
+                    int s = p, e = p + 1;
+                    while (s > 0 && (uint32_t)(w_key[s - 1] >> 32) == v) --s;
+                    while (e < K && (uint32_t)(w_key[e] >> 32) == v) ++e;
+                    int rank = s;
+                    if (e - s > 1) {
+                        const int j = 0xffff - (int)(kp & 0xffffu);
+                        for (int qq = s; qq < e; ++qq) {
+                            if (qq == p) continue;
+                            const int i = 0xffff - (int)(w_key[qq] & 0xffffu);
+                            if (precedes(conf_img, a.C, c, i, 0.f, j, 0.f)) ++rank;       // equal values: earlier columns, then index
+                        }
+                    } else {
+                        rank = p;
+                    }
+                    tmp[rank] = kp;
+                }
+                __syncwarp();
+                for (int p = lane; p < K; p += 32) w_key[p] = tmp[p];
+                __syncwarp();
+            }
+        }
+        // 3. boxes in visiting order, greedy sweep out of shared memory.  The alive mask lives in REGISTERS (lane w holds
+        //    word w: K <= 256 = 8 words); a live box r tests the later candidates 32 at a time, the owner lane of each word
+        //    clears the hits -- no shared-memory traffic, atomics or barriers inside the loop.
+        for (int p = lane; p < K; p += 32) w_box[p] = load_box(bmin, bmax, 0xffff - (int)(w_key[p] & 0xffffu));
+        __syncwarp();
+        const int words = (K + 31) / 32;
+        uint32_t alive = 0u;
+        if (lane < words) alive = (lane * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - lane * 32)) - 1u);
+        int kept = 0;
+        for (int g = 0; g < words; ++g) {
+            uint32_t m = __shfl_sync(0xffffffffu, alive, g);
+            while (m) {                                               // warp-uniform
+                const int bit = __ffs(m) - 1;
+                const int r = g * 32 + bit;
+                const float4 bi = w_box[r];
+                const float ai = box_area(bi);
+                if (lane == 0) list[kept] = (uint16_t)(0xffff - (int)(w_key[r] & 0xffffu));   // kept <= r: slot already consumed
+                ++kept;
+                for (int wd = g; wd < words; ++wd) {
+                    const int jj = wd * 32 + lane;
+                    const uint32_t aw = __shfl_sync(0xffffffffu, alive, wd);
+                    bool kill = false;
+                    if (jj > r && jj < K && ((aw >> lane) & 1u)) {
+                        const float4 bj = w_box[jj];
+                        kill = iou_hit(bi, ai, bj, box_area(bj), a.thr_iou, thr_lo, quick);
+                    }
+                    const uint32_t km = __ballot_sync(0xffffffffu, kill);
+                    if (lane == wd) alive &= ~km;
+                }
+                m = __shfl_sync(0xffffffffu, alive, g) & (bit == 31 ? 0u : (0xffffffffu << (bit + 1)));
+            }
+        }
+        // suppressed candidates = the ones whose alive bit was cleared
+        for (int p0 = 0; p0 < K; p0 += 32) {
+            const uint32_t aw = __shfl_sync(0xffffffffu, alive, p0 >> 5);
+            const int p = p0 + lane;
+            if (p < K && !((aw >> lane) & 1u)) {
+                const int j = 0xffff - (int)(w_key[p] & 0xffffu);
+                atomicOr(&w_supp[j >> 5], 1u << (j & 31));
+            }
+        }
+        __syncwarp();
+        uint16_t* kept_out = a.cand + ((size_t)b * a.C + c) * a.N;
+        for (int p = lane; p < kept; p += 32) kept_out[p] = list[p];
+        uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
+        for (int w = lane; w < a.W; w += 32) supp_out[w] = w_supp[w];
+        if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+        __syncwarp();
     }   // class loop
 }
 
@@ -167,13 +368,14 @@ __global__ void __launch_bounds__(256) nms_order_kernel(NmsArgs a) {
     }
 }
 
-// apply: a CTA owns a [64 boxes][32 classes] tile of one image.  The tile is loaded with coalesced 128-byte rows into
-// shared memory; each warp then walks class COLUMNS (lanes = boxes), so the kept list of the class is uniform across
-// the warp and its boxes are broadcast from shared memory -- the IoU loop has no global loads and no divergence.
-// Only tiles of classes that kept something are touched; modified tiles are written back coalesced.
-static constexpr int AP_BOXES = 64, AP_CLASSES = 32;
-__global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
-    __shared__ float tile[AP_BOXES][AP_CLASSES + 1];
+// apply: a CTA owns a [128 boxes][32 classes] tile of one image.  The tile is loaded with coalesced 128-bit loads into
+// shared memory; each warp then walks class COLUMNS (lanes = boxes, 4 per lane), so the kept list of the class is uniform
+// across the warp and its boxes are broadcast from shared memory -- the IoU loop has no global loads and no divergence.
+// Candidates look their fate up in the suppressed mask select wrote.  Only tiles of classes that kept something are
+// touched; modified tiles are written back coalesced.
+static constexpr int AP_BOXES = 128, AP_CLASSES = 32, AP_H = AP_BOXES / 32;
+__global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
+    __shared__ float tile[AP_BOXES][AP_CLASSES + 1];                     // +1: column walks are bank-conflict-free
     __shared__ float4 kbox[8][32];
     __shared__ float karea[8][32];
     __shared__ int tile_cnt[AP_CLASSES];
@@ -182,6 +384,8 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
     const int c_tiles = (a.C + AP_CLASSES - 1) / AP_CLASSES;
     const int n_tiles = (a.N + AP_BOXES - 1) / AP_BOXES;
     const long long total_tiles = (long long)a.B * n_tiles * c_tiles;
+    const bool quick = a.thr_iou > 0.0f;
+    const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
     for (long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
         const int ct = (int)(tix % c_tiles);
         const long long r0 = tix / c_tiles;
@@ -201,93 +405,98 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a) {
         __syncthreads();                                             // everyone has read it before the next tile resets it
         if (!ak) continue;                                           // block-uniform
         float* conf_img = a.conf + (size_t)b * a.N * a.C;
-        // load: row = box, 32 consecutive classes = one 128-byte segment per warp
-        for (int r = warp; r < AP_BOXES; r += 8) {
-            const int n = n0 + r, c = c0 + lane;
-            tile[r][lane] = (n < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
+        if (vec4) {                                                  // thread = (box row, 4 classes): 8 threads cover a 128-byte row
+            const int q = (threadIdx.x & 7) * 4;
+            for (int r = threadIdx.x >> 3; r < AP_BOXES; r += 32) {
+                const int n = n0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < a.N && c0 + q < a.C) v = *reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + q);
+                tile[r][q] = v.x; tile[r][q + 1] = v.y; tile[r][q + 2] = v.z; tile[r][q + 3] = v.w;
+            }
+        } else {
+            for (int r = warp; r < AP_BOXES; r += 8) {
+                const int n = n0 + r, c = c0 + lane;
+                tile[r][lane] = (n < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
+            }
         }
         __syncthreads();
         const float* bmin = a.xy_min + (size_t)b * a.N * 2;
         const float* bmax = a.xy_max + (size_t)b * a.N * 2;
-        float4 bn[2];
-        bool n_ok[2];
+        float4 bn[AP_H];
+        float barea[AP_H];
+        bool n_ok[AP_H];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < AP_H; ++h) {
             const int n = n0 + h * 32 + lane;
             n_ok[h] = n < a.N;
             bn[h] = n_ok[h] ? load_box(bmin, bmax, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            barea[h] = box_area(bn[h]);
         }
-        const float barea[2] = {__fmul_rn(__fsub_rn(bn[0].z, bn[0].x), __fsub_rn(bn[0].w, bn[0].y)),
-                                __fmul_rn(__fsub_rn(bn[1].z, bn[1].x), __fsub_rn(bn[1].w, bn[1].y))};
         bool wrote = false;
-        const bool quick = a.thr_iou > 0.0f;
-        const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
             const int cnt = tile_cnt[cl];
             if (cnt == 0) continue;                                  // warp-uniform
             const uint16_t* kept = a.cand + ((size_t)b * a.C + c0 + cl) * a.N;
-            float v[2];
-            bool cand[2], found[2] = {false, false}, hit[2] = {false, false};
+            const uint32_t* supp = a.supp + ((size_t)b * a.C + c0 + cl) * a.W + (n0 >> 5);
+            bool skip[AP_H], hit[AP_H];
+            bool all_skip = true;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) { v[h] = tile[h * 32 + lane][cl]; cand[h] = v[h] > a.thr; }
-            for (int k0 = 0; k0 < cnt; k0 += 32) {
-                const int kc = min(32, cnt - k0);
-                int kidx = -1;
-                if (lane < kc) {
-                    kidx = kept[k0 + lane];
-                    const float4 kq = load_box(bmin, bmax, kidx);
-                    kbox[warp][lane] = kq;
-                    karea[warp][lane] = __fmul_rn(__fsub_rn(kq.z, kq.x), __fsub_rn(kq.w, kq.y));
-                }
-                __syncwarp();
-                for (int t = 0; t < kc; ++t) {
-                    const float4 kb = kbox[warp][t];
-                    const float ka = karea[warp][t];
-                    const int ki = __shfl_sync(0xffffffffu, kidx, t);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        found[h] |= (ki == n0 + h * 32 + lane);
-                        if (cand[h] || hit[h]) continue;
-                        if (quick) {
-                            // Same float32 operations as iou_ref up to the divide (bit-identical inter and den), then a
-                            // conservative filter: rn(inter/den) >= thr needs inter >= thr*(1-2^-24)*den, so anything
-                            // below 0.999*thr*den is certainly no hit and skips the IEEE division.  Disjoint pairs
-                            // (inter == 0) fall out here too.  NaNs fail the '<' and take the exact path.
-                            const float iw = fmaxf(__fsub_rn(fminf(kb.z, bn[h].z), fmaxf(kb.x, bn[h].x)), 0.0f);
-                            const float ih = fmaxf(__fsub_rn(fminf(kb.w, bn[h].w), fmaxf(kb.y, bn[h].y)), 0.0f);
-                            const float inter = __fmul_rn(iw, ih);
-                            const float den = fmaxf(__fsub_rn(__fadd_rn(ka, barea[h]), inter), 1e-10f);
-                            if (inter < __fmul_rn(thr_lo, den)) continue;
-                            hit[h] = __fdiv_rn(inter, den) >= a.thr_iou;
-                        } else {
-                            hit[h] = iou_ref(kb, bn[h]) >= a.thr_iou;
-                        }
+            for (int h = 0; h < AP_H; ++h) {
+                const bool cand = tile[h * 32 + lane][cl] > a.thr;
+                hit[h] = false;
+                if (cand && n_ok[h]) hit[h] = (__ldg(supp + h) >> lane) & 1u;       // suppressed candidate
+                skip[h] = cand || !n_ok[h];
+                all_skip &= skip[h];
+            }
+            if (!__all_sync(0xffffffffu, all_skip)) {
+                for (int k0 = 0; k0 < cnt; k0 += 32) {
+                    const int kc = min(32, cnt - k0);
+                    if (lane < kc) {
+                        const float4 kq = load_box(bmin, bmax, kept[k0 + lane]);
+                        kbox[warp][lane] = kq;
+                        karea[warp][lane] = box_area(kq);
                     }
+                    __syncwarp();
+                    for (int t = 0; t < kc; ++t) {
+                        const float4 kb = kbox[warp][t];
+                        const float ka = karea[warp][t];
+#pragma unroll
+                        for (int h = 0; h < AP_H; ++h)
+                            if (!skip[h] && !hit[h]) hit[h] = iou_hit(kb, ka, bn[h], barea[h], a.thr_iou, thr_lo, quick);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const bool zero = n_ok[h] && (cand[h] ? !found[h] : hit[h]);
-                if (zero) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
-            }
+            for (int h = 0; h < AP_H; ++h)
+                if (hit[h]) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
         }
         if (wrote) dirty = 1;
         __syncthreads();
         if (dirty) {
-            for (int r = warp; r < AP_BOXES; r += 8) {
-                const int n = n0 + r, c = c0 + lane;
-                if (n < a.N && c < a.C) conf_img[(size_t)n * a.C + c] = tile[r][lane];
+            if (vec4) {
+                const int q = (threadIdx.x & 7) * 4;
+                for (int r = threadIdx.x >> 3; r < AP_BOXES; r += 32) {
+                    const int n = n0 + r;
+                    if (n < a.N && c0 + q < a.C)
+                        *reinterpret_cast<float4*>(conf_img + (size_t)n * a.C + c0 + q) = make_float4(tile[r][q], tile[r][q + 1], tile[r][q + 2], tile[r][q + 3]);
+                }
+            } else {
+                for (int r = warp; r < AP_BOXES; r += 8) {
+                    const int n = n0 + r, c = c0 + lane;
+                    if (n < a.N && c < a.C) conf_img[(size_t)n * a.C + c] = tile[r][lane];
+                }
             }
         }
         __syncthreads();
     }
 }
 
+static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 size_t nms_workspace_bytes(int B, int N, int C) {
-    const size_t lists = (size_t)B * C * N * sizeof(uint16_t);
-    const size_t a16 = (lists + 15) & ~(size_t)15;
-    return 2 * a16 + (((size_t)B * C * sizeof(int)) + 15 & ~(size_t)15);
+    const size_t lists = al16((size_t)B * C * N * sizeof(uint16_t));
+    const size_t masks = al16((size_t)B * C * ((N + 31) / 32) * sizeof(uint32_t));
+    return 2 * lists + masks + al16((size_t)B * C * sizeof(int));
 }
 
 int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
@@ -299,30 +508,39 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
                nms_workspace_bytes(B, N, C));
     Y2_REQUIRE((reinterpret_cast<uintptr_t>(xy_min) & 7) == 0 && (reinterpret_cast<uintptr_t>(xy_max) & 7) == 0,
                "nms: box arrays must be 8-byte aligned");
+    Y2_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "nms: workspace must be 16-byte aligned");
     if (status_out) Y2_CUDA(cudaMemsetAsync(status_out, 0, (size_t)B * sizeof(int), s));
     if (B == 0 || N == 0 || C == 0) return 0;
     Y2_REQUIRE(B <= 65535, "nms: batch too large for one launch");
     NmsArgs a;
-    a.conf = conf; a.xy_min = xy_min; a.xy_max = xy_max; a.B = B; a.N = N; a.C = C;
+    a.conf = conf; a.xy_min = xy_min; a.xy_max = xy_max; a.B = B; a.N = N; a.C = C; a.W = (N + 31) / 32;
     a.thr = threshold; a.thr_iou = threshold_iou;
-    const size_t a16 = ((size_t)B * C * N * sizeof(uint16_t) + 15) & ~(size_t)15;
-    a.cand = reinterpret_cast<uint16_t*>(ws);
-    a.sorted = reinterpret_cast<uint16_t*>(static_cast<char*>(ws) + a16);
-    a.kept_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + 2 * a16);
+    const size_t lists = al16((size_t)B * C * N * sizeof(uint16_t));
+    const size_t masks = al16((size_t)B * C * a.W * sizeof(uint32_t));
+    char* base = static_cast<char*>(ws);
+    a.cand = reinterpret_cast<uint16_t*>(base);
+    a.sorted = reinterpret_cast<uint16_t*>(base + lists);
+    a.supp = reinterpret_cast<uint32_t*>(base + 2 * lists);
+    a.kept_cnt = reinterpret_cast<int*>(base + 2 * lists + masks);
     a.status = status_out;
     a.order_out = order_out;
+    const int vec4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(conf) & 15) == 0;
+    const size_t smem = sel_smem_bytes(a.W);
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_current_device(attr_seen))
+        Y2_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(NMS_MAX_N / 32)));
     dim3 grid((C + 31) / 32, B);
-    nms_select_kernel<<<grid, NMS_WARPS * 32, 0, s>>>(a);
+    nms_select_kernel<<<grid, NMS_WARPS * 32, smem, s>>>(a, vec4);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     if (order_out) {
         nms_order_kernel<<<B, 256, (size_t)N * sizeof(float), s>>>(a);
         Y2_CUDA(cudaGetLastError());
-    note_launch();
+        note_launch();
     }
     long long blocks = (long long)B * ((N + AP_BOXES - 1) / AP_BOXES) * ((C + AP_CLASSES - 1) / AP_CLASSES);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a);
+    nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a, vec4);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

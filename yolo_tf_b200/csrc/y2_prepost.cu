@@ -96,55 +96,82 @@ int standardize_launch(const void* x, int elem_bytes, int B, size_t n, float* ou
 }
 
 // ---------------------------------------------------------------------------------------------
-// detections: one block (8 warps) per image, a warp per box: coalesced row read, shuffle argmax with "first maximum"
-// tie-break, then an ordered append (box index order) through a per-chunk warp prefix in shared memory.
+// detections (detect.py:72-87), two passes, no host round trip:
+//   argmax  : a warp per box over the whole batch (coalesced row read, shuffle argmax with "first maximum" tie-break);
+//             class and score are parked UNCOMPACTED at index n of the output arrays.
+//   compact : one block per image walks its boxes in chunks of blockDim (box-index order), block-wide exclusive scan of
+//             the keep flags (`score > threshold`), ordered append.  A kept box moves from n to pos <= n and every chunk is
+//             read into registers before anything of it is written, so the compaction is done in place.
 __global__ void __launch_bounds__(256)
-detections_kernel(const float* __restrict__ conf, const float* __restrict__ xy_min, const float* __restrict__ xy_max, int N, int C,
-                  float threshold, float sx, float sy, int* __restrict__ count, int* __restrict__ box, int* __restrict__ cls,
-                  float* __restrict__ score, float* __restrict__ xywh) {
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int keep[8], base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    for (int n0 = 0; n0 < N; n0 += 8) {
-        const int n = n0 + warp;
+detections_argmax_kernel(const float* __restrict__ conf, long long boxes, int C, int* __restrict__ cls, float* __restrict__ score) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long g = warp0; g < boxes; g += nwarps) {
+        const float* row = conf + (size_t)g * C;
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        if (n < N) {
-            const float* row = conf + ((size_t)b * N + n) * C;
-            for (int c = lane; c < C; c += 32) {
-                const float v = __ldg(row + c);
-                if (v > best) { best = v; bi = c; }         // ascending c per lane: strict > keeps the first maximum
-            }
+        for (int c = lane; c < C; c += 32) {
+            const float v = __ldg(row + c);
+            if (v > best) { best = v; bi = c; }             // ascending c per lane: strict > keeps the first maximum
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        const bool k = (n < N) && (best > threshold);
-        if (lane == 0) keep[warp] = k ? 1 : 0;
-        __syncthreads();
-        int pos = base;
-        for (int w = 0; w < warp; ++w) pos += keep[w];
-        if (k && lane == 0) {
+        if (lane == 0) { cls[g] = bi; score[g] = best; }
+    }
+}
+__global__ void __launch_bounds__(1024)
+detections_compact_kernel(const float* __restrict__ xy_min, const float* __restrict__ xy_max, int N, float threshold, float sx, float sy,
+                          int* __restrict__ count, int* __restrict__ box, int* __restrict__ cls, float* __restrict__ score,
+                          float* __restrict__ xywh) {
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __shared__ int wsum[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += blockDim.x) {
+        const int n = n0 + threadIdx.x;
+        float sc = 0.f;
+        int ci = 0;
+        bool k = false;
+        if (n < N) {
+            sc = score[(size_t)b * N + n];
+            ci = cls[(size_t)b * N + n];
+            k = sc > threshold;                              // strict, NaN never kept (detect.py:80)
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();                                     // every thread has read its (cls, score) and published its warp's count
+        int pos = base + __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += wsum[w];
+        if (k) {
             const size_t o = (size_t)b * N + pos;
-            box[o] = n; cls[o] = bi; score[o] = best;
-            const float x0 = xy_min[((size_t)b * N + n) * 2], y0 = xy_min[((size_t)b * N + n) * 2 + 1];
-            const float x1 = xy_max[((size_t)b * N + n) * 2], y1 = xy_max[((size_t)b * N + n) * 2 + 1];
-            xywh[o * 4 + 0] = __fmul_rn(x0, sx); xywh[o * 4 + 1] = __fmul_rn(y0, sy);
-            xywh[o * 4 + 2] = __fmul_rn(__fsub_rn(x1, x0), sx); xywh[o * 4 + 3] = __fmul_rn(__fsub_rn(y1, y0), sy);
+            box[o] = n; cls[o] = ci; score[o] = sc;
+            const float2 lo = __ldg(reinterpret_cast<const float2*>(xy_min) + (size_t)b * N + n);
+            const float2 hi = __ldg(reinterpret_cast<const float2*>(xy_max) + (size_t)b * N + n);
+            *reinterpret_cast<float4*>(xywh + o * 4) = make_float4(__fmul_rn(lo.x, sx), __fmul_rn(lo.y, sy), __fmul_rn(__fsub_rn(hi.x, lo.x), sx),
+                                                                  __fmul_rn(__fsub_rn(hi.y, lo.y), sy));
         }
         __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += keep[w]; base += t; }
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nw; ++w) t += wsum[w]; base += t; }
         __syncthreads();
     }
     if (threadIdx.x == 0) count[b] = base;
 }
 int detections_launch(const float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold, float sx, float sy,
                       int* count, int* box, int* cls, float* score, float* xywh, cudaStream_t s) {
-    detections_kernel<<<B, 256, 0, s>>>(conf, xy_min, xy_max, N, C, threshold, sx, sy, count, box, cls, score, xywh);
+    Y2_REQUIRE((reinterpret_cast<uintptr_t>(xy_min) & 7) == 0 && (reinterpret_cast<uintptr_t>(xy_max) & 7) == 0 &&
+               (reinterpret_cast<uintptr_t>(xywh) & 15) == 0, "detections: box arrays must be 8-byte, xywh 16-byte aligned");
+    const long long boxes = (long long)B * N;
+    long long blocks = (boxes + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    detections_argmax_kernel<<<(int)blocks, 256, 0, s>>>(conf, boxes, C, cls, score);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    detections_compact_kernel<<<B, 1024, 0, s>>>(xy_min, xy_max, N, threshold, sx, sy, count, box, cls, score, xywh);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -398,4 +398,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// The same with the 16-bit operand formats chosen per operand (kind::f16 takes f16 or bf16 for A and for B independently:
+// instruction-descriptor fields a_format [7,10) and b_format [10,13), 0 = f16, 1 = bf16).
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(uint32_t m, uint32_t n, bool a_f16, bool b_f16) {
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 }  // namespace y2

@@ -37,6 +37,7 @@ struct WgradParams {
     float* sk_partial;
     float* sk_run;                            // [grid][128][block_n] running sums of capped accumulation chains (CapIter)
     int kcap;                                 // longest tensor-core accumulation chain in k-blocks (0 = unlimited)
+    int fmt;                                  // FMT_* bits: element formats of the x (A) and dx (B) planes
     unsigned int* sk_flags;
     unsigned int epoch;
 };
@@ -166,7 +167,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else if (warp == 1) {
         // MMA issuer: whole warp converged, the elected lane issues.  D = f32, A = B = bf16, both MN-major (bits 15, 16)
         const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t idesc = make_idesc_bf16(WG_M, (uint32_t)p.block_n) | (1u << 15) | (1u << 16);
+        const uint32_t mn = (1u << 15) | (1u << 16);
+        const uint32_t idesc = make_idesc_16(WG_M, (uint32_t)p.block_n, p.fmt & FMT_A_HI, p.fmt & FMT_B_HI) | mn;
+        const uint32_t idesc_hl = make_idesc_16(WG_M, (uint32_t)p.block_n, p.fmt & FMT_A_HI, p.fmt & FMT_B_LO) | mn;
+        const uint32_t idesc_lh = make_idesc_16(WG_M, (uint32_t)p.block_n, p.fmt & FMT_A_LO, p.fmt & FMT_B_HI) | mn;
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t ha = (uint32_t)(make_mnmajor_desc(0, a_row, a_atom) >> 32);      // high words: constants
         const uint32_t hb = (uint32_t)(make_mnmajor_desc(0, 128, b_atom) >> 32);
@@ -197,8 +201,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 for (int k = 0; k < WG_KPIX / 16; ++k) {
                     const uint32_t ak = (uint32_t)k * a_kstep, bk = (uint32_t)k * b_kstep;
                     tc_mma_f16_e(leader, d_tmem, da_hi + ak, ha, db_hi + bk, hb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    tc_mma_f16_e(leader, d_tmem, da_hi + ak, ha, db_lo + bk, hb, idesc, 1u);
-                    tc_mma_f16_e(leader, d_tmem, da_lo + ak, ha, db_hi + bk, hb, idesc, 1u);
+                    tc_mma_f16_e(leader, d_tmem, da_hi + ak, ha, db_lo + bk, hb, idesc_hl, 1u);
+                    tc_mma_f16_e(leader, d_tmem, da_lo + ak, ha, db_hi + bk, hb, idesc_lh, 1u);
                 }
                 tc_commit_e(leader, &empty[stage]);
                 if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -498,6 +502,7 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
     p.sk_partial = reinterpret_cast<float*>(static_cast<char*>(sk_ws) + 4096);
     p.sk_run = p.sk_partial + (size_t)num_sms * WG_M * 256;     // second half of tc_conv_streamk_bytes()
     p.kcap = g_conv_kcap;
+    p.fmt = g_wgrad_fmt;
     const int stage_bytes = 2 * (WG_M * WG_KPIX * 2 + bn * WG_KPIX * 2);
     int stages = (WG_SMEM - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -543,11 +548,9 @@ int wgrad_tc_run(const bf16* x_planes, int B, int H, int W, int Cin, int ksize, 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         Y2_REQUIRE(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-        attr = true;
-    }
     unsigned int e = wg_epoch.fetch_add(1) + 0x40000001u;     // disjoint from the forward kernel's epochs for a long time
     p.epoch = e;
     wgrad_tc_kernel<<<L.grid, WG_THREADS, L.smem_bytes, stream>>>(L.map_x, L.map_d, L.p);

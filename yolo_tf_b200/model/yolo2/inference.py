@@ -76,6 +76,8 @@ class _Engine(object):
         self.classes, self.num_anchors, self.arch = classes, num_anchors, arch
         self.loaded_version = None
         self.loaded_store = None
+        self.loaded_key = None
+        self.center = True
         self.ws = None
         L = _lib.lib()
         self.layers = []
@@ -92,7 +94,7 @@ class _Engine(object):
         return cls._cache[key]
 
     def sync_weights(self, scope, store, device, center=True, weights_initializer=V.xavier_uniform):
-        if self.loaded_store is store and self.loaded_version == store.version:
+        if self.loaded_store is store and self.loaded_version == store.version and self.loaded_key == (scope, bool(center)):
             return
         L = _lib.lib()
         n = len(self.layers)
@@ -111,7 +113,8 @@ class _Engine(object):
                 bias = store.get(name + "/biases", (cout,), V.zeros, device)
                 _lib.check(L.y2_load_weights(self.h, i, _lib.ptr(w), None, None, None, None, _lib.ptr(bias),
                                              _lib.current_stream()))
-        self.loaded_store, self.loaded_version = store, store.version
+        self.loaded_store, self.loaded_version, self.loaded_key = store, store.version, (scope, bool(center))
+        self.center = bool(center)
 
     def forward(self, x, precision=0):
         import torch
@@ -176,7 +179,8 @@ class _Engine(object):
             views[name + "/weights"] = flat[w_off.value:w_off.value + k * k * cin * cout].view(k, k, cin, cout)
             if bn:
                 views[name + "/BatchNorm/gamma"] = flat[g_off.value:g_off.value + cout]
-                views[name + "/BatchNorm/beta"] = flat[b_off.value:b_off.value + cout]
+                # center=False graphs (`_darknet`): the shift is the separate `<conv>/biases` variable, there is no beta
+                views[name + ("/BatchNorm/beta" if self.center else "/biases")] = flat[b_off.value:b_off.value + cout]
             else:
                 views[name + "/biases"] = flat[b_off.value:b_off.value + cout]
         return flat, views

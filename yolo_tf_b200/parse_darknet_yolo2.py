@@ -32,8 +32,11 @@ def transpose_biases(biases, num_anchors):
     return np.concatenate([biases[:, 4:5], biases[:, 0:4], biases[:, 5:]], -1).reshape([-1])
 
 
-def read(path, classes, num_anchors, scope='yolo2_darknet'):
-    """-> (header dict, {variable name: float32 ndarray}) with TF variable names and layouts."""
+def read(path, classes, num_anchors, scope='yolo2_darknet', center=True):
+    """-> (header dict, {variable name: float32 ndarray}) with TF variable names and layouts.
+    center=False (the `_darknet` / `_tiny` graphs, inference.py:62-66,125-126): those graphs have no BatchNorm/beta but a
+    `<conv>/biases` variable, and the reference's walk (`for suffix in ['biases', 'beta', 'gamma', ...]`,
+    parse_darknet_yolo2.py:85-90) assigns the file's first per-layer block to it."""
     path = os.path.expanduser(os.path.expandvars(path))
     raw = np.fromfile(path, dtype=np.uint8)
     if raw.size < 16:
@@ -55,7 +58,8 @@ def read(path, classes, num_anchors, scope='yolo2_darknet'):
         prefix = '%s/%s/' % (scope, name)
         if has_bn:
             for suffix in ('beta', 'gamma', 'moving_mean', 'moving_variance'):        # parse_darknet_yolo2.py:85 order
-                values[prefix + 'BatchNorm/' + suffix] = np.array(take(cout, prefix + suffix), dtype=np.float32)
+                name = prefix + ('biases' if (suffix == 'beta' and not center) else 'BatchNorm/' + suffix)
+                values[name] = np.array(take(cout, name), dtype=np.float32)
         else:
             values[prefix + 'biases'] = np.array(take(cout, prefix + 'biases'), dtype=np.float32)
         w = take(cout * cin * k * k, prefix + 'weights').reshape([cout, cin, k, k])   # Darknet format
@@ -67,8 +71,9 @@ def read(path, classes, num_anchors, scope='yolo2_darknet'):
     return header, values
 
 
-def load(path, classes, num_anchors, scope='yolo2_darknet', store=None):
-    """Read `path` and assign every variable into the store (the sess.run(v.assign(p)) loop of the reference)."""
-    header, values = read(path, classes, num_anchors, scope)
+def load(path, classes, num_anchors, scope='yolo2_darknet', store=None, center=True):
+    """Read `path` and assign every variable into the store (the sess.run(v.assign(p)) loop of the reference).
+    Pass center=False when the config selects `_darknet` / `_tiny` (see read())."""
+    header, values = read(path, classes, num_anchors, scope, center)
     (store if store is not None else V.default_store()).assign(values)
     return header
