@@ -574,6 +574,10 @@ def run_train(args, torch, dist, dev, world, rank, local, barrier):
     store.assign({"yolo2_darknet/" + k: v for k, v in params.items()})
     builder = Builder.from_values([str(i) for i in range(C)], size, size, ANCHORS_VOC, hparam=HPARAM)
     train_op = create_train_op(builder, AdamOptimizer(1e-6), clip_gradient_norm=args.clip)       # train.py:127-129,160
+    from yolo_tf_b200.model.yolo2 import inference
+    for key, val in (("train_f16", args.train_f16), ("train_kcap", args.train_kcap)):
+        if val >= 0:
+            _lib.check(L.y2_set_option(inference._Engine.get(dev, C, 5).h, key.encode(), val))
     rs = np.random.RandomState(100 + rank)
     host_x = [torch.from_numpy(rs.normal(0, 1, size=(B, size, size, 3)).astype(np.float32)).pin_memory() for _ in range(2)]
     dev_x = [t.to(dev) for t in host_x]
@@ -710,6 +714,8 @@ def main():
     ap.add_argument("--pair", type=int, default=-1, help="CTA-pair (cta_group::2) conv mode: -1 = library default, 0 off, 1 = 3x3 N=256 layers, 2 = all eligible")
     ap.add_argument("--conv0-tc", type=int, default=-1, help="conv0 on the tensor cores (y2_set_option conv0_tc): -1 = library default")
     ap.add_argument("--clip", type=float, default=1.0, help="train: per-tensor clip_by_norm (train.py:128; 0 = off)")
+    ap.add_argument("--train-f16", type=int, default=-1, help="train: fp16 planes in the training forward (y2_set_option train_f16); -1 = library default (1)")
+    ap.add_argument("--train-kcap", type=int, default=-1, help="train: accumulation-chain cap of the training forward in k-blocks (train_kcap); -1 = library default (8)")
     ap.add_argument("--cpu-images", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nms-sweep", action="store_true")

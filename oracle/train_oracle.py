@@ -26,19 +26,21 @@ from .darknet_oracle import BN_EPS, LEAKY_ALPHA, layer_table
 BN_DECAY = 0.999
 
 
-def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=torch.float64, taps=None, device="cpu", taps_numpy=True):
+def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=torch.float64, taps=None, device="cpu", taps_numpy=True, table=None):
     """Returns dict(objectives, total, grads {variable name -> ndarray}, net, new_moving {name -> ndarray},
     dnet = d total / d net).  Variable names as in oracle/darknet_oracle.py (no scope prefix).
     ``device``: where torch evaluates this same restatement.  "cpu" is the oracle of record; "cuda" (float64,
     TF32 off) is used by the -m gpu tests only for BASELINE config 3 at its full size (B = 64, 416 x 416), where the
-    float64 step is ~7 TFLOP and tens of GB -- minutes on the host cores, seconds on the device."""
+    float64 step is ~7 TFLOP and tens of GB -- minutes on the host cores, seconds on the device.
+    ``table``: layer table (default: darknet's ``layer_table``); pass ``tiny_layer_table(classes, A)`` for ``tiny()``
+    (model/yolo2/inference.py:25-50), whose 2x2 stride-1 SAME max-pool (:42) pads bottom/right only and ignores the padding."""
     anchors = np.asarray(anchors, dtype=np.float64)
     A = len(anchors)
     P = {k: torch.tensor(np.asarray(v), dtype=dtype, device=device, requires_grad=("moving" not in k)) for k, v in params.items()}
     x = torch.tensor(np.ascontiguousarray(x_nhwc), dtype=dtype, device=device).permute(0, 3, 1, 2)
     new_moving = {}
     passthrough = None
-    for name, k, cin, cout, then in layer_table(classes, A):
+    for name, k, cin, cout, then in (table if table is not None else layer_table(classes, A)):
         if then == "after_concat":
             b, c, h, w = passthrough.shape
             r = passthrough.permute(0, 2, 3, 1).reshape(b, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5)
@@ -62,6 +64,8 @@ def train_step_oracle(x_nhwc, params, classes, anchors, labels, hparam, dtype=to
             passthrough = x
         if then in ("pool", "passthrough+pool"):
             x = F.max_pool2d(x, 2, 2)
+        elif then == "pool_s1":
+            x = F.max_pool2d(F.pad(x, (0, 1, 0, 1), value=float("-inf")), 2, 1)
     net = x.permute(0, 2, 3, 1).contiguous()
     net.retain_grad()
     b, hc, wc, _ = net.shape

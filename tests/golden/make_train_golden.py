@@ -29,12 +29,11 @@ def summary(name, g):
     return np.concatenate([[np.sqrt((flat ** 2).sum())], flat[:8] if flat.size >= 8 else np.pad(flat, (0, 8 - flat.size)), [flat @ probe]])
 
 
-def main():
+def one_step(func, x):
+    """One training step of the reference's own `func` ('darknet' | 'tiny') graph + Model + Objectives -> dict of arrays."""
     from oracle import head_oracle as ho
-    rs = np.random.RandomState(29)
-    x = rs.normal(0, 1, size=(2, 64, 96, 3)).astype(np.float32)                  # 2 x 3 cells, batch 2
-    labels = ho.synthetic_labels(2, CLASSES, 3, 2, seed=SEED_LABELS)
-    params = mb.checkpoint("darknet", CLASSES, ANCHORS_N, True)
+    labels = ho.synthetic_labels(x.shape[0], CLASSES, x.shape[2] // 32, x.shape[1] // 32, seed=SEED_LABELS)
+    params = mb.checkpoint(func, CLASSES, ANCHORS_N, True)
     g = mb.Graph(params, True)
     leaves = {}
     base_var = g.var
@@ -56,14 +55,14 @@ def main():
     exec(compile(ast.Module(body=[n for n in ast.parse(open(mb.REF_FN2).read()).body if isinstance(n, ast.FunctionDef) and n.name == "reorg"],
                             type_ignores=[]), mb.REF_FN2, "exec"), ns_r)
     ns = {"tf": tf, "slim": slim, "inspect": inspect, "leaky_relu": ns_l["leaky_relu"], "reorg": ns_r["reorg"], "__name__": "model.yolo2.inference"}
-    exec(compile(ast.Module(body=[n for n in ast.parse(open(mb.REF_INF).read()).body if isinstance(n, ast.FunctionDef) and n.name == "darknet"],
+    exec(compile(ast.Module(body=[n for n in ast.parse(open(mb.REF_INF).read()).body if isinstance(n, ast.FunctionDef) and n.name == func],
                             type_ignores=[]), mb.REF_INF, "exec"), ns)
     # Model / Objectives of the reference, sharing the same tf stand-in
     ns2 = {"np": np, "tf": tf, "yolo": None}
     tree2 = ast.parse(open(mh.REF2).read())
     exec(compile(ast.Module(body=[n for n in tree2.body if isinstance(n, ast.ClassDef) and n.name in ("Model", "Objectives")], type_ignores=[]),
                  mh.REF2, "exec"), ns2)
-    scope, net = ns["darknet"](mh.T(torch.as_tensor(x, dtype=torch.float64)), CLASSES, ANCHORS_N, True)
+    scope, net = ns[func](mh.T(torch.as_tensor(x, dtype=torch.float64)), CLASSES, ANCHORS_N, True)
     net.v.retain_grad()
     model = ns2["Model"](net, CLASSES, ho.ANCHORS_VOC, training=True)
     obj = ns2["Objectives"](model, *[mh.T(torch.tensor(np.asarray(l), dtype=torch.float64)) for l in labels])
@@ -77,8 +76,18 @@ def main():
     assert all(leaves[n].grad is not None for n in names), [n for n in names if leaves[n].grad is None]
     arrays["grad_names"] = np.array(names)
     arrays["grad_summary"] = np.stack([summary(n, leaves[n].grad.numpy()) for n in names])
+    return arrays
+
+
+def main():
+    rs = np.random.RandomState(29)
+    x = rs.normal(0, 1, size=(2, 64, 96, 3)).astype(np.float32)                  # 2 x 3 cells, batch 2
+    arrays = one_step("darknet", x)
+    # tiny() (inference.py:25-50) through the same machinery, incl. its stride-1 SAME max-pool; keys prefixed "tiny_"
+    xt = np.random.RandomState(31).normal(0, 1, size=(3, 96, 64, 3)).astype(np.float32)
+    arrays.update({"tiny_" + k: v for k, v in one_step("tiny", xt).items()})
     np.savez_compressed(os.path.join(HERE, "train_reference.npz"), **arrays)
-    print("total", float(total.detach()), {k: float(obj[k].v.detach()) for k in mh.HPARAM}, len(names), "gradients")
+    print("darknet total", float(arrays["total"]), "tiny total", float(arrays["tiny_total"]), len(arrays["grad_names"]), "+", len(arrays["tiny_grad_names"]), "gradients")
     print("wrote train_reference.npz %.0f KiB" % (os.path.getsize(os.path.join(HERE, "train_reference.npz")) / 1024))
 
 

@@ -110,7 +110,7 @@ def test_tiny_padded_channels_are_exact_zeros_and_variables_keep_logical_shapes(
     assert np.abs(w).max() <= 0.2 and 0.08 < w.std() < 0.1
 
 
-def test_tiny_builder_detect_pipeline_and_training_refusal(cuda):
+def test_tiny_builder_detect_pipeline(cuda):
     """config/yolo2/tiny-20.ini selects `inference = tiny`: Builder -> Model -> device NMS, checked against the oracles."""
     import torch
     from oracle.nms_c import nms_c_batch
@@ -135,6 +135,75 @@ def test_tiny_builder_detect_pipeline_and_training_refusal(cuda):
     non_max_suppress_device(conf, lo, hi, 0.02, 0.4)
     nms_c_batch(c_ref, lo.cpu().numpy(), hi.cpu().numpy(), 0.02, 0.4)
     assert np.array_equal(conf.cpu().numpy().view(np.uint32), c_ref.view(np.uint32))
-    with pytest.raises(_lib.Y2Error):
-        inference.tiny(torch.from_numpy(x).to(cuda), classes, 5, training=True)
     assert inference.TINY_DOWNSAMPLING == (32, 32) and inference._TINY_DOWNSAMPLING == (32, 32)
+
+
+def _rel(a, b):
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("size,batch,seed", [((96, 64), 3, 31), ((128, 128), 8, 5), ((416, 416), 8, 7)])
+def test_tiny_training_step_vs_autograd_oracle(cuda, size, batch, seed):
+    """SURVEY 8(f) row 4, the training half: `tiny(training=True)` -> Model -> Objectives -> backward through the reference-shaped
+    API against oracle/train_oracle.py on tiny's layer table (pinned to one step of the reference's own tiny() source,
+    tests/golden/train_reference.npz): batch-statistics BN over 9 convs, the stride-1 SAME max-pool and its overlapping-window
+    gradient, conv0 / conv1 stored with 32 channels but trained as the 16-channel variables they are.
+    forward / objectives / d(total)/d(net): 1e-4; variable gradients: float32's own accuracy (as for Darknet-19)."""
+    import torch
+    from oracle.train_oracle import train_step_oracle
+    from tests_gpu_train_helpers import check_gradients_like_float32
+    from yolo_tf_b200 import _lib
+    from yolo_tf_b200.model.yolo2 import Builder
+    classes = 20
+    h, w = size
+    table = tiny_layer_table(classes, 5)
+    params = init_params(classes, 5, seed=seed, table=table)
+    store = _setup_store(params)
+    x = np.random.RandomState(seed + 10).normal(0, 1, size=(batch, h, w, 3)).astype(np.float32)
+    labels = ho.synthetic_labels(batch, classes, w // 32, h // 32, seed=seed)
+    builder = Builder.from_values([str(i) for i in range(classes)], w, h, ho.ANCHORS_VOC, inference_name="tiny")
+    builder(torch.from_numpy(x).to(cuda), training=True)
+    builder.create_objectives(labels)
+    flat, grads = builder.backward(allreduce=False)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().y2_check_async_errors())
+    dev = "cuda" if h >= 416 else "cpu"
+    ref = train_step_oracle(x, params, classes, ho.ANCHORS_VOC, labels, ho.HPARAM_DEFAULT, table=table, device=dev)
+    f32 = train_step_oracle(x, params, classes, ho.ANCHORS_VOC, labels, ho.HPARAM_DEFAULT, dtype=torch.float32, table=table, device=dev)
+    net_err, dnet_err = _rel(builder.output.cpu().numpy(), ref["net"]), _rel(builder.objectives.grad_inputs.cpu().numpy(), ref["dnet"])
+    print("tiny %s B=%d: forward %.2e (fp32 oracle %.2e), dnet %.2e (fp32 %.2e)" % (size, batch, net_err, _rel(f32["net"], ref["net"]), dnet_err,
+                                                                                 _rel(f32["dnet"], ref["dnet"])))
+    assert net_err <= 1e-4 and dnet_err <= 1e-4
+    for k, v in ref["objectives"].items():
+        assert abs(float(builder.objectives[k]) - v) <= 1e-4 * max(abs(v), 1e-9), k
+    assert set(grads) == {"yolo2_tiny/" + k for k in ref["grads"]} and flat.numel() == sum(v.size for v in ref["grads"].values())
+    assert tuple(grads["yolo2_tiny/conv0/weights"].shape) == (3, 3, 3, 16) and tuple(grads["yolo2_tiny/conv1/weights"].shape) == (3, 3, 16, 32)
+    check_gradients_like_float32(grads, ref, f32, "yolo2_tiny/")
+    for name, v in ref["new_moving"].items():          # slim UPDATE_OPS
+        got = store.global_variables()["yolo2_tiny/" + name].cpu().numpy()
+        assert np.abs(got - v).max() <= 1e-5 * max(1.0, np.abs(v).max()), name
+
+
+def test_tiny_train_op_moves_the_variables(cuda):
+    """create_train_op on the tiny graph: one Adam step changes every variable and the next forward uses the new weights."""
+    import torch
+    from yolo_tf_b200 import variables
+    from yolo_tf_b200.model.yolo2 import Builder
+    from yolo_tf_b200.optimizer import AdamOptimizer, create_train_op
+    classes = 20
+    params = init_params(classes, 5, seed=3, table=tiny_layer_table(classes, 5))
+    store = _setup_store(params)
+    x = torch.from_numpy(np.random.RandomState(4).normal(0, 1, size=(4, 128, 128, 3)).astype(np.float32)).to(cuda)
+    labels = ho.synthetic_labels(4, classes, 4, 4, seed=4)
+    builder = Builder.from_values([str(i) for i in range(classes)], 128, 128, ho.ANCHORS_VOC, inference_name="tiny")
+    op = create_train_op(builder, AdamOptimizer(1e-3), clip_gradient_norm=1.0)
+    before = {k: v.clone() for k, v in store.global_variables().items()}
+    l0 = float(op(x, labels))
+    l1 = float(op(x, labels))
+    torch.cuda.synchronize()
+    after = store.global_variables()
+    assert np.isfinite(l0) and np.isfinite(l1) and l1 != l0
+    moved = [k for k in before if "moving" not in k and not torch.equal(before[k], after[k])]
+    assert len(moved) == 26, sorted(set(before) - set(moved))
+    assert tuple(after["yolo2_tiny/conv0/weights"].shape) == (3, 3, 3, 16)

@@ -2,7 +2,9 @@
 (vs torch fp64), and the whole step -- forward with batch-statistics BN, loss, backward -- through the
 reference-shaped API (Builder(training=True) -> create_objectives -> backward) vs the CPU autograd oracle.
 
-Tolerances: forward / loss 1e-4 relative (north_star); gradients max|a-b|/max|b| per tensor <= GRAD_TOL.
+Tolerances: forward / objectives / d(total)/d(net) 1e-4 relative (north_star), incl. BASELINE configs[2] at its full size
+(B = 64, 416 x 416, 20 classes); end-to-end variable gradients per tensor against the float64 oracle, bounded by a multiple of
+what the float32 evaluation of the same oracle achieves (the step is discontinuous: leaky sign, pool argmax, best-anchor mask).
 """
 import numpy as np
 import pytest
@@ -10,9 +12,9 @@ import pytest
 from oracle import head_oracle as ho
 from oracle.darknet_oracle import init_params
 from oracle.train_oracle import train_step_oracle
+from tests_gpu_train_helpers import GRAD_TOL, check_gradients_like_float32
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 2e-4
 
 
 def _rel(a, b):
@@ -45,7 +47,7 @@ def test_wgrad_kernel_vs_fp64(cuda, b, hw, cin, k, cout, max_ctas):
     assert _rel(got, ref) <= 1e-4
 
 
-def _run_train_step(cuda, classes, size, batch, anchors, seed):
+def _run_train_step(cuda, classes, size, batch, anchors, seed, oracle=True):
     import torch
     from yolo_tf_b200 import _lib, variables
     from yolo_tf_b200.model.yolo2 import Builder
@@ -62,21 +64,20 @@ def _run_train_step(cuda, classes, size, batch, anchors, seed):
     flat, grads = builder.backward(allreduce=False)
     torch.cuda.synchronize()
     _lib.check(_lib.lib().y2_check_async_errors())
-    ref = train_step_oracle(x, params, classes, anchors, labels, ho.HPARAM_DEFAULT)
+    ref = train_step_oracle(x, params, classes, anchors, labels, ho.HPARAM_DEFAULT) if oracle else None
     return builder, flat, grads, ref, store
 
 
 @pytest.mark.parametrize("classes,size,batch,anchors,seed,fwd_tol", [
-    # batch-statistics BN renormalises every layer with few samples per channel (16..100 here) and amplifies the
-    # 2^-17 operand rounding of the split-bf16 GEMMs: the training-mode forward is held to 5e-4 (measured 1.4-2.0e-4;
-    # torch-float32 itself is at 2e-5), the inference-mode forward to 1e-4 (tests/test_gpu_backbone.py, measured 2.5e-5)
-    (20, 160, 4, ho.ANCHORS_VOC, 1, 5e-4), (20, 64, 4, ho.ANCHORS_VOC, 1, 5e-4),
-    (20, 96, 3, ho.ANCHORS_VOC, 2, 5e-4), (80, 64, 2, ho.ANCHORS_COCO, 3, 5e-4)])
+    # batch-statistics BN amplifies every layer's error ~1.16x per following layer (it removes the noise-free mean and
+    # renormalises): round 1's bf16 planes landed at 1.4-2.4e-4 here.  The training forward now runs on fp16 planes with
+    # 8-k-block accumulation chains: measured 1.7-2.3e-5, torch-float32 itself 1.3-1.8e-5 -> the 1e-4 bar.
+    (20, 160, 4, ho.ANCHORS_VOC, 1, 1e-4), (20, 64, 4, ho.ANCHORS_VOC, 1, 1e-4),
+    (20, 96, 3, ho.ANCHORS_VOC, 2, 1e-4), (80, 64, 2, ho.ANCHORS_COCO, 3, 1e-4)])
 def test_train_step_vs_autograd_oracle(cuda, classes, size, batch, anchors, seed, fwd_tol):
     """Truth = the float64 autograd oracle.  The training step is discontinuous in its inputs (max-pool argmax,
     leaky sign at 0, best-anchor equality mask), so even torch-float32 differs from float64 by several per cent on
-    a few gradient tensors at these tiny sizes.  Per-tensor criterion: our error <= max(GRAD_TOL, 4 x the error
-    of the float32 oracle against the same float64 truth)."""
+    a few gradient tensors at these tiny sizes: the gradient bar is float32's own accuracy (_check_gradients_like_float32)."""
     import torch
     builder, flat, grads, ref, store = _run_train_step(cuda, classes, size, batch, anchors, seed)
     params = init_params(classes, 5, seed=seed)
@@ -95,22 +96,37 @@ def test_train_step_vs_autograd_oracle(cuda, classes, size, batch, anchors, seed
     print("worst gradient errors (ours, fp32-oracle floor):", [(k, "%.1e" % v, "%.1e" % floor[k]) for k, v in worst])
     assert report["net"][0] <= fwd_tol
     for k, v in ref["objectives"].items():
-        assert abs(float(builder.objectives[k]) - v) <= 5 * fwd_tol * max(abs(v), 1e-9), k
-    assert report["dnet"][0] <= max(5 * fwd_tol, 4 * report["dnet"][1])
-    # End-to-end gradients: sanity level only (max-norm is ill-conditioned here, see the docstring; the strict
-    # check is test_backward_per_layer_teacher_forced).  Every tensor must point the same way as the truth.
-    cos = {}
-    for name, g_ref in ref["grads"].items():
-        a = grads["yolo2_darknet/" + name].cpu().numpy().astype(np.float64).ravel()
-        b = np.asarray(g_ref, dtype=np.float64).ravel()
-        cos[name] = float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
-    print("lowest cosine(ours, fp64 truth):", sorted(cos.items(), key=lambda kv: kv[1])[:4])
-    assert min(cos.values()) >= 0.98, sorted(cos.items(), key=lambda kv: kv[1])[:4]
+        assert abs(float(builder.objectives[k]) - v) <= fwd_tol * max(abs(v), 1e-9), k
+    assert report["dnet"][0] <= fwd_tol
+    check_gradients_like_float32(grads, ref, f32)
     assert flat.numel() == sum(v.size for v in ref["grads"].values())
     # slim UPDATE_OPS: moving averages follow the batch statistics (decay 0.999)
     for name, v in ref["new_moving"].items():
         got = store.global_variables()["yolo2_darknet/" + name].cpu().numpy()
         assert np.abs(got - v).max() <= 1e-5 * max(1.0, np.abs(v).max()), name
+
+
+def test_train_step_at_baseline_config3_size_vs_fp64_oracle(cuda):
+    """BASELINE configs[2] ITSELF -- B = 64, 416 x 416, 20 classes -- against the float64 autograd oracle (the same restatement,
+    oracle/train_oracle.py, evaluated by torch on the device: ~7 TFLOP of float64, minutes on the host cores).  Round 1 only
+    tested this size for repeatability; the inference bug found at B = 32 showed that small-batch parity does not carry over.
+    forward `net`, the 4 objectives and d(total)/d(net): 1e-4 (north_star).  Variable gradients: float32's own accuracy, per
+    tensor and in aggregate (_check_gradients_like_float32; at this size float32 itself is 1e-4 .. 4e-2 off float64)."""
+    import torch
+    classes, size, batch, seed = 20, 416, 64, 1
+    builder, flat, grads, _, store = _run_train_step(cuda, classes, size, batch, ho.ANCHORS_VOC, seed, oracle=False)
+    params = init_params(classes, 5, seed=seed)
+    x = np.random.RandomState(seed + 10).normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
+    labels = ho.synthetic_labels(batch, classes, size // 32, size // 32, seed=seed)
+    ref = train_step_oracle(x, params, classes, ho.ANCHORS_VOC, labels, ho.HPARAM_DEFAULT, device="cuda")
+    f32 = train_step_oracle(x, params, classes, ho.ANCHORS_VOC, labels, ho.HPARAM_DEFAULT, dtype=torch.float32, device="cuda")
+    torch.cuda.empty_cache()
+    net_err, dnet_err = _rel(builder.output.cpu().numpy(), ref["net"]), _rel(builder.objectives.grad_inputs.cpu().numpy(), ref["dnet"])
+    print("B=64 forward %.2e (fp32 oracle %.2e), dnet %.2e (fp32 %.2e)" % (net_err, _rel(f32["net"], ref["net"]), dnet_err, _rel(f32["dnet"], ref["dnet"])))
+    assert net_err <= 1e-4 and dnet_err <= 1e-4
+    for k, v in ref["objectives"].items():
+        assert abs(float(builder.objectives[k]) - v) <= 1e-4 * max(abs(v), 1e-9), k
+    check_gradients_like_float32(grads, ref, f32)
 
 
 def test_training_then_inference_uses_updated_moving_stats(cuda):

@@ -23,6 +23,12 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
 
 
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().cuda()
+    b = torch.as_tensor(b).double().cuda()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
 def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     size = int(sys.argv[2]) if len(sys.argv) > 2 else 416
@@ -42,6 +48,10 @@ def main():
     cw = size // 32
     labels = ho.synthetic_labels(batch, classes, cw, cw, seed=seed)
     builder = Builder.from_values([str(i) for i in range(classes)], size, size, anchors)
+    eng0 = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+    for key in ("train_f16", "train_kcap"):                       # training-forward numerics (defaults: fp16 planes, 8 k-blocks)
+        if os.environ.get("Y2_" + key.upper()):
+            _lib.check(_lib.lib().y2_set_option(eng0.h, key.encode(), int(os.environ["Y2_" + key.upper()])))
     builder(torch.from_numpy(x).cuda(), training=True)
     builder.create_objectives(labels)
     flat, grads = builder.backward(allreduce=False)
@@ -53,6 +63,7 @@ def main():
     ref = train_step_oracle(x, params, classes, anchors, labels, ho.HPARAM_DEFAULT, taps=taps64, device="cuda", taps_numpy=False)
     f32 = train_step_oracle(x, params, classes, anchors, labels, ho.HPARAM_DEFAULT, dtype=torch.float32, taps=taps32, device="cuda", taps_numpy=False)
     out = {"batch": batch, "size": size, "classes": classes, "seed": seed,
+           "train_f16": os.environ.get("Y2_TRAIN_F16", "default"), "train_kcap": os.environ.get("Y2_TRAIN_KCAP", "default"),
            "net": [rel(builder.output, ref["net"]), rel(f32["net"], ref["net"])],
            "dnet": [rel(builder.objectives.grad_inputs, ref["dnet"]), rel(f32["dnet"], ref["dnet"])],
            "objectives": {k: [abs(float(builder.objectives[k]) - v) / max(abs(v), 1e-30), abs(f32["objectives"][k] - v) / max(abs(v), 1e-30)]
@@ -72,10 +83,13 @@ def main():
     out["layers_y"] = layers
     g = {}
     for name, g_ref in ref["grads"].items():
-        g[name] = [rel(grads["yolo2_darknet/" + name], g_ref), rel(f32["grads"][name], g_ref)]
+        g[name] = [rel(grads["yolo2_darknet/" + name], g_ref), rel(f32["grads"][name], g_ref),
+                   rel_l2(grads["yolo2_darknet/" + name], g_ref), rel_l2(f32["grads"][name], g_ref)]
     out["grads"] = g
     out["worst_grad"] = max(v[0] for v in g.values())
     out["worst_grad_fp32_floor"] = max(v[1] for v in g.values())
+    out["worst_grad_l2"] = max(v[2] for v in g.values())
+    out["worst_grad_l2_fp32_floor"] = max(v[3] for v in g.values())
     print(json.dumps(out, indent=1))
 
 

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -98,7 +99,10 @@ static std::vector<LayerDesc> darknet19_layers(int classes, int anchors) {
 struct LayerState {
     LayerDesc d;
     int cout_pad = 0, block_n = 0;
-    bf16* wpack = nullptr;     // [2][cout_pad][k*k*cin]
+    bf16* wpack = nullptr;     // [2][cout_pad][k*k*cin] bf16 planes (inference; packed lazily, see ensure_pack)
+    bf16* wpack16 = nullptr;   // the same as fp16 planes of w * 2^k (training forward; ensure_pack16)
+    float* wsc = nullptr;      // [2 + cout_s]: 2^k, 2^-k, then the epilogue scale of the raw training conv (2^-k per channel)
+    bool pack_fresh = false, pack16_fresh = false;
     float* w_f32 = nullptr;    // conv0 only (CUDA-core kernel reads HWIO fp32)
     float* scale = nullptr;    // [cout]  inference fold: gamma * rsqrt(moving_var + eps)
     float* bias = nullptr;     // [cout]  inference fold: beta - moving_mean * scale   (final layer: biases)
@@ -119,11 +123,15 @@ struct TrainPlan {
     std::vector<int> oh, ow;
     std::vector<float*> z;          // raw conv outputs
     std::vector<bf16*> y, pooled;   // activations (planes); y[19] lives in the concat buffer
+    std::vector<bf16*> y16, pooled16;   // the same activations as fp16 planes (f16 mode): what the forward convs read
+    bf16* concat16 = nullptr;
+    int f16 = 0;
     std::vector<float*> stat;       // per layer: mean, inv, scale, bias, m1, m2 (6 * cout floats)
     bf16* concat = nullptr;
     float *g0 = nullptr, *g1 = nullptr, *gcat = nullptr;
     bf16* dx = nullptr;
     double* red = nullptr;
+    float* pad = nullptr;           // scratch for parameter gradients at a padded stored shape (tiny's conv0 / conv1)
     void* streamk = nullptr;
     const float* x = nullptr;
 };
@@ -156,6 +164,8 @@ struct y2_handle {
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
     int conv0_tc = 2;                  // y2_set_option("conv0_tc"): conv0 on the tensor cores (SIMT-built im2col tile) instead of the CUDA cores; 2 = + unchecked gather for interior tiles
+    int train_f16 = 1;                 // y2_set_option("train_f16"): training forward on fp16 planes (22 significand bits) with short accumulation chains; 0 = bf16 planes as in inference
+    int train_kcap = 16;               // y2_set_option("train_kcap"): accumulation-chain cap of the training forward convs in k-blocks
     int pair = 1;                      // y2_set_option("pair"): CTA-pair (cta_group::2) convs: 0 off, 1 = 3x3 layers with 256-wide N tiles, 2 = every eligible layer
     int probe_layer = -1;              // test hooks (y2_train_probe)
     float *probe_gy = nullptr, *probe_gin = nullptr;
@@ -209,7 +219,7 @@ int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int
             (i > 0 && cudaMalloc(&s.wpack, 2 * (size_t)s.cout_pad * K * sizeof(bf16)) != cudaSuccess) ||
             cudaMalloc(&s.scale, s.d.cout_s * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&s.bias, s.d.cout_s * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout * sizeof(float)) != cudaSuccess) {
+            cudaMalloc(&s.gamma, 4 * (size_t)s.d.cout_s * sizeof(float)) != cudaSuccess) {
             set_error("y2_create: cudaMalloc failed at layer %zu (%s)", i, cudaGetErrorString(cudaGetLastError()));
             h->layers.push_back(s);            // y2_destroy frees this layer's partial allocations with the earlier layers'
             y2_destroy(h);
@@ -217,7 +227,10 @@ int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int
         }
         cudaMemset(s.scale, 0, s.d.cout_s * sizeof(float));      // padded channels: scale = bias = 0 -> exact zeros
         cudaMemset(s.bias, 0, s.d.cout_s * sizeof(float));
-        s.beta = s.gamma + s.d.cout; s.mmean = s.beta + s.d.cout; s.mvar = s.mmean + s.d.cout;
+        // raw BN variables at the STORED channel count; padded channels keep gamma = beta = mean = var = 0, which makes their
+        // training-mode scale and bias exactly 0 as well (bn_stats: scale = gamma * inv)
+        cudaMemset(s.gamma, 0, 4 * (size_t)s.d.cout_s * sizeof(float));
+        s.beta = s.gamma + s.d.cout_s; s.mmean = s.beta + s.d.cout_s; s.mvar = s.mmean + s.d.cout_s;
         h->layers.push_back(s);
     }
     *out = h;
@@ -230,7 +243,7 @@ void y2_destroy(y2_handle* h) {
     cudaDeviceSynchronize();
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& s : h->layers) {
-        cudaFree(s.wpack); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias); cudaFree(s.gamma); cudaFree(s.wpack_dgrad);
+        cudaFree(s.wpack); cudaFree(s.wpack16); cudaFree(s.wsc); cudaFree(s.w_f32); cudaFree(s.scale); cudaFree(s.bias); cudaFree(s.gamma); cudaFree(s.wpack_dgrad);
     }
     delete h;
 }
@@ -264,8 +277,7 @@ int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* g
     } else if (w_hwio != L.w_f32) {
         Y2_CUDA(cudaMemcpyAsync(L.w_f32, w_hwio, K * L.d.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
-    if (layer > 0 && pack_weights_launch(L.w_f32, L.wpack, L.d.ksize, L.d.cin_s, L.d.cout_s, L.cout_pad, s)) return -1;
-    L.dgrad_fresh = false;
+    L.pack_fresh = L.pack16_fresh = L.dgrad_fresh = false;      // re-packed by the first consumer (ensure_pack*)
     if (L.d.has_bn) {
         Y2_REQUIRE(moving_mean && moving_variance, "y2_load_weights: layer %d needs BN statistics", layer);
         const size_t cb = L.d.cout * sizeof(float);
@@ -284,6 +296,32 @@ int y2_load_weights(y2_handle* h, int layer, const float* w_hwio, const float* g
     L.loaded = true;
     return 0;
 }
+
+}  // extern "C"
+
+// Packed tensor-core operands of a layer's weights, made on first use after y2_load_weights: the inference plan reads the bf16
+// planes, the training forward the fp16 planes (a training step never pays for the bf16 pack and vice versa).
+static int ensure_pack(y2_handle* h, int i, cudaStream_t s) {
+    LayerState& L = h->layers[i];
+    if (i == 0 || L.pack_fresh) return 0;
+    if (pack_weights_launch(L.w_f32, L.wpack, L.d.ksize, L.d.cin_s, L.d.cout_s, L.cout_pad, s)) return -1;
+    L.pack_fresh = true;
+    return 0;
+}
+static int ensure_pack16(y2_handle* h, int i, cudaStream_t s) {
+    LayerState& L = h->layers[i];
+    if (i == 0 || L.pack16_fresh) return 0;
+    const size_t K = (size_t)L.d.ksize * L.d.ksize * L.d.cin_s;
+    if (!L.wpack16) Y2_CUDA(cudaMalloc(&L.wpack16, 2 * (size_t)L.cout_pad * K * sizeof(bf16)));
+    if (!L.wsc) Y2_CUDA(cudaMalloc(&L.wsc, (2 + (size_t)L.d.cout_s) * sizeof(float)));
+    if (pow2_scale_launch(L.w_f32, K * L.d.cout_s, L.wsc, s)) return -1;
+    if (fold_scale_launch(nullptr, L.wsc + 1, L.wsc + 2, L.d.cout_s, s)) return -1;
+    if (pack_weights_launch(L.w_f32, L.wpack16, L.d.ksize, L.d.cin_s, L.d.cout_s, L.cout_pad, s, 1, L.wsc)) return -1;
+    L.pack16_fresh = true;
+    return 0;
+}
+
+extern "C" {
 
 // workspace layout is a pure function of (B,H,W): used by both the size query and the planner
 struct WsLayout {
@@ -416,6 +454,8 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
     if (!P.valid || P.B != B || P.H != H || P.W != W || P.ws != ws || P.precision != precision || P.ws_bytes != ws_bytes)
         if (build_plan(h, B, H, W, ws, ws_bytes, precision, s)) return -1;
     const int nl = (int)h->layers.size();
+    for (int i = 1; i < nl; ++i)
+        if (ensure_pack(h, i, s)) return -1;
     const LayerState& L0 = h->layers[0];
     if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[0], s));
     {
@@ -513,6 +553,8 @@ int y2_set_option(y2_handle* h, const char* key, int value) {
     if (strcmp(key, "halo") == 0) { h->halo = value; h->plan.valid = false; return 0; }
     if (strcmp(key, "pair") == 0) { h->pair = value; h->plan.valid = false; return 0; }
     if (strcmp(key, "conv0_tc") == 0) { h->conv0_tc = value; return 0; }
+    if (strcmp(key, "train_f16") == 0) { h->train_f16 = value ? 1 : 0; h->tplan.valid = false; return 0; }
+    if (strcmp(key, "train_kcap") == 0) { Y2_REQUIRE(value >= 0, "y2_set_option: train_kcap must be >= 0"); h->train_kcap = value; return 0; }
     set_error("y2_set_option: unknown option '%s'", key);
     return -1;
 }

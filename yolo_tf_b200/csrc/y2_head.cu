@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
     const int D = 5 + a.C;
     float* s_in = sm;                              // [G][D]
     float* s_conf = s_in + (size_t)a.G * D;        // [G][C]
-    float* s_box = s_conf + (size_t)a.G * a.C;     // [G][24]: xmin ymin xmax ymax | iou w h area | x y oxmin oymin | oxmax oymax sqw sqh | sx sy w01 h01
+    float* s_box = s_conf + (size_t)a.G * a.C;     // [G][24]: xmin ymin xmax ymax | iou w h area | x y oxmin oymin | oxmax oymax sqw sqh | sx sy w01 h01 | (cx, cy, anchor as ints)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (long long g0 = (long long)blockIdx.x * a.G; g0 < a.boxes; g0 += (long long)gridDim.x * a.G) {
         const int g_cnt = (int)min((long long)a.G, a.boxes - g0);
@@ -62,12 +62,20 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(src4 + i);
             for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s_in[i] = __ldg(a.net + g0 * D + i);
         }
+        // per-box cell coordinates and anchor index: ONE thread per box does the integer divisions (a warp doing them
+        // redundantly in all 32 lanes was a third of the kernel's instructions)
+        if (threadIdx.x < g_cnt) {
+            const int n = (int)((g0 + threadIdx.x) % ((long long)a.cells * a.A));
+            const int cell = n / a.A;
+            int* meta = reinterpret_cast<int*>(s_box + (size_t)threadIdx.x * 24 + 20);
+            meta[0] = cell % a.Wc; meta[1] = cell / a.Wc; meta[2] = n - cell * a.A;
+        }
         __syncthreads();
         for (int g = warp; g < g_cnt; g += nw) {
-            const float* in = s_in + (size_t)g * D;
+            const float* in = s_in + g * D;
             const long long gi = g0 + g;
-            const int n = (int)(gi % ((long long)a.cells * a.A));
-            const int cell = n / a.A, an = n - cell * a.A;
+            const int* meta = reinterpret_cast<const int*>(s_box + g * 24 + 20);
+            const int an = meta[2];
             // softmax over classes (max-subtracted, as tf.nn.softmax); up to 4 classes per lane stay in registers
             float mx = -INFINITY;
             float ev[4];
@@ -99,20 +107,20 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
                 const int c = lane + 32 * t;
                 if (c < a.C) {
                     const float pr = ev[t] / se;
-                    s_conf[(size_t)g * a.C + c] = iou * pr;
+                    s_conf[g * a.C + c] = iou * pr;
                     if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
                 }
             }
             for (int c = lane + 128; c < a.C; c += 32) {
                 const float pr = expf(in[5 + c] - mx) / se;
-                s_conf[(size_t)g * a.C + c] = iou * pr;
+                s_conf[g * a.C + c] = iou * pr;
                 if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
             }
             if (lane == 0) {
                 const float hw = w / 2.0f, hh = h / 2.0f;
                 const float oxmin = sx - hw, oymin = sy - hh, oxmax = sx + hw, oymax = sy + hh;
-                const float cx = (float)(cell % a.Wc), cy = (float)(cell / a.Wc);
-                float4* bx = reinterpret_cast<float4*>(s_box + (size_t)g * 24);
+                const float cx = (float)meta[0], cy = (float)meta[1];
+                float4* bx = reinterpret_cast<float4*>(s_box + g * 24);
                 bx[0] = make_float4(cx + oxmin, cy + oymin, cx + oxmax, cy + oymax);
                 bx[1] = make_float4(iou, w, h, w * h);
                 bx[2] = make_float4(cx + sx, cy + sy, oxmin, oymin);

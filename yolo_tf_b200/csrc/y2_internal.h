@@ -201,7 +201,7 @@ int pack_weights_launch(const float* w_hwio, bf16* wpack, int ksize, int cin, in
 int bn_fold_launch(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                    float* scale, float* bias, int n, cudaStream_t s);
 int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
-                          int C, cudaStream_t s, int stride = 2);
+                          int C, cudaStream_t s, int stride = 2, int f16 = 0);
 int pad_weights_launch(const float* w_hwio, float* out, int ksize, int cin, int cout, int cin_s, int cout_s, cudaStream_t s);
 // reorg (space-to-depth 2) on 16-byte vectors; elem_bytes in {2,4}; out row pitch in elements.
 int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes,
@@ -212,8 +212,9 @@ size_t bn_partial_bytes();
 int bn_stats_launch(const float* z, size_t rows, int C, const float* gamma, const float* beta, float eps, float decay,
                     float* mean, float* inv, float* scale, float* bias, float* moving_mean, float* moving_var,
                     double* partial, cudaStream_t s);
+// y16_*: optional second copy of y as fp16 planes (same pitch), the input format of the training forward's next conv
 int bn_apply_launch(const float* z, const float* scale, const float* bias, bf16* y_hi, bf16* y_lo, size_t rows, int C,
-                    long long ldy, cudaStream_t s);
+                    long long ldy, cudaStream_t s, bf16* y16_hi = nullptr, bf16* y16_lo = nullptr);
 int bn_bwd_reduce_launch(const float* z, const float* g, long long ldg, size_t rows, int C, const float* scale,
                          const float* bias, const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1,
                          float* m2, double* partial, cudaStream_t s);
@@ -223,13 +224,16 @@ int bn_bwd_apply_launch(const float* z, const float* g, long long ldg, const flo
 int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* dbias, double* partial, cudaStream_t s);
 int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, size_t rows, int C, int Cpad, cudaStream_t s);
 int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
-                       int C, cudaStream_t s);
+                       int C, cudaStream_t s, int f16 = 0);
 // pool layers without passthrough: forward z -> pooled planes; backward z + pooled gradient -> dgamma/dbeta + dx planes
 int bn_apply_pool_launch(const float* z, const float* scale, const float* bias, bf16* p_hi, bf16* p_lo, int B, int H, int W, int C,
-                         cudaStream_t s);
+                         cudaStream_t s, bf16* p16_hi = nullptr, bf16* p16_lo = nullptr);
 int bn_bwd_pool_launch(const float* z, const float* gp, long long ldgp, int B, int H, int W, int C, const float* scale, const float* bias,
                        const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1, float* m2, bf16* dx_hi,
-                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s);
+                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s, int f16 = 0);
+int maxpool_s1_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W, int C,
+                          cudaStream_t s, int f16 = 0);
+int compact_hwio_launch(const float* src, float* dst, int taps, int cin_s, int cout_s, int cin, int cout, cudaStream_t s);
 int reorg_bwd_add_launch(const float* gr, long long ldr, float* g, int B, int H, int W, int C, cudaStream_t s);
 int pack_dgrad_weights_launch(const float* w_hwio, bf16* out, int ksize, int cin, int cout, int cin_pad, int cout_pad,
                               cudaStream_t s);

@@ -185,7 +185,7 @@ int bn_fold_launch(const float* gamma, const float* beta, const float* mean, con
 // max-pool ignores padding, so the window of the last row/column is clipped (the clipped taps re-read a valid one).
 __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
                                       bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W,
-                                      int C, int stride) {
+                                      int C, int stride, int f16) {
     const int Ho = H / stride, Wo = W / stride, c8 = C / 8;
     const size_t total = (size_t)B * Ho * Wo * c8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -217,8 +217,8 @@ __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t hw = hw0[q * 4 + w], lw = lw0[q * 4 + w];
-                const float va = bf16_lo_f(hw) + bf16_lo_f(lw);
-                const float vb = bf16_hi_f(hw) + bf16_hi_f(lw);
+                const float va = plane_dec((unsigned short)hw, f16) + plane_dec((unsigned short)lw, f16);
+                const float vb = plane_dec((unsigned short)(hw >> 16), f16) + plane_dec((unsigned short)(lw >> 16), f16);
                 if (va > best_a || q == 0) { best_a = va; ha = hw & 0xFFFFu; la = lw & 0xFFFFu; }
                 if (vb > best_b || q == 0) { best_b = vb; hb = hw & 0xFFFF0000u; lb = lw & 0xFFFF0000u; }
             }
@@ -231,11 +231,11 @@ __global__ void maxpool_planes_kernel(const bf16* __restrict__ in_hi, const bf16
     }
 }
 int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int H, int W,
-                          int C, cudaStream_t s, int stride) {
+                          int C, cudaStream_t s, int stride, int f16) {
     Y2_REQUIRE(stride == 1 || stride == 2, "maxpool: stride must be 1 or 2");
     Y2_REQUIRE(C % 8 == 0 && H % stride == 0 && W % stride == 0, "maxpool: C%%8, H%%stride, W%%stride must be 0");
     const size_t total = (size_t)B * (H / stride) * (W / stride) * (C / 8);
-    maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C, stride);
+    maxpool_planes_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B, H, W, C, stride, f16);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -34,6 +34,20 @@ __device__ __forceinline__ void split4(const float f[4], uint2* hi, uint2* lo) {
     *hi = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
     *lo = make_uint2(pack2(f[0] - h[0], f[1] - h[1]), pack2(f[2] - h[2], f[3] - h[3]));
 }
+// the same in either plane format (f16 = 1: fp16 hi / lo, see y2_internal.h)
+__device__ __forceinline__ void split4f(const float f[4], uint2* hi, uint2* lo, int f16) {
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) plane_split(f[j], f16, h[j], l[j]);
+    *hi = make_uint2(plane_pack2(h[0], h[1]), plane_pack2(h[2], h[3]));
+    *lo = make_uint2(plane_pack2(l[0], l[1]), plane_pack2(l[2], l[3]));
+}
+__device__ __forceinline__ void merge4f(uint2 h, uint2 l, float v[4], int f16) {
+    v[0] = plane_dec((unsigned short)h.x, f16) + plane_dec((unsigned short)l.x, f16);
+    v[1] = plane_dec((unsigned short)(h.x >> 16), f16) + plane_dec((unsigned short)(l.x >> 16), f16);
+    v[2] = plane_dec((unsigned short)h.y, f16) + plane_dec((unsigned short)l.y, f16);
+    v[3] = plane_dec((unsigned short)(h.y >> 16), f16) + plane_dec((unsigned short)(l.y >> 16), f16);
+}
 
 // ---------------------------------------------------------------------------------------------
 // generic two-quantity column reduction over a [rows][C] fp32 matrix (4 channels per thread):
@@ -279,7 +293,8 @@ int bias_grad_launch(const float* g, long long ldg, size_t rows, int C, float* d
 // has no integer division and keeps two rows of loads in flight.  Requires c4 = C/4 to divide 256 (C <= 1024).
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
-                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, size_t rows, int C, long long ldy) {
+                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, size_t rows, int C, long long ldy, bf16* __restrict__ y16_hi,
+                bf16* __restrict__ y16_lo) {
     const int c4 = C / 4;
     const int c = (int)(threadIdx.x % c4) * 4;
     const int rpb = 256 / c4;
@@ -293,6 +308,11 @@ bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
         split4(f, &h, &l);
         *reinterpret_cast<uint2*>(y_hi + r * ldy + c) = h;
         *reinterpret_cast<uint2*>(y_lo + r * ldy + c) = l;
+        if (y16_hi) {                                       // the fp16 planes the next forward conv reads (same pitch)
+            split4f(f, &h, &l, 1);
+            *reinterpret_cast<uint2*>(y16_hi + r * ldy + c) = h;
+            *reinterpret_cast<uint2*>(y16_lo + r * ldy + c) = l;
+        }
     };
     size_t r = (size_t)blockIdx.x * rpb + threadIdx.x / c4;
     for (; r + rstep < rows; r += 2 * rstep) {
@@ -310,9 +330,9 @@ static inline int ew_grid(size_t items) {
     return (int)b;
 }
 int bn_apply_launch(const float* z, const float* scale, const float* bias, bf16* y_hi, bf16* y_lo, size_t rows, int C,
-                    long long ldy, cudaStream_t s) {
+                    long long ldy, cudaStream_t s, bf16* y16_hi, bf16* y16_lo) {
     Y2_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && 256 % (C / 4) == 0, "bn_apply: C/4 must divide 256 and the pitch be a multiple of 4");
-    bn_apply_kernel<<<ew_grid(rows * (size_t)(C / 4) / 2), 256, 0, s>>>(z, scale, bias, y_hi, y_lo, rows, C, ldy);
+    bn_apply_kernel<<<ew_grid(rows * (size_t)(C / 4) / 2), 256, 0, s>>>(z, scale, bias, y_hi, y_lo, rows, C, ldy, y16_hi, y16_lo);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -400,7 +420,7 @@ int split_planes_pad_launch(const float* src, long long ld, bf16* hi, bf16* lo, 
 // max-pool backward: the first maximum of each 2x2 window (row-major window order, strict >) gets the
 // gradient.  Values compared are the exact hi+lo activations.  One thread = 4 channels of one window.
 __global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp, const bf16* __restrict__ y_hi,
-                                   const bf16* __restrict__ y_lo, float* __restrict__ g, int B, int H, int W, int C) {
+                                   const bf16* __restrict__ y_lo, float* __restrict__ g, int B, int H, int W, int C, int f16) {
     const int Ho = H / 2, Wo = W / 2, c4 = C / 4;
     // thread -> fixed channel group; windows walked with 32-bit index arithmetic (c4 divides 256 or is a multiple of it)
     const unsigned windows = (unsigned)B * Ho * Wo;
@@ -431,8 +451,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp,
             off[q] = (((size_t)b * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C + (size_t)cv * 4;
             const uint2 h = __ldg(reinterpret_cast<const uint2*>(y_hi + off[q]));
             const uint2 l = __ldg(reinterpret_cast<const uint2*>(y_lo + off[q]));
-            v[q][0] = bf16lo(h.x) + bf16lo(l.x); v[q][1] = bf16hi(h.x) + bf16hi(l.x);
-            v[q][2] = bf16lo(h.y) + bf16lo(l.y); v[q][3] = bf16hi(h.y) + bf16hi(l.y);
+            merge4f(h, l, v[q], f16);
         }
         float o[4][4];
 #pragma unroll
@@ -449,11 +468,83 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gp, long long ldgp,
     }
 }
 int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W,
-                       int C, cudaStream_t s) {
+                       int C, cudaStream_t s, int f16) {
     Y2_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool_bwd: bad shape");
     Y2_REQUIRE(256 % (C / 4) == 0 || (C / 4) % 256 == 0, "maxpool_bwd: C/4 must divide 256 or be a multiple of it");
     Y2_REQUIRE((size_t)B * (H / 2) * (W / 2) < (1ull << 31), "maxpool_bwd: too many windows");
-    maxpool_bwd_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)) / ((C / 4 + 255) / 256) * ((C / 4 + 255) / 256), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C);
+    maxpool_bwd_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)) / ((C / 4 + 255) / 256) * ((C / 4 + 255) / 256), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C, f16);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2 stride-1 SAME max-pool backward (tiny, model/yolo2/inference.py:42).  Window (wy, wx) covers the pixels
+// (wy .. wy+1, wx .. wx+1) clipped to the image (TF pads bottom / right only and the maximum ignores padding: the clipped taps
+// re-read a valid pixel and, compared with strict >, never win); its gradient goes to the FIRST maximum in window order.
+// Gather form, no atomics: one thread = 4 channels of one INPUT pixel; it re-derives the winner of each of the (up to) four
+// windows that contain the pixel and adds the gradients of the ones it wins.
+__global__ void maxpool_s1_bwd_kernel(const float* __restrict__ gp, long long ldgp, const bf16* __restrict__ y_hi,
+                                      const bf16* __restrict__ y_lo, float* __restrict__ g, int B, int H, int W, int C, int f16) {
+    const int c4 = C / 4;
+    const size_t total = (size_t)B * H * W * c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % c4);
+        size_t t = i / c4;
+        const int x = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int wy = y - 1; wy <= y; ++wy) {
+            if (wy < 0) continue;
+            for (int wx = x - 1; wx <= x; ++wx) {
+                if (wx < 0) continue;
+                const int dy = (wy + 1 < H) ? 1 : 0, dx = (wx + 1 < W) ? 1 : 0;
+                float v[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const size_t off = (((size_t)b * H + wy + (q >> 1) * dy) * W + wx + (q & 1) * dx) * C + (size_t)cv * 4;
+                    merge4f(__ldg(reinterpret_cast<const uint2*>(y_hi + off)), __ldg(reinterpret_cast<const uint2*>(y_lo + off)), v[q], f16);
+                }
+                const size_t prow = ((size_t)b * H + wy) * W + wx;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int best = 0;
+#pragma unroll
+                    for (int q = 1; q < 4; ++q)
+                        if (v[q][j] > v[best][j]) best = q;
+                    const int py = wy + (best >> 1) * dy, px = wx + (best & 1) * dx;
+                    if (py == y && px == x) acc[j] += __ldg(gp + prow * ldgp + cv * 4 + j);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(g + (((size_t)b * H + y) * W + x) * C + (size_t)cv * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+int maxpool_s1_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W, int C,
+                          cudaStream_t s, int f16) {
+    Y2_REQUIRE(C % 4 == 0, "maxpool_s1_bwd: C must be a multiple of 4");
+    maxpool_s1_bwd_kernel<<<ew_grid((size_t)B * H * W * (C / 4)), 256, 0, s>>>(gp, ldgp, y_hi, y_lo, g, B, H, W, C, f16);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+// gradient of a variable whose STORED shape is padded (tiny: conv0's 16 outputs / conv1's 16 inputs live in 32 channels):
+// [taps][cin_s][cout_s] -> the variable's own [taps][cin][cout]
+__global__ void compact_hwio_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int cin_s, int cout_s, int cin, int cout) {
+    const size_t total = (size_t)taps * cin * cout;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % cout);
+        const size_t r = i / cout;
+        const int c = (int)(r % cin);
+        const size_t tap = r / cin;
+        dst[i] = __ldg(src + (tap * cin_s + c) * cout_s + n);
+    }
+}
+int compact_hwio_launch(const float* src, float* dst, int taps, int cin_s, int cout_s, int cin, int cout, cudaStream_t s) {
+    compact_hwio_kernel<<<ew_grid((size_t)taps * cin * cout), 256, 0, s>>>(src, dst, taps, cin_s, cout_s, cin, cout);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -468,13 +559,13 @@ int maxpool_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const 
 struct PoolWin {
     float z[4][4];      // raw conv output of the 4 window pixels
     float yb[4][4];     // z*scale + bias (sign decides the leaky slope)
-    uint32_t hi[4][2], lo[4][2];   // planes of y (2 packed words = 4 channels)
     int best[4];        // winning pixel per channel
     float zw[4], ybw[4];   // z and z*scale+bias of the winner
     size_t off[4];      // element offsets of the 4 pixels (row pitch C)
 };
+// f16: the plane format whose rounding decides the winner (the format the NEXT forward conv reads its input in)
 __device__ __forceinline__ void pool_window_load(PoolWin& w, const float* __restrict__ z, const float (&sc)[4], const float (&bi)[4],
-                                                 int b, int yo, int xo, int H, int W, int C, int c) {
+                                                 int b, int yo, int xo, int H, int W, int C, int c, int f16) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         w.off[q] = (((size_t)b * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C + c;
@@ -491,10 +582,8 @@ __device__ __forceinline__ void pool_window_load(PoolWin& w, const float* __rest
             y[j] = fmaxf(w.yb[q][j], 0.1f * w.yb[q][j]);
         }
         uint2 h, l;
-        split4(y, &h, &l);
-        w.hi[q][0] = h.x; w.hi[q][1] = h.y; w.lo[q][0] = l.x; w.lo[q][1] = l.y;
-        v[q][0] = bf16lo(h.x) + bf16lo(l.x); v[q][1] = bf16hi(h.x) + bf16hi(l.x);
-        v[q][2] = bf16lo(h.y) + bf16lo(l.y); v[q][3] = bf16hi(h.y) + bf16hi(l.y);
+        split4f(y, &h, &l, f16);
+        merge4f(h, l, v[q], f16);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -527,7 +616,9 @@ __device__ __forceinline__ PoolIdx pool_index(int B, int H, int W, int C) {
 // forward: z -> pooled planes
 __global__ void __launch_bounds__(256)
 bn_apply_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ bias,
-                     bf16* __restrict__ p_hi, bf16* __restrict__ p_lo, int B, int H, int W, int C) {
+                     bf16* __restrict__ p_hi, bf16* __restrict__ p_lo, int B, int H, int W, int C, bf16* __restrict__ p16_hi,
+                     bf16* __restrict__ p16_lo) {
+    const int f16 = p16_hi ? 1 : 0;
     const PoolIdx ix = pool_index(B, H, W, C);
     float sc[4], bi[4];
 #pragma unroll
@@ -537,29 +628,27 @@ bn_apply_pool_kernel(const float* __restrict__ z, const float* __restrict__ scal
         const unsigned t = w / ix.Wo;
         const int yo = (int)(t % ix.Ho), b = (int)(t / ix.Ho);
         PoolWin pw;
-        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c);
-        uint32_t oh[2], ol[2];
+        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c, f16);
+        float yw[4];                                         // the winner's activation; its planes are a pure function of it
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int qa = pw.best[2 * k], qb = pw.best[2 * k + 1];
-            uint32_t ha = 0, hb = 0, la = 0, lb = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q == qa) { ha = pw.hi[q][k] & 0xFFFFu; la = pw.lo[q][k] & 0xFFFFu; }
-                if (q == qb) { hb = pw.hi[q][k] & 0xFFFF0000u; lb = pw.lo[q][k] & 0xFFFF0000u; }
-            }
-            oh[k] = ha | hb; ol[k] = la | lb;
-        }
+        for (int j = 0; j < 4; ++j) yw[j] = fmaxf(pw.ybw[j], 0.1f * pw.ybw[j]);
         const size_t po = (size_t)w * C + ix.c;
-        *reinterpret_cast<uint2*>(p_hi + po) = make_uint2(oh[0], oh[1]);
-        *reinterpret_cast<uint2*>(p_lo + po) = make_uint2(ol[0], ol[1]);
+        uint2 h, l;
+        split4(yw, &h, &l);
+        *reinterpret_cast<uint2*>(p_hi + po) = h;
+        *reinterpret_cast<uint2*>(p_lo + po) = l;
+        if (f16) {
+            split4f(yw, &h, &l, 1);
+            *reinterpret_cast<uint2*>(p16_hi + po) = h;
+            *reinterpret_cast<uint2*>(p16_lo + po) = l;
+        }
     }
 }
 int bn_apply_pool_launch(const float* z, const float* scale, const float* bias, bf16* p_hi, bf16* p_lo, int B, int H, int W, int C,
-                         cudaStream_t s) {
+                         cudaStream_t s, bf16* p16_hi, bf16* p16_lo) {
     Y2_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0 && H % 2 == 0 && W % 2 == 0, "bn_apply_pool: bad shape");
     Y2_REQUIRE((size_t)B * (H / 2) * (W / 2) < (1ull << 31), "bn_apply_pool: too many windows");
-    bn_apply_pool_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(z, scale, bias, p_hi, p_lo, B, H, W, C);
+    bn_apply_pool_kernel<<<ew_grid((size_t)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(z, scale, bias, p_hi, p_lo, B, H, W, C, p16_hi, p16_lo);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -573,7 +662,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_pool_kernel(const float* __restrict__ z, const float* __restrict__ gp, long long ldgp, const float* __restrict__ scale,
                    const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ inv,
                    const float* __restrict__ m1, const float* __restrict__ m2, bf16* __restrict__ dx_hi, bf16* __restrict__ dx_lo,
-                   double* __restrict__ partial, float* __restrict__ gy_out, int B, int H, int W, int C) {
+                   double* __restrict__ partial, float* __restrict__ gy_out, int B, int H, int W, int C, int f16) {
     const PoolIdx ix = pool_index(B, H, W, C);
     const int c4 = C / 4;
     float sc[4], bi[4], mu[4], iv[4], q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
@@ -598,7 +687,7 @@ bn_bwd_pool_kernel(const float* __restrict__ z, const float* __restrict__ gp, lo
             for (int j = 0; j < 4; ++j) g[j] = __ldg(gp + (size_t)w * ldgp + ix.c + j);
         }
         PoolWin pw;
-        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c);
+        pool_window_load(pw, z, sc, bi, b, yo, xo, H, W, C, ix.c, f16);
         if (!APPLY) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -652,20 +741,20 @@ bn_bwd_pool_kernel(const float* __restrict__ z, const float* __restrict__ gp, lo
 }
 int bn_bwd_pool_launch(const float* z, const float* gp, long long ldgp, int B, int H, int W, int C, const float* scale, const float* bias,
                        const float* mean, const float* inv, float* dgamma, float* dbeta, float* m1, float* m2, bf16* dx_hi,
-                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s) {
+                       bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s, int f16) {
     Y2_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0 && H % 2 == 0 && W % 2 == 0 && C <= 1024, "bn_bwd_pool: bad shape");
     const size_t windows = (size_t)B * (H / 2) * (W / 2);
     Y2_REQUIRE(windows < (1ull << 31), "bn_bwd_pool: too many windows");
     int nb = red_blocks(windows * 4, C);
     bn_bwd_pool_kernel<false><<<nb, 256, 0, s>>>(z, gp, ldgp, scale, bias, mean, inv, nullptr, nullptr, nullptr, nullptr, partial, nullptr,
-                                                  B, H, W, C);
+                                                  B, H, W, C, f16);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     bn_bwd_finish_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(partial, nb, C, 1.0 / (double)(windows * 4), dgamma, dbeta, m1, m2);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     bn_bwd_pool_kernel<true><<<ew_grid(windows * (size_t)(C / 4)), 256, 0, s>>>(z, gp, ldgp, scale, bias, mean, inv, m1, m2, dx_hi, dx_lo,
-                                                                               nullptr, gy_out, B, H, W, C);
+                                                                               nullptr, gy_out, B, H, W, C, f16);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -146,7 +146,7 @@ class Builder(object):
         return self
 
     def __call__(self, data, training=False):
-        _, self.output = self.func(data, len(self.names), len(self.anchors), training=training)
+        self.scope, self.output = self.func(data, len(self.names), len(self.anchors), training=training)
         self.model = Model(self.output, len(self.names), self.anchors, training=training)
 
     def create_objectives(self, labels):
@@ -163,8 +163,11 @@ class Builder(object):
         With torch.distributed initialised, the bucket is averaged over the data-parallel replicas with ONE
         all-reduce (the reference has no multi-GPU support, README.md:99)."""
         from ... import parallel
-        eng = inference._Engine.get(self.output.device, len(self.names), len(self.anchors))
+        eng = inference._Engine.get(self.output.device, len(self.names), len(self.anchors), self._arch())
         flat, views = eng.backward(self.objectives.grad_inputs)
         if allreduce:
             parallel.allreduce_mean_(flat)
-        return flat, {"yolo2_darknet/" + k: v for k, v in views.items()}
+        return flat, {self.scope + "/" + k: v for k, v in views.items()}
+
+    def _arch(self):
+        return inference.ARCH_TINY if self.func in (inference.tiny, inference._tiny) else inference.ARCH_DARKNET

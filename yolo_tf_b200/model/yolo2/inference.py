@@ -8,7 +8,7 @@ concat, the final linear 1x1 conv -- runs as hand-written sm_100a kernels behind
 
 ``tiny`` (inference.py:25-50) is the second function the shipped configs select
 (config/yolo2/tiny-{20,80}.ini): the same kernels behind a different layer table (y2_create_net with
-Y2_ARCH_TINY); inference only.
+Y2_ARCH_TINY), inference and training step.
 """
 import sys
 
@@ -221,14 +221,15 @@ def tiny(net, classes, num_anchors, training=False, center=True, precision=None)
     """Tiny YOLOv2 backbone (inference.py:25-50): conv0..conv4 (16..256 channels, each + 2x2/2 max-pool), conv5 (512) +
     2x2 stride-1 SAME max-pool, conv6/conv7 (1024), linear 1x1 conv.  Same signature and ``(scope, net)`` return as the
     reference; scope == 'yolo2_tiny'.  Weights not present in the variable store are created with the reference's
-    initializer for this function (truncated_normal(stddev=0.1), :33).  Inference only: training=True raises."""
+    initializer for this function (truncated_normal(stddev=0.1), :33).  training=True runs the batch-statistics forward and keeps
+    the state `Builder.backward` needs, like `darknet`."""
     scope = __name__.split('.')[-2] + '_' + sys._getframe().f_code.co_name
     if not net.is_cuda:
         raise _lib.Y2Error("tiny: input must be a CUDA tensor (no CPU path exists)")
-    if training:
-        raise _lib.Y2Error("tiny: the training step (batch-statistics BN + backward) is only built for darknet")
     eng = _Engine.get(net.device, classes, num_anchors, ARCH_TINY)
     eng.sync_weights(scope, V.default_store(), net.device, center=center, weights_initializer=V.truncated_normal_01)
+    if training:
+        return scope, eng.forward_train(net.contiguous(), scope, V.default_store())
     return scope, eng.forward(net.contiguous(), precision=PRECISION if precision is None else precision)
 
 

@@ -59,7 +59,7 @@ class TrainOp(object):
         import torch
         from .model.yolo2 import inference
         L = _lib.lib()
-        eng = inference._Engine.get(flat.device, len(self.builder.names), len(self.builder.anchors))
+        eng = inference._Engine.get(flat.device, len(self.builder.names), len(self.builder.anchors), self.builder._arch())
         store = V.default_store()
         names = list(views.keys())                             # bucket order: per layer weights, gamma, beta | biases
         if L.y2_num_param_tensors(eng.h) != len(names):
