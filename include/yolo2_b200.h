@@ -38,11 +38,11 @@ void y2_destroy(y2_handle* h);
  * 'inference'))`, model/yolo2/__init__.py:107; config/yolo2/{darknet,tiny}-*.ini).  y2_create_net selects it:
  *   Y2_ARCH_DARKNET  `darknet()`  model/yolo2/inference.py:61-120  (y2_create == this)
  *   Y2_ARCH_TINY     `tiny()`     model/yolo2/inference.py:25-50: 16..512-channel 3x3 convs, five 2x2/2 max-pools, one
- *                    2x2 stride-1 SAME max-pool (:42), two 1024-channel 3x3 convs, linear 1x1 conv.  Inference only:
- *                    the training entry points return an error for this network (the reference trains it through the
- *                    same TF autodiff; here only Darknet-19's backward is built).
+ *                    2x2 stride-1 SAME max-pool (:42), two 1024-channel 3x3 convs, linear 1x1 conv.  Inference and the
+ *                    training step (the reference trains it through the same train.py / TF autodiff).
  * Layers whose channel count is below 32 (tiny conv0: 16) are stored zero-padded to 32; y2_layer_info,
- * y2_load_weights and y2_get_activation speak the logical (variable) shapes. */
+ * y2_load_weights, y2_get_activation and the gradient bucket (y2_param_offsets) speak the logical (variable) shapes;
+ * y2_train_get_tensor / y2_train_probe (test hooks) the stored ones. */
 #define Y2_ARCH_DARKNET 0
 #define Y2_ARCH_TINY 1
 int y2_create_net(y2_handle** out, int device, int classes, int num_anchors, int arch);
@@ -88,7 +88,11 @@ unsigned long long y2_launch_count(void);
  * dnet = d(total_loss)/d(out) (from y2_loss_fwd_bwd) -> gradients of every variable in ONE flat float32
  * bucket of y2_param_count() elements, laid out per layer (conv0..conv20, conv) as
  * [weights HWIO | gamma | beta] or [weights | biases] (y2_param_offsets) -- the unit of the single NCCL
- * all-reduce per step.  y2_get_bn_state reads back gamma/beta/moving statistics (device pointers). */
+ * all-reduce per step.  y2_get_bn_state reads back gamma/beta/moving statistics (device pointers).
+ * Numerics: the training forward's convs run on fp16 split planes (22 significand bits, weights pre-scaled by a per-layer
+ * power of two) with accumulation chains of "train_kcap" (16) k-blocks, so that the network output stays within 1e-4 of
+ * float64 although batch-statistics BN amplifies every layer's error; y2_set_option(h, "train_f16", 0) selects the
+ * bf16 planes of the inference path (range-safe, 16 bits, ~2e-4 at the network output). */
 size_t y2_train_workspace_bytes(const y2_handle* h, int B, int H, int W);
 int y2_darknet_forward_train(y2_handle* h, const float* x, int B, int H, int W, float* out, void* ws, size_t ws_bytes,
                              void* stream);
@@ -162,13 +166,20 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
  * the batch and extent admit the spatial tiling (e.g. batch 32 at 416/608); 0 keeps the separate pool pass and
  * materialises the un-pooled activations for y2_get_activation.  "halo" (default 1): run the 32-channel 3x3 layer
  * (conv1, inference.py:75) from one halo tile per output tile with its weights resident in shared memory instead of nine
- * im2col fetches; 0 selects the im2col path (bit-identical results, used by the equivalence tests). */
+ * im2col fetches; 0 selects the im2col path (bit-identical results, used by the equivalence tests).
+ * "pair" (default 1): CTA-pair (cta_group::2) convs, 0 off / 1 the 3x3 layers with 256-wide N tiles / 2 every eligible layer.
+ * "conv0_tc" (default 2): conv0 on the tensor cores.  "keep_activations" (default 0): 1 gives every layer's output its own
+ * workspace slot so that y2_get_activation can read it after the forward (changes y2_workspace_bytes); by default the
+ * outputs alternate between two arenas.  "train_f16" (default 1), "train_kcap" (default 16): numerics of the training
+ * forward, see the training step above. */
 int y2_set_option(y2_handle* h, const char* key, int value);
 
 /* One conv (+scale/bias +leaky) on float32 NHWC tensors through the same tcgen05 kernel the
  * network uses (splits operands on the fly).  Diagnostic / test entry point.
  * block_n = 0 picks the tile width; max_ctas = 0 uses every SM (smaller values change how the
- * stream-K scheduler cuts tiles across CTAs -- used by tests to exercise the partial hand-off). */
+ * stream-K scheduler cuts tiles across CTAs -- used by tests to exercise the partial hand-off).
+ * precision: 0 / 1 as y2_darknet_forward; 2 = fp16 split planes for both operands (the training forward's format);
+ * 3 / 4 = mixed bf16 x fp16 operands, kept as a hardware probe only: tcgen05 kind::f16 faults on them (illegal instruction). */
 int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio, int ksize, int cout,
               const float* scale, const float* bias, int leaky, float* y, int precision, int block_n, int max_ctas,
               void* stream);

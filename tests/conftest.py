@@ -21,6 +21,10 @@ def cuda():
         pytest.skip("no CUDA device")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    # layer-by-layer parity tests read every layer's output back after the forward: one workspace slot per layer
+    # (the product default, two alternating arenas, is covered by test_gpu_options.py, smoke() and bench.py)
+    from yolo_tf_b200.model.yolo2 import inference
+    inference._Engine.KEEP_ACTIVATIONS = True
     return torch.device("cuda:0")
 
 

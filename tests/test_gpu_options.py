@@ -87,3 +87,46 @@ def test_halo_conv_matches_im2col_and_fp64(cuda, b, h, w, cout):
     ref = torch.maximum(ref, 0.1 * ref).cpu().numpy()
     assert np.array_equal(got[0], got[1])
     assert float(np.abs(got[1] - ref).max() / np.abs(ref).max()) <= TOL
+
+
+@pytest.mark.parametrize("arch,classes,size,batch", [("darknet", 80, 416, 4), ("darknet", 20, 96, 32), ("tiny", 20, 128, 8)])
+def test_alternating_workspace_arenas_give_the_same_output_in_less_memory(cuda, arch, classes, size, batch):
+    """Product default: a layer's output lives until the next layer has read it, so the outputs alternate between two arenas
+    (the test suite otherwise runs with one slot per layer, keep_activations = 1, to read every tap back).  Same bits out,
+    >= 2x less workspace, and the per-layer getter says why it cannot serve."""
+    import torch
+    from oracle.darknet_oracle import tiny_layer_table
+    from yolo_tf_b200 import _lib, variables
+    from yolo_tf_b200.model.yolo2 import inference
+    table = tiny_layer_table(classes, 5) if arch == "tiny" else None
+    params = init_params(classes, 5, seed=21, table=table)
+    store = variables.reset_default_store()
+    store.assign({"yolo2_%s/%s" % (arch, k): v for k, v in params.items()})
+    xd = torch.from_numpy(np.random.RandomState(6).normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)).to(cuda)
+    fn = getattr(inference, arch)
+    L = _lib.lib()
+    keep = inference._Engine.KEEP_ACTIVATIONS
+    try:
+        outs, ws = {}, {}
+        for k in (True, False):
+            inference._Engine.KEEP_ACTIVATIONS = k
+            _, out = fn(xd, classes, 5)
+            torch.cuda.synchronize()
+            _lib.check(L.y2_check_async_errors())
+            eng = inference._Engine.get(torch.device("cuda:0"), classes, 5, inference.ARCH_TINY if arch == "tiny" else inference.ARCH_DARKNET)
+            outs[k], ws[k] = out.clone(), L.y2_workspace_bytes(eng.h, batch, size, size)
+            if not k:
+                with pytest.raises(_lib.Y2Error, match="keep_activations"):
+                    eng.activation(2, False, (batch, size // 4, size // 4, eng.layers[2][2]))
+        assert torch.equal(outs[True], outs[False])
+        assert ws[False] < ws[True], ws
+        if arch == "darknet":           # the saving at the bench sizes (size query only): 1.8 -> 0.46 GB at B = 32 / 416^2, 30 -> 7 GB at B = 256 / 608^2
+            big = {}
+            for k in (True, False):
+                inference._Engine.KEEP_ACTIVATIONS = k
+                e = inference._Engine.get(torch.device("cuda:0"), classes, 5)
+                big[k] = (L.y2_workspace_bytes(e.h, 32, 416, 416), L.y2_workspace_bytes(e.h, 256, 608, 608))
+            assert big[False][0] * 3 <= big[True][0] and big[False][1] * 3 <= big[True][1], big
+            assert big[False][1] <= 8 * 2 ** 30, big
+    finally:
+        inference._Engine.KEEP_ACTIVATIONS = keep

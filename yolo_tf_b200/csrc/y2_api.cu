@@ -164,6 +164,7 @@ struct y2_handle {
     int fuse_pool = 1;                 // y2_set_option("fuse_pool")
     int halo = 1;                      // y2_set_option("halo"): halo-tile mode for the 32-channel 3x3 layer (conv1)
     int conv0_tc = 2;                  // y2_set_option("conv0_tc"): conv0 on the tensor cores (SIMT-built im2col tile) instead of the CUDA cores; 2 = + unchecked gather for interior tiles
+    int keep_activations = 0;          // y2_set_option("keep_activations"): 1 = every layer's output keeps its own workspace slot (y2_get_activation, tests); 0 = two alternating arenas
     int train_f16 = 1;                 // y2_set_option("train_f16"): training forward on fp16 planes (22 significand bits) with short accumulation chains; 0 = bf16 planes as in inference
     int train_kcap = 16;               // y2_set_option("train_kcap"): accumulation-chain cap of the training forward convs in k-blocks
     int pair = 1;                      // y2_set_option("pair"): CTA-pair (cta_group::2) convs: 0 off, 1 = 3x3 layers with 256-wide N tiles, 2 = every eligible layer
@@ -334,33 +335,50 @@ static int layout_workspace(const y2_handle* h, int B, int H, int W, WsLayout* o
     Y2_REQUIRE(H % 32 == 0 && W % 32 == 0, "input size %dx%d is not divisible by the downsampling 32 (utils/__init__.py:52-56)", W, H);
     const int nl = (int)h->layers.size();
     out->act_off.assign(nl, 0); out->pool_off.assign(nl, 0); out->oh.assign(nl, 0); out->ow.assign(nl, 0);
-    size_t off = 0;
+    // A layer's output (un-pooled and / or pooled planes) is read by the NEXT layer only (the passthrough tap is copied into
+    // the concat buffer by its own layer), so by default the outputs alternate between two arenas sized for the largest
+    // layer: 0.46 GB instead of 1.8 GB at B = 32 / 416^2, 7 GB instead of 30 GB at B = 256 / 608^2.  keep_activations = 1
+    // gives every layer its own slot so that y2_get_activation can read any of them after the forward (tests, diagnostics).
+    std::vector<size_t> a_bytes(nl, 0), p_bytes(nl, 0);
     int ch = H, cw = W;
     for (int i = 0; i < nl; ++i) {
         const LayerState& L = h->layers[i];
         out->oh[i] = ch; out->ow[i] = cw;
         const size_t M = (size_t)B * ch * cw;
-        if (i == 0) {                              // conv0 writes its pooled output only
-            out->act_off[i] = off;
-            off = align_up(off + 2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
+        if (i == nl - 1) break;                    // final layer writes the caller's buffer
+        if (i == 0) {                              // conv0 writes its pooled output only (kept in the "act" slot)
+            a_bytes[i] = align_up(2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
             ch /= 2; cw /= 2;
             continue;
         }
-        if (i == nl - 1) break;                    // final layer writes the caller's buffer
-        if (L.d.to_concat) {                       // conv19 writes into the concat buffer
-            out->act_off[i] = (size_t)-1;
-        } else {
-            out->act_off[i] = off;
-            off = align_up(off + 2 * M * L.d.cout_s * sizeof(bf16), 1024);
-        }
+        // the un-pooled output: not for the layer that writes into the concat buffer (conv19), and -- arena mode -- not for
+        // a pool layer whose max-pool is certain to be fused into its conv epilogue (build_plan's condition is a superset)
+        const bool surely_fused = !h->keep_activations && L.d.pool == 1 && !L.d.passthrough && h->fuse_pool && tc_conv_can_fuse_pool(B, ch, cw);
+        if (!L.d.to_concat && !surely_fused) a_bytes[i] = align_up(2 * M * L.d.cout_s * sizeof(bf16), 1024);
         if (L.d.pool == 1) {
-            out->pool_off[i] = off;
-            off = align_up(off + 2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
+            p_bytes[i] = align_up(2 * (M / 4) * L.d.cout_s * sizeof(bf16), 1024);
             ch /= 2; cw /= 2;
         } else if (L.d.pool == 2) {                // stride 1: same extent
-            out->pool_off[i] = off;
-            off = align_up(off + 2 * M * L.d.cout_s * sizeof(bf16), 1024);
+            p_bytes[i] = align_up(2 * M * L.d.cout_s * sizeof(bf16), 1024);
         }
+    }
+    size_t off = 0;
+    if (h->keep_activations) {
+        for (int i = 0; i < nl - 1; ++i) {
+            out->act_off[i] = a_bytes[i] ? off : (size_t)-1;
+            off += a_bytes[i];
+            out->pool_off[i] = off;
+            off += p_bytes[i];
+        }
+    } else {
+        size_t arena = 0;
+        for (int i = 0; i < nl - 1; ++i) arena = std::max(arena, a_bytes[i] + p_bytes[i]);
+        for (int i = 0; i < nl - 1; ++i) {
+            const size_t base = (i & 1) ? arena : 0;
+            out->act_off[i] = a_bytes[i] ? base : (size_t)-1;
+            out->pool_off[i] = base + a_bytes[i];
+        }
+        off = 2 * arena;
     }
     out->concat_off = off;
     off = align_up(off + 2 * (size_t)B * ch * cw * h->cat_c * sizeof(bf16), 1024);
@@ -523,6 +541,9 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
     Y2_REQUIRE(P.valid, "y2_get_activation: no forward has run");
     const int nl = (int)h->layers.size();
     Y2_REQUIRE(layer >= 0 && layer < nl - 1, "y2_get_activation: layer %d out of range", layer);
+    Y2_REQUIRE(h->keep_activations || h->layers[layer].d.to_concat,
+               "y2_get_activation: the layers' outputs share two alternating arenas; y2_set_option(h, \"keep_activations\", 1) before the "
+               "forward keeps every layer's output readable");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const LayerDesc& d = h->layers[layer].d;
     const size_t M = (size_t)P.B * P.oh[layer] * P.ow[layer];
@@ -549,10 +570,11 @@ int y2_get_activation(y2_handle* h, int layer, int pooled, float* dst, void* str
  * "halo" (default 1); "pair" -- CTA-pair convs (see y2_handle::pair). */
 int y2_set_option(y2_handle* h, const char* key, int value) {
     Y2_REQUIRE(h && key, "y2_set_option: null argument");
-    if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }
+    if (strcmp(key, "fuse_pool") == 0) { h->fuse_pool = value ? 1 : 0; h->plan.valid = false; return 0; }      // changes y2_workspace_bytes in arena mode
     if (strcmp(key, "halo") == 0) { h->halo = value; h->plan.valid = false; return 0; }
     if (strcmp(key, "pair") == 0) { h->pair = value; h->plan.valid = false; return 0; }
     if (strcmp(key, "conv0_tc") == 0) { h->conv0_tc = value; return 0; }
+    if (strcmp(key, "keep_activations") == 0) { h->keep_activations = value ? 1 : 0; h->plan.valid = false; return 0; }
     if (strcmp(key, "train_f16") == 0) { h->train_f16 = value ? 1 : 0; h->tplan.valid = false; return 0; }
     if (strcmp(key, "train_kcap") == 0) { Y2_REQUIRE(value >= 0, "y2_set_option: train_kcap must be >= 0"); h->train_kcap = value; return 0; }
     set_error("y2_set_option: unknown option '%s'", key);

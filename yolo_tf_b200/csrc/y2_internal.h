@@ -233,6 +233,7 @@ int bn_bwd_pool_launch(const float* z, const float* gp, long long ldgp, int B, i
                        bf16* dx_lo, double* partial, float* gy_out, cudaStream_t s, int f16 = 0);
 int maxpool_s1_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, const bf16* y_lo, float* g, int B, int H, int W, int C,
                           cudaStream_t s, int f16 = 0);
+int repitch_planes_launch(const bf16* src_hi, const bf16* src_lo, bf16* dst_hi, bf16* dst_lo, size_t rows, int C, int Cpad, cudaStream_t s);
 int compact_hwio_launch(const float* src, float* dst, int taps, int cin_s, int cout_s, int cin, int cout, cudaStream_t s);
 int reorg_bwd_add_launch(const float* gr, long long ldr, float* g, int B, int H, int W, int C, cudaStream_t s);
 int pack_dgrad_weights_launch(const float* w_hwio, bf16* out, int ksize, int cin, int cout, int cin_pad, int cout_pad,

@@ -531,6 +531,26 @@ int maxpool_s1_bwd_launch(const float* gp, long long ldgp, const bf16* y_hi, con
     return 0;
 }
 
+// planes [rows][C] -> planes [rows][Cpad] with zero-filled columns (the weight-gradient GEMM reads its gradient operand in
+// whole 64-channel atoms; tiny's 32-channel conv1 is the one layer whose dx planes are narrower)
+__global__ void repitch_planes_kernel(const bf16* __restrict__ src_hi, const bf16* __restrict__ src_lo, bf16* __restrict__ dst_hi,
+                                      bf16* __restrict__ dst_lo, size_t rows, int C, int Cpad) {
+    const size_t total = rows * (size_t)Cpad;
+    const bf16 zero = __float2bfloat16_rn(0.f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / Cpad;
+        const int c = (int)(i - r * Cpad);
+        dst_hi[i] = c < C ? src_hi[r * C + c] : zero;
+        dst_lo[i] = c < C ? src_lo[r * C + c] : zero;
+    }
+}
+int repitch_planes_launch(const bf16* src_hi, const bf16* src_lo, bf16* dst_hi, bf16* dst_lo, size_t rows, int C, int Cpad, cudaStream_t s) {
+    repitch_planes_kernel<<<ew_grid(rows * (size_t)Cpad), 256, 0, s>>>(src_hi, src_lo, dst_hi, dst_lo, rows, C, Cpad);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
 // gradient of a variable whose STORED shape is padded (tiny: conv0's 16 outputs / conv1's 16 inputs live in 32 channels):
 // [taps][cin_s][cout_s] -> the variable's own [taps][cin][cout]
 __global__ void compact_hwio_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int cin_s, int cout_s, int cin, int cout) {

@@ -68,6 +68,9 @@ def tiny_layer_geometry(classes, num_anchors):
 class _Engine(object):
     """One y2_handle per (device, classes, anchors, network); re-uploads weights when the store changes."""
     _cache = {}
+    # Diagnostics / tests: give every layer's output its own workspace slot so that `activation()` can read it after the forward.
+    # Off (the default), the outputs alternate between two arenas (2.4x less workspace).
+    KEEP_ACTIVATIONS = False
 
     def __init__(self, device_index, classes, num_anchors, arch=ARCH_DARKNET):
         import ctypes
@@ -91,7 +94,11 @@ class _Engine(object):
         key = (device.index or 0, classes, num_anchors, arch)
         if key not in cls._cache:
             cls._cache[key] = cls(key[0], classes, num_anchors, arch)
-        return cls._cache[key]
+        eng = cls._cache[key]
+        if getattr(eng, "_keep", None) != bool(cls.KEEP_ACTIVATIONS):
+            _lib.check(_lib.lib().y2_set_option(eng.h, b"keep_activations", int(bool(cls.KEEP_ACTIVATIONS))))
+            eng._keep = bool(cls.KEEP_ACTIVATIONS)
+        return eng
 
     def sync_weights(self, scope, store, device, center=True, weights_initializer=V.xavier_uniform):
         if self.loaded_store is store and self.loaded_version == store.version and self.loaded_key == (scope, bool(center)):
