@@ -50,6 +50,23 @@ def test_standardization_batched_matches_per_image(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 37, 29, 3), (2, 416, 416, 3), (4, 20, 12, 3)])
+def test_standardization_uint8_paths_agree_with_the_oracle(cuda, shape):
+    """uint8 images take a one-pass path (exact integer sums, 16 pixels per load) when an image is a multiple of 16 bytes, the
+    generic two-pass path otherwise; both against the numpy restatement, and against each other through a float32 copy."""
+    import torch
+    from yolo_tf_b200.utils.preprocess import per_image_standardization
+    rs = np.random.RandomState(sum(shape))
+    batch = rs.randint(0, 256, size=shape).astype(np.uint8)
+    got = per_image_standardization(torch.from_numpy(batch).to(cuda)).cpu().numpy()
+    via_f32 = per_image_standardization(torch.from_numpy(batch.astype(np.float32)).to(cuda)).cpu().numpy()
+    for b in range(shape[0]):
+        ref = np.asarray(per_image_standardization_oracle(batch[b].astype(np.float32)), dtype=np.float64)
+        assert np.abs(got[b] - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1.0), b
+        assert np.abs(got[b] - via_f32[b]).max() <= 1e-5 * max(np.abs(ref).max(), 1.0), b
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,c", [(845, 80), (1805, 20), (7, 3)])
 def test_detections_gpu_vs_oracle(cuda, n, c):
     import torch

@@ -28,6 +28,7 @@ def main():
     x = np.random.RandomState(2).normal(0, 1, size=(batch, size, size, 3)).astype(np.float32)
     taps = {}
     ref = darknet_oracle(x[:nref], params, classes, 5, taps=taps, dtype=torch.float64)
+    inference._Engine.KEEP_ACTIVATIONS = True          # one workspace slot per layer: every tap stays readable after the forward
     eng = inference._Engine.get(torch.device("cuda:0"), classes, 5)
     xd = torch.from_numpy(x).cuda()
     L = _lib.lib()

@@ -66,6 +66,93 @@ std_apply_kernel(const T* __restrict__ x, size_t n, const float* __restrict__ me
         dst[i] = __fdiv_rn(ld_as_float<T>(src, i) - mu, d);
 }
 
+// ---- uint8 fast path (what detect.py:59-65 produces): sum and sum of squares of bytes are EXACT integers, so one pass gives
+// the mean and the population variance (var = S2/n - mean^2 in float64: 53 bits hold both terms exactly) -- no second pass over
+// the image; 16 pixels per 128-bit load.  partial[b][chunk] = {S1, S2} as doubles (exact below 2^53).
+__global__ void __launch_bounds__(256)
+std_u8_sums_kernel(const unsigned char* __restrict__ x, size_t n, double* __restrict__ partial) {
+    const int b = blockIdx.y, chunks = gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * STD_CHUNK, hi = lo + STD_CHUNK < n ? lo + STD_CHUNK : n;
+    const unsigned char* src = x + (size_t)b * n;
+    unsigned int s1 = 0, s2 = 0;                             // <= 64 bytes per thread: 64 * 255^2 < 2^32
+    if ((((size_t)b * n) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        for (size_t i = lo + (size_t)threadIdx.x * 16; i + 16 <= hi; i += 256 * 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const unsigned int p = (w[k] >> (8 * j)) & 0xffu; s1 += p; s2 += p * p; }
+            }
+        }
+        const size_t tail = lo + ((hi - lo) / 16) * 16;      // STD_CHUNK % 16 == 0: only the image's last chunk has one
+        for (size_t i = tail + threadIdx.x; i < hi; i += 256) { const unsigned int p = __ldg(src + i); s1 += p; s2 += p * p; }
+    } else {
+        for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const unsigned int p = __ldg(src + i); s1 += p; s2 += p * p; }
+    }
+    __shared__ unsigned long long sm1[256], sm2[256];
+    sm1[threadIdx.x] = s1; sm2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sm1[threadIdx.x] += sm1[threadIdx.x + o]; sm2[threadIdx.x] += sm2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[((size_t)b * chunks + blockIdx.x) * 2 + 0] = (double)sm1[0];
+        partial[((size_t)b * chunks + blockIdx.x) * 2 + 1] = (double)sm2[0];
+    }
+}
+__global__ void std_u8_finish_kernel(const double* __restrict__ partial, int chunks, int B, double n, float* __restrict__ mean,
+                                     float* __restrict__ denom) {
+    const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = lane; c < chunks; c += 32) { s1 += partial[((size_t)b * chunks + c) * 2]; s2 += partial[((size_t)b * chunks + c) * 2 + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) {
+        const double mu = s1 / n;
+        double var = s2 / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean[b] = (float)mu;
+        denom[b] = fmaxf((float)sqrt(var), (float)(1.0 / sqrt(n)));
+    }
+}
+__global__ void __launch_bounds__(256)
+std_u8_apply_kernel(const unsigned char* __restrict__ x, size_t n, const float* __restrict__ mean, const float* __restrict__ denom,
+                    float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float mu = mean[b], d = denom[b];
+    const unsigned char* src = x + (size_t)b * n;
+    float* dst = out + (size_t)b * n;
+    const size_t n16 = n / 16;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 o;
+            o.x = __fdiv_rn((float)(w[k] & 0xffu) - mu, d);
+            o.y = __fdiv_rn((float)((w[k] >> 8) & 0xffu) - mu, d);
+            o.z = __fdiv_rn((float)((w[k] >> 16) & 0xffu) - mu, d);
+            o.w = __fdiv_rn((float)(w[k] >> 24) - mu, d);
+            reinterpret_cast<float4*>(dst)[i * 4 + k] = o;
+        }
+    }
+}
+static int standardize_run_u8(const unsigned char* x, int B, size_t n, float* out, double* partial, float* mean, float* denom, cudaStream_t s) {
+    const int chunks = (int)((n + STD_CHUNK - 1) / STD_CHUNK);
+    std_u8_sums_kernel<<<dim3(chunks, B), 256, 0, s>>>(x, n, partial);
+    std_u8_finish_kernel<<<(B + 7) / 8, 256, 0, s>>>(partial, chunks, B, (double)n, mean, denom);
+    int ab = (int)((n / 16 + 255) / 256);
+    if (ab > 148 * 2) ab = 148 * 2;
+    if (ab < 1) ab = 1;
+    std_u8_apply_kernel<<<dim3(ab, B), 256, 0, s>>>(x, n, mean, denom, out);
+    Y2_CUDA(cudaGetLastError());
+    for (int i = 0; i < 3; ++i) note_launch();
+    return 0;
+}
+
 template <typename T>
 static int standardize_run(const T* x, int B, size_t n, float* out, double* partial, float* mean, float* denom, cudaStream_t s) {
     const int chunks = (int)((n + STD_CHUNK - 1) / STD_CHUNK);
@@ -83,14 +170,17 @@ static int standardize_run(const T* x, int B, size_t n, float* out, double* part
 }
 size_t standardize_workspace_bytes(int B, size_t n) {
     const size_t chunks = (n + STD_CHUNK - 1) / STD_CHUNK;
-    return ((size_t)B * chunks * sizeof(double) + 255) / 256 * 256 + 2 * (((size_t)B * sizeof(float) + 255) / 256 * 256);
+    return ((size_t)B * chunks * 2 * sizeof(double) + 255) / 256 * 256 + 2 * (((size_t)B * sizeof(float) + 255) / 256 * 256);
 }
 int standardize_launch(const void* x, int elem_bytes, int B, size_t n, float* out, void* ws, cudaStream_t s) {
     const size_t chunks = (n + STD_CHUNK - 1) / STD_CHUNK;
     char* p = static_cast<char*>(ws);
-    double* partial = reinterpret_cast<double*>(p); p += ((size_t)B * chunks * sizeof(double) + 255) / 256 * 256;
+    double* partial = reinterpret_cast<double*>(p); p += ((size_t)B * chunks * 2 * sizeof(double) + 255) / 256 * 256;
     float* mean = reinterpret_cast<float*>(p); p += ((size_t)B * sizeof(float) + 255) / 256 * 256;
     float* denom = reinterpret_cast<float*>(p);
+    // uint8 with 16-byte aligned images: exact integer sums in one pass + vectorised apply; otherwise the generic two-pass path
+    if (elem_bytes == 1 && n % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        return standardize_run_u8(static_cast<const unsigned char*>(x), B, n, out, partial, mean, denom, s);
     if (elem_bytes == 1) return standardize_run(static_cast<const unsigned char*>(x), B, n, out, partial, mean, denom, s);
     return standardize_run(static_cast<const float*>(x), B, n, out, partial, mean, denom, s);
 }
