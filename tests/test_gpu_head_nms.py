@@ -210,6 +210,22 @@ def test_nms_vs_c_oracle(cuda, B, hc, wc, C, K, quant):
     assert np.array_equal(order, ref_order)
 
 
+def test_nms_many_images_takes_the_per_warp_path_for_heavy_classes(cuda):
+    """With few CTAs in flight (every test above) a class with more than 64 candidates is handled by the whole CTA; a batch of
+    hundreds of images (BASELINE configs[4]) keeps one warp per class.  B = 128, ~125 candidates per class with ties: both paths
+    must give the bits of the C oracle."""
+    rs = np.random.RandomState(23)
+    conf, lo, hi = _sweep_inputs(rs, 128, 13, 13, 80, 10000, 64)
+    got, _, status = _run_nms(cuda, conf, lo, hi, 0.3, 0.4, want_order=False)
+    assert not status.any()
+    for sl in (slice(0, 2), slice(126, 128)):
+        ref = conf[sl].copy()
+        nms_c_batch(ref, lo[sl], hi[sl], 0.3, 0.4)
+        assert np.array_equal(got[sl].view(np.uint32), ref.view(np.uint32))
+    small, _, _ = _run_nms(cuda, conf[:3], lo[:3], hi[:3], 0.3, 0.4, want_order=False)       # 9 CTAs: the cooperative path
+    assert np.array_equal(small.view(np.uint32), got[:3].view(np.uint32))
+
+
 def test_nms_python_oracle_small(cuda):
     rs = np.random.RandomState(5)
     conf, lo, hi = _sweep_inputs(rs, 1, 5, 5, 4, 60, 8)

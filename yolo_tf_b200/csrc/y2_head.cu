@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             const long long gi = g0 + g;
             const int* meta = reinterpret_cast<const int*>(s_box + g * 24 + 20);
             const int an = meta[2];
-            // softmax over classes (max-subtracted, as tf.nn.softmax); up to 4 classes per lane stay in registers
+            // softmax over classes (max-subtracted, as tf.nn.softmax); up to 4 classes per lane stay in registers.
+            // Exponentials and quotients use the hardware approximations (ex2.approx / rcp.approx: a few ulp, 1e-6 relative on
+            // every value that matters -- the parity bar is 1e-4): the libm versions made this kernel instruction-bound
+            // (444 warp instructions per box, profiles/ncu_r2c_hbm_kernels.txt); padded lanes carry -inf -> exp = 0, no branches.
             float mx = -INFINITY;
             float ev[4];
 #pragma unroll
@@ -90,15 +93,19 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             float se = 0.f;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                ev[t] = (lane + 32 * t < a.C) ? expf(ev[t] - mx) : 0.f;
+                ev[t] = __expf(ev[t] - mx);
                 se += ev[t];
             }
-            for (int c = lane + 128; c < a.C; c += 32) se += expf(in[5 + c] - mx);
+            for (int c = lane + 128; c < a.C; c += 32) se += __expf(in[5 + c] - mx);
             se = warp_sum(se);
+            const float rse = __fdividef(1.0f, se);
             // the five box logits in parallel: lanes 0..2 sigmoid (iou, x, y), lanes 3..4 exp * anchor (w, h)
             float bv = 0.f;
-            if (lane < 3) bv = sigmoidf_(in[lane]);
-            else if (lane < 5) bv = expf(in[lane]) * __ldg(a.anchors + 2 * an + (lane - 3));
+            {
+                const float t5 = in[lane < 5 ? lane : 0];
+                const float e5 = __expf(lane < 3 ? -t5 : t5);
+                bv = lane < 3 ? __fdividef(1.0f, 1.0f + e5) : e5 * __ldg(a.anchors + 2 * an + (lane == 4 ? 1 : 0));
+            }
             const float iou = __shfl_sync(0xffffffffu, bv, 0);
             const float sx = __shfl_sync(0xffffffffu, bv, 1), sy = __shfl_sync(0xffffffffu, bv, 2);
             const float w = __shfl_sync(0xffffffffu, bv, 3), h = __shfl_sync(0xffffffffu, bv, 4);
@@ -106,13 +113,13 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             for (int t = 0; t < 4; ++t) {
                 const int c = lane + 32 * t;
                 if (c < a.C) {
-                    const float pr = ev[t] / se;
+                    const float pr = ev[t] * rse;
                     s_conf[g * a.C + c] = iou * pr;
                     if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
                 }
             }
             for (int c = lane + 128; c < a.C; c += 32) {
-                const float pr = expf(in[5 + c] - mx) / se;
+                const float pr = __expf(in[5 + c] - mx) * rse;
                 s_conf[g * a.C + c] = iou * pr;
                 if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
             }

@@ -155,6 +155,162 @@ __device__ void select_class_general(const NmsArgs& a, int b, int c, uint32_t* a
     __syncwarp();
 }
 
+// Greedy sweep over K <= 32 * NW candidates staged in visiting order (box[], shared memory).  The alive mask lives in
+// REGISTERS (lane w owns word w) and every lane keeps ITS candidates (jj = 32 * wd + lane) in registers; a live box r is
+// tested against all later candidates in one fully unrolled pass whose NW word-iterations are independent (the alive words are
+// read before any of them is updated), so the loads / IoU tests / ballots of different words overlap instead of forming one
+// dependent chain per word.  Returns the number of kept boxes (their indices in list[]) and the final alive mask.
+template <int NW>
+__device__ __forceinline__ int nms_sweep(const float4* __restrict__ box, const unsigned long long* __restrict__ key, uint16_t* __restrict__ list,
+                                         int K, float thr_iou, float thr_lo, bool quick, int lane, uint32_t& alive_out) {
+    uint32_t alive = 0u;
+    if (lane < NW && lane * 32 < K) alive = (lane * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - lane * 32)) - 1u);
+    float4 bj[NW];
+    float aj[NW];
+#pragma unroll
+    for (int wd = 0; wd < NW; ++wd) {
+        const int jj = wd * 32 + lane;
+        bj[wd] = jj < K ? box[jj] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aj[wd] = box_area(bj[wd]);
+    }
+    int kept = 0;
+#pragma unroll 1
+    for (int g = 0; g < NW; ++g) {
+        uint32_t m = __shfl_sync(0xffffffffu, alive, g);
+        while (m) {                                                   // warp-uniform
+            const int bit = __ffs(m) - 1;
+            const int r = g * 32 + bit;
+            const float4 bi = box[r];
+            const float ai = box_area(bi);
+            if (lane == 0) list[kept] = (uint16_t)(0xffff - (int)(key[r] & 0xffffu));   // kept <= r: slot already consumed
+            ++kept;
+            uint32_t km_mine = 0u;
+#pragma unroll
+            for (int wd = 0; wd < NW; ++wd) {
+                if (wd >= g) {                                        // warp-uniform
+                    const int jj = wd * 32 + lane;
+                    const uint32_t aw = __shfl_sync(0xffffffffu, alive, wd);
+                    const bool kill = jj > r && ((aw >> lane) & 1u) && iou_hit(bi, ai, bj[wd], aj[wd], thr_iou, thr_lo, quick);
+                    const uint32_t km = __ballot_sync(0xffffffffu, kill);
+                    if (lane == wd) km_mine = km;
+                }
+            }
+            alive &= ~km_mine;
+            m = __shfl_sync(0xffffffffu, alive, g) & (bit == 31 ? 0u : (0xffffffffu << (bit + 1)));
+        }
+    }
+    alive_out = alive;
+    return kept;
+}
+
+// One class with many candidates (COOP_MIN < K <= SEL_CAP) handled by the WHOLE CTA -- the latency-bound regime (few CTAs,
+// e.g. a batch of 32 images whose scores put 200 candidates into one class): a single warp's greedy sweep is a chain of
+// ~300 instructions per kept box, 160 kept boxes long.  Here thread t owns candidate t: cooperative bitonic sort
+// (one compare-exchange per thread and stage), and in the sweep warp w owns alive word w -- every kept box costs one 32-wide
+// IoU test per warp and one __syncthreads.  All threads of the CTA call this with the same arguments.
+// key / box / supp: the arrays of warp 0; alive_sm[8]; list: the class's candidate list, overwritten with the kept list.
+static constexpr int COOP_MIN = 64;
+__device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigned long long* key, float4* box, uint32_t* supp,
+                                  uint32_t* alive_sm, uint16_t* list, bool quick, float thr_lo) {
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const float* conf_img = a.conf + (size_t)b * a.N * a.C;
+    const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+    const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+    const int n2 = K <= 128 ? 128 : 256;
+    {
+        unsigned long long k = 0ull;                                  // padding sorts last (every real key is > 0)
+        if (t < K) {
+            const int idx = list[t];
+            k = ((unsigned long long)ford(__ldg(conf_img + (size_t)idx * a.C + c)) << 32) | (unsigned long long)(0xffffu - idx);
+        }
+        if (t < n2) key[t] = k;
+    }
+    for (int w = t; w < a.W; w += NMS_WARPS * 32) supp[w] = 0u;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (t < (n2 >> 1)) {
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = key[lo], y = key[hi];
+                if ((x < y) == desc) { key[lo] = y; key[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (c > 0) {                                                      // ties descend into earlier class columns
+        bool tie = false;
+        unsigned long long kp = 0ull;
+        if (t < K) {
+            kp = key[t];
+            const uint32_t v = (uint32_t)(kp >> 32);
+            tie = (t > 0 && (uint32_t)(key[t - 1] >> 32) == v) || (t + 1 < K && (uint32_t)(key[t + 1] >> 32) == v);
+        }
+        if (__syncthreads_or(tie ? 1 : 0)) {
+            unsigned long long* tmp = reinterpret_cast<unsigned long long*>(box);
+            if (t < K) {
+                int rank = t;
+                if (tie) {
+                    const uint32_t v = (uint32_t)(kp >> 32);
+                    int s0 = t, e0 = t + 1;
+                    while (s0 > 0 && (uint32_t)(key[s0 - 1] >> 32) == v) --s0;
+                    while (e0 < K && (uint32_t)(key[e0] >> 32) == v) ++e0;
+                    rank = s0;
+                    const int j = 0xffff - (int)(kp & 0xffffu);
+                    for (int qq = s0; qq < e0; ++qq) {
+                        if (qq == t) continue;
+                        const int i = 0xffff - (int)(key[qq] & 0xffffu);
+                        if (precedes(conf_img, a.C, c, i, 0.f, j, 0.f)) ++rank;
+                    }
+                }
+                tmp[rank] = kp;
+            }
+            __syncthreads();
+            if (t < K) key[t] = tmp[t];
+            __syncthreads();
+        }
+    }
+    float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < K) { bj = load_box(bmin, bmax, 0xffff - (int)(key[t] & 0xffffu)); box[t] = bj; }
+    const float aj = box_area(bj);
+    const int words = (K + 31) / 32;
+    uint32_t alive_w = 0u;                                            // warp w owns word w (uniform across its lanes)
+    if (warp < words) alive_w = (warp * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - warp * 32)) - 1u);
+    if (lane == 0 && warp < words) alive_sm[warp] = alive_w;
+    __syncthreads();
+    int kept = 0, g = 0, prev = -1;
+    while (g < words) {                                               // CTA-uniform control flow throughout
+        // a reader that sees warp g's update of this step still finds the same lowest bit: only bits above r are cleared
+        const uint32_t m = alive_sm[g] & (prev >= 31 ? 0u : (0xffffffffu << (prev + 1)));
+        if (m == 0u) { ++g; prev = -1; continue; }
+        const int bit = __ffs(m) - 1;
+        const int r = g * 32 + bit;
+        prev = bit;
+        const float4 bi = box[r];
+        if (t == 0) list[kept] = (uint16_t)(0xffff - (int)(key[r] & 0xffffu));      // kept <= r: slot already consumed
+        ++kept;
+        if (warp >= g && warp < words) {
+            const bool kill = t > r && ((alive_w >> lane) & 1u) && iou_hit(bi, box_area(bi), bj, aj, a.thr_iou, thr_lo, quick);
+            const uint32_t km = __ballot_sync(0xffffffffu, kill);
+            alive_w &= ~km;
+            if (lane == 0 && km) alive_sm[warp] = alive_w;
+        }
+        __syncthreads();
+    }
+    if (t < K && !((alive_w >> lane) & 1u)) {                         // suppressed candidates = cleared alive bits
+        const int j = 0xffff - (int)(key[t] & 0xffffu);
+        atomicOr(&supp[j >> 5], 1u << (j & 31));
+    }
+    __syncthreads();
+    uint16_t* kept_out = a.cand + ((size_t)b * a.C + c) * a.N;
+    if (t < kept) kept_out[t] = list[t];
+    uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
+    for (int w = t; w < a.W; w += NMS_WARPS * 32) supp_out[w] = supp[w];
+    if (t == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+    __syncthreads();
+}
+
 // dynamic shared memory of nms_select_kernel: per warp {key[SEL_CAP] u64, box[SEL_CAP] float4, supp[Wp] u32, alive[Wp] u32},
 // then list[32][SEL_CAP] u16 and cnt[33]; Wp = W rounded up to a multiple of 4
 //   key  : (ford(value) << 32) | (0xffff - index): descending key = visiting order up to ties
@@ -188,15 +344,25 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     if (vec4) {                                          // C % 4 == 0, 16-byte aligned rows: lane = (box, 4 classes)
         const int q = lane & 7, cl = 4 * q;
         if (c0 + cl < a.C) {
-            for (int n = warp * 4 + (lane >> 3); n < a.N; n += NMS_WARPS * 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + cl));
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+            // four rows of loads in flight per lane (the shared-memory atomics below would otherwise serialise the loads)
+            for (int n0 = warp * 4 + (lane >> 3); n0 < a.N; n0 += NMS_WARPS * 4 * 4) {
+                float4 v[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (vv[t] > a.thr) {
-                        const int slot = atomicAdd(&s_cnt[cl + t], 1);
-                        if (slot < SEL_CAP) s_list[cl + t][slot] = (uint16_t)n;
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u * NMS_WARPS * 4;
+                    v[u] = n < a.N ? __ldg(reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + cl)) : make_float4(a.thr, a.thr, a.thr, a.thr);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u * NMS_WARPS * 4;
+                    const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (vv[t] > a.thr) {                      // rows past N carry thr itself: never a candidate
+                            const int slot = atomicAdd(&s_cnt[cl + t], 1);
+                            if (slot < SEL_CAP) s_list[cl + t][slot] = (uint16_t)n;
+                        }
+                }
             }
         }
     } else if (c0 + lane < a.C) {                        // lane = class, a warp reads 32 consecutive classes of one box
@@ -224,6 +390,9 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     }
     const bool quick = a.thr_iou > 0.0f;
     const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
+    // Few CTAs in flight (a detection batch, not a sweep over hundreds of images): the machine is idle anyway and the kernel's
+    // time is its longest class -- classes with more than COOP_MIN candidates then get the whole CTA (select_class_coop).
+    const bool coop = (int)(gridDim.x * gridDim.y) <= 2 * 148;
     // one warp per class from here on; classes are handed out dynamically (the candidate counts of real score matrices
     // are very uneven: a few classes hold most of an image's candidates)
     for (;;) {
@@ -242,6 +411,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
             select_class_general(a, b, c, w_alive, w_supp, lane);
             continue;
         }
+        if (coop && K > COOP_MIN) continue;                           // phase B below
         // 2. keys -> shared memory, bitonic sort (descending), exact re-ranking of equal-value runs
         uint16_t* list = s_list[cl];
         int n2 = 32;
@@ -300,38 +470,15 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
                 __syncwarp();
             }
         }
-        // 3. boxes in visiting order, greedy sweep out of shared memory.  The alive mask lives in REGISTERS (lane w holds
-        //    word w: K <= 256 = 8 words); a live box r tests the later candidates 32 at a time, the owner lane of each word
-        //    clears the hits -- no shared-memory traffic, atomics or barriers inside the loop.
+        // 3. boxes in visiting order, greedy sweep (nms_sweep: alive mask and every lane's candidates in registers)
         for (int p = lane; p < K; p += 32) w_box[p] = load_box(bmin, bmax, 0xffff - (int)(w_key[p] & 0xffffu));
         __syncwarp();
-        const int words = (K + 31) / 32;
         uint32_t alive = 0u;
-        if (lane < words) alive = (lane * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - lane * 32)) - 1u);
-        int kept = 0;
-        for (int g = 0; g < words; ++g) {
-            uint32_t m = __shfl_sync(0xffffffffu, alive, g);
-            while (m) {                                               // warp-uniform
-                const int bit = __ffs(m) - 1;
-                const int r = g * 32 + bit;
-                const float4 bi = w_box[r];
-                const float ai = box_area(bi);
-                if (lane == 0) list[kept] = (uint16_t)(0xffff - (int)(w_key[r] & 0xffffu));   // kept <= r: slot already consumed
-                ++kept;
-                for (int wd = g; wd < words; ++wd) {
-                    const int jj = wd * 32 + lane;
-                    const uint32_t aw = __shfl_sync(0xffffffffu, alive, wd);
-                    bool kill = false;
-                    if (jj > r && jj < K && ((aw >> lane) & 1u)) {
-                        const float4 bj = w_box[jj];
-                        kill = iou_hit(bi, ai, bj, box_area(bj), a.thr_iou, thr_lo, quick);
-                    }
-                    const uint32_t km = __ballot_sync(0xffffffffu, kill);
-                    if (lane == wd) alive &= ~km;
-                }
-                m = __shfl_sync(0xffffffffu, alive, g) & (bit == 31 ? 0u : (0xffffffffu << (bit + 1)));
-            }
-        }
+        int kept;
+        if (K <= 32) kept = nms_sweep<1>(w_box, w_key, list, K, a.thr_iou, thr_lo, quick, lane, alive);
+        else if (K <= 64) kept = nms_sweep<2>(w_box, w_key, list, K, a.thr_iou, thr_lo, quick, lane, alive);
+        else if (K <= 128) kept = nms_sweep<4>(w_box, w_key, list, K, a.thr_iou, thr_lo, quick, lane, alive);
+        else kept = nms_sweep<8>(w_box, w_key, list, K, a.thr_iou, thr_lo, quick, lane, alive);
         // suppressed candidates = the ones whose alive bit was cleared
         for (int p0 = 0; p0 < K; p0 += 32) {
             const uint32_t aw = __shfl_sync(0xffffffffu, alive, p0 >> 5);
@@ -349,6 +496,19 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
         if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
         __syncwarp();
     }   // class loop
+    if (coop) {                                                       // phase B: the heavy classes, one at a time, all 8 warps
+        __syncthreads();
+        unsigned long long* key0 = reinterpret_cast<unsigned long long*>(sel_smem);
+        float4* box0 = reinterpret_cast<float4*>(sel_smem + SEL_CAP * 8);
+        uint32_t* supp0 = reinterpret_cast<uint32_t*>(sel_smem + SEL_CAP * 24);
+        uint32_t* alive0 = supp0 + Wp;                                // warp 0's alive words: Wp >= 8 whenever N >= 225
+        for (int cl = 0; cl < 32; ++cl) {
+            const int c = c0 + cl;
+            if (c >= a.C) break;
+            const int K = s_cnt[cl];
+            if (K > COOP_MIN && K <= SEL_CAP) select_class_coop(a, b, c, K, key0, box0, supp0, alive0, s_list[cl], quick, thr_lo);
+        }
+    }
 }
 
 // Final permutation: rank sort of all N boxes under the class-(C-1) visiting order. One CTA per image.
