@@ -193,8 +193,10 @@ def _sweep_inputs(rs, B, hc, wc, C, K, quant=None):
 
 @pytest.mark.parametrize("B,hc,wc,C,K,quant", [(4, 13, 13, 80, 1000, None), (2, 19, 19, 80, 3000, None),
                                                (3, 13, 13, 20, 600, 32), (2, 13, 13, 80, 10000, 16), (2, 7, 7, 3, 400, 4),
-                                               # > 256 candidates per class: the general (global-memory) select path, with ties
+                                               # 256 < candidates per class <= 1024: the whole-CTA select path with its own column scan, with ties
                                                (2, 13, 13, 4, 2500, 8),
+                                               # > 1024 candidates per class: the general (global-memory) select path, with ties
+                                               (1, 19, 19, 2, 3000, 8),
                                                # C % 4 != 0: scalar loads
                                                (2, 9, 9, 6, 700, None),
                                                # ~250 candidates per class with heavy ties: both select paths in one launch

@@ -148,6 +148,7 @@ struct Plan {
     void* streamk = nullptr;
     std::vector<TcConvLaunch> launch;   // per layer (index 0 unused)
     std::vector<char> fused;            // per layer: max-pool fused into the conv epilogue
+    bool reorg_fused = false;           // the passthrough layer's epilogue writes the concat buffer in reorg order itself
 };
 
 }  // namespace y2
@@ -452,6 +453,15 @@ static int build_plan(y2_handle* h, int B, int H, int W, void* ws, size_t ws_byt
             p.out_hi = P.act[i];
             p.out_lo = P.act[i] + M * L.d.cout_s;
             if (fuse && !L.d.passthrough) p.out_hi = p.out_lo = nullptr;   // the un-pooled tensor is never materialised
+            // passthrough layer with its pool fused (spatial tiles): the epilogue writes the un-pooled output straight into the
+            // concat buffer in reorg order -- the separate reorg pass (29 us at B = 32) and the act slot are not needed.  Tests
+            // that read conv12's activation back (keep_activations) keep the separate pass.
+            if (fuse && L.d.passthrough && !h->keep_activations && p.tx != 0 && cat_c) {
+                p.reorg = 1; p.ldc = cat_c;
+                p.out_hi = P.concat;
+                p.out_lo = P.concat + (M / 4) * cat_c;
+                P.reorg_fused = true;
+            }
         }
         if (tc_conv_bind_output(&T)) return -1;
         input = L.d.pool ? P.pooled[i] : P.act[i];
@@ -493,7 +503,7 @@ int y2_darknet_forward(y2_handle* h, const float* x, int B, int H, int W, float*
         if (h->profiling) Y2_CUDA(cudaEventRecord(h->ev[4 * i + 1], s));
         const int oh = P.oh[i], ow = P.ow[i];
         const size_t M = (size_t)B * oh * ow;
-        if (L.d.passthrough) {
+        if (L.d.passthrough && !P.reorg_fused) {
             // reorg(passthrough) -> concat channels [0, 2048); both planes in one launch (batch 2B)
             if (reorg_launch(P.act[i], P.concat, 2 * B, oh, ow, L.d.cout_s, 2, 2, h->cat_c, s)) return -1;
         }
@@ -657,6 +667,7 @@ int y2_debug_set(int key, double value) {
     else if (key == 1) g_sched_handoff_kb = value;
     else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
     else if (key == 4) g_conv_force_halo = (int)value;
+    else if (key == 11) g_nms_apply_mode = (int)value;      // nms_apply_kernel work items: 0 by regime, 1 dynamic chunks, 2 one per class column
     else if (key == 9) g_conv_fmt = (int)value;             // FMT_* bits of the convs planned from now on (y2_conv2d sets them itself)
     else if (key == 10) g_wgrad_fmt = (int)value;           // FMT_* bits of y2_conv2d_wgrad: 3 = x planes in fp16
     else if (key == 8) g_conv_kcap = (int)value;            // longest tensor-core accumulation chain in k-blocks (0 = unlimited; default 32)

@@ -414,6 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int n0 = nt * p.block_n;
             long long row = (long long)mt * BLOCK_M + q * 32 + lane;
             size_t pool_row = 0;
+            int reorg_sub = 0;                               // position of this pixel inside its 2x2 block: dy * 2 + dx
             if (p.tx) {                                      // spatial tile: row r = (image bb, yy, xx) inside the block
                 const int r = q * 32 + lane;
                 const int xt = mt % p.tiles_x, r2 = mt / p.tiles_x;
@@ -421,6 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int px = xt * p.tx + xx, py = (r2 % p.tiles_y) * p.ty + yy, pb = (r2 / p.tiles_y) * p.tb + bb;
                 row = ((long long)pb * p.H + py) * p.W + px;
                 pool_row = ((size_t)pb * (p.H / 2) + py / 2) * (p.W / 2) + px / 2;
+                reorg_sub = (py & 1) * 2 + (px & 1);
             }
             const bool row_ok = row < p.M && mt < p.m_tiles128;      // (pair: the odd last 128-row tile has no partner rows)
             const bool first_sub = (kb0 == seg_a), last_sub = (kb1 == seg_b);   // position in this CTA's accumulation chain
@@ -612,7 +614,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                             ++store_seq;
                         } else {
-                        const size_t off = (size_t)row * p.ldc + n0 + c;
+                        // p.reorg (passthrough layer, spatial tiles): the un-pooled output goes straight to its space-to-depth place in
+                        // the concat buffer, out[b, y/2, x/2, (dy*2+dx)*N + n] (model/yolo2/function.py:22-29) -- no reorg pass
+                        const size_t off = p.reorg ? pool_row * (size_t)p.ldc + (size_t)reorg_sub * p.N + n0 + c : (size_t)row * p.ldc + n0 + c;
                         uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
                         uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll

@@ -110,9 +110,11 @@ struct ConvParams {
     // CTA-pair mode (cta_group::2): m_tiles counts 256-row pair tiles, m_tiles128 the 128-row tiles that exist
     int pair, m_tiles128;
     int kcap;                // longest accumulation chain in k-blocks (0 = unlimited), see CapIter
+    int reorg;               // spatial tiles only: write the un-pooled output in space-to-depth(2) order (ldc = pitch of that buffer)
     int fmt;                 // FMT_* bits (y2_ptx.cuh): element format of the A (activation) and B (weight) hi / lo planes; 0 = all bf16
 };
 extern int g_conv_tma_store;   // 1 = TMA-store epilogue where the layout allows it
+extern int g_nms_apply_mode;           // diagnostics (y2_debug_set key 11): work-item scheme of nms_apply_kernel
 extern int g_conv_fmt, g_wgrad_fmt;   // FMT_* bits of the GEMMs planned from now on (diagnostic entry points; the network sets them per launch)
 extern int g_conv_kcap;        // ConvParams::kcap of the convs planned from now on (default 32)
 extern int g_conv_force_pair;  // y2_conv2d: run eligible convs as CTA pairs (diagnostics / tests)

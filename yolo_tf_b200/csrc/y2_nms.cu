@@ -22,15 +22,16 @@
 //            and a bitmask of the SUPPRESSED candidates per (image, class).  Classes with more than SEL_CAP candidates
 //            take the general path (lists in global memory, rank sort).
 //   order  : (optional) final permutation of the N boxes = the order of the list the reference returns.
-//   apply  : a CTA owns a [128 boxes][32 classes] tile (coalesced 128-bit loads through shared memory); warps walk
-//            class columns with lanes = boxes (4 per lane), the class's kept boxes broadcast from shared memory.  A
-//            candidate is zeroed iff its bit in the suppressed mask is set; a non-candidate (it sorts after every
-//            candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
+//   apply  : a CTA owns a [128 boxes][32 classes] tile (coalesced 128-bit loads through shared memory); lanes = boxes
+//            (4 per lane), work items = (class column, chunk of 32 kept boxes) handed out to the warps dynamically, the
+//            chunk's boxes broadcast from shared memory.  A candidate is zeroed iff its bit in the suppressed mask is set;
+//            a non-candidate (it sorts after every candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
 // Scores are read once by select and once by apply, both coalesced; only tiles that change are written back.
 #include "y2_internal.h"
 
 namespace y2 {
 
+int g_nms_apply_mode = 0;
 static constexpr int NMS_WARPS = 8;
 static constexpr int NMS_MAX_N = 8192;     // bitmasks: 256 words per warp
 static constexpr int SEL_CAP = 256;        // candidates per class handled out of shared memory
@@ -93,6 +94,7 @@ struct NmsArgs {
     int* kept_cnt;       // [B][C]
     int* status;         // [B] nullable: 1 = a reference assert (NaN / xy_min > xy_max) would fire
     int* order_out;      // [B][N] nullable
+    int apply_mode;      // diagnostics: 0 = choose by regime, 1 = chunk items handed out dynamically, 2 = one item per class column
 };
 
 // General path for one (image, class), one warp: any number of candidates, lists in global memory, rank sort.
@@ -203,34 +205,63 @@ __device__ __forceinline__ int nms_sweep(const float4* __restrict__ box, const u
     return kept;
 }
 
-// One class with many candidates (COOP_MIN < K <= SEL_CAP) handled by the WHOLE CTA -- the latency-bound regime (few CTAs,
-// e.g. a batch of 32 images whose scores put 200 candidates into one class): a single warp's greedy sweep is a chain of
-// ~300 instructions per kept box, 160 kept boxes long.  Here thread t owns candidate t: cooperative bitonic sort
-// (one compare-exchange per thread and stage), and in the sweep warp w owns alive word w -- every kept box costs one 32-wide
-// IoU test per warp and one __syncthreads.  All threads of the CTA call this with the same arguments.
-// key / box / supp: the arrays of warp 0; alive_sm[8]; list: the class's candidate list, overwritten with the kept list.
-static constexpr int COOP_MIN = 64;
-__device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigned long long* key, float4* box, uint32_t* supp,
-                                  uint32_t* alive_sm, uint16_t* list, bool quick, float thr_lo) {
+// One class with many candidates (COOP_MIN < K <= COOP_CAP) handled by the WHOLE CTA -- the latency-bound regime (few CTAs,
+// e.g. a batch of 32 images whose scores put hundreds of candidates into one class): a single warp's greedy sweep is a chain
+// of ~300 instructions per kept box, 160 kept boxes long.  Here the 256 threads own up to 4 candidates each: cooperative
+// bitonic sort (compare-exchanges spread over the CTA, one __syncthreads per stage), and in the sweep warp w owns the alive
+// words w, w+8, w+16, w+24 -- every kept box costs at most four 32-wide IoU tests per warp and one __syncthreads.
+// All threads of the CTA call this with the same arguments.  pool: the per-warp areas of the select kernel, free in this phase.
+static constexpr int COOP_MIN = 64, COOP_CAP = 1024, COOP_R = COOP_CAP / (NMS_WARPS * 32);
+__host__ __device__ inline size_t coop_pool_bytes(int W) { return (size_t)COOP_CAP * (8 + 16 + 2) + (size_t)((W + 3) & ~3) * 4 + 32 * 4; }
+__device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigned char* pool, const uint16_t* cand_list, bool quick,
+                                  float thr_lo) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    constexpr int NT = NMS_WARPS * 32;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(pool);
+    float4* box = reinterpret_cast<float4*>(pool + COOP_CAP * 8);
+    uint16_t* list = reinterpret_cast<uint16_t*>(pool + COOP_CAP * 24);           // candidates, later the kept list
+    uint32_t* supp = reinterpret_cast<uint32_t*>(pool + COOP_CAP * 26);
+    uint32_t* alive_sm = supp + ((a.W + 3) & ~3);                                  // [32]
     const float* conf_img = a.conf + (size_t)b * a.N * a.C;
     const float* bmin = a.xy_min + (size_t)b * a.N * 2;
     const float* bmax = a.xy_max + (size_t)b * a.N * 2;
-    const int n2 = K <= 128 ? 128 : 256;
-    {
+    __shared__ int scan_sm[NMS_WARPS], scan_base;
+    if (cand_list) {                                                  // K <= SEL_CAP: the compaction pass recorded all of them
+        for (int p = t; p < K; p += NT) list[p] = cand_list[p];
+    } else {                                                          // more: re-scan the class column (index order, block scan)
+        if (t == 0) scan_base = 0;
+        __syncthreads();
+        for (int n0 = 0; n0 < a.N; n0 += NT) {
+            const int n = n0 + t;
+            const bool is = n < a.N && __ldg(conf_img + (size_t)n * a.C + c) > a.thr;
+            const uint32_t m = __ballot_sync(0xffffffffu, is);
+            if (lane == 0) scan_sm[warp] = __popc(m);
+            __syncthreads();
+            int pos = scan_base + __popc(m & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; ++w) pos += scan_sm[w];
+            if (is) list[pos] = (uint16_t)n;
+            __syncthreads();
+            if (t == 0) { int s = 0; for (int w = 0; w < NMS_WARPS; ++w) s += scan_sm[w]; scan_base += s; }
+            __syncthreads();
+        }
+    }
+    for (int w = t; w < a.W; w += NT) supp[w] = 0u;
+    __syncthreads();
+    int n2 = 128;
+    while (n2 < K) n2 <<= 1;
+    for (int p = t; p < n2; p += NT) {
         unsigned long long k = 0ull;                                  // padding sorts last (every real key is > 0)
-        if (t < K) {
-            const int idx = list[t];
+        if (p < K) {
+            const int idx = list[p];
             k = ((unsigned long long)ford(__ldg(conf_img + (size_t)idx * a.C + c)) << 32) | (unsigned long long)(0xffffu - idx);
         }
-        if (t < n2) key[t] = k;
+        key[p] = k;
     }
-    for (int w = t; w < a.W; w += NMS_WARPS * 32) supp[w] = 0u;
     __syncthreads();
     for (int size = 2; size <= n2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (t < (n2 >> 1)) {
-                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+            for (int q = t; q < (n2 >> 1); q += NT) {
+                const int lo = ((q & ~(stride - 1)) << 1) | (q & (stride - 1));
                 const int hi = lo + stride;
                 const bool desc = (lo & size) == 0;
                 const unsigned long long x = key[lo], y = key[hi];
@@ -241,25 +272,24 @@ __device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigne
     }
     if (c > 0) {                                                      // ties descend into earlier class columns
         bool tie = false;
-        unsigned long long kp = 0ull;
-        if (t < K) {
-            kp = key[t];
-            const uint32_t v = (uint32_t)(kp >> 32);
-            tie = (t > 0 && (uint32_t)(key[t - 1] >> 32) == v) || (t + 1 < K && (uint32_t)(key[t + 1] >> 32) == v);
+        for (int p = t; p < K; p += NT) {
+            const uint32_t v = (uint32_t)(key[p] >> 32);
+            tie |= (p > 0 && (uint32_t)(key[p - 1] >> 32) == v) || (p + 1 < K && (uint32_t)(key[p + 1] >> 32) == v);
         }
         if (__syncthreads_or(tie ? 1 : 0)) {
             unsigned long long* tmp = reinterpret_cast<unsigned long long*>(box);
-            if (t < K) {
-                int rank = t;
-                if (tie) {
-                    const uint32_t v = (uint32_t)(kp >> 32);
-                    int s0 = t, e0 = t + 1;
-                    while (s0 > 0 && (uint32_t)(key[s0 - 1] >> 32) == v) --s0;
-                    while (e0 < K && (uint32_t)(key[e0] >> 32) == v) ++e0;
+            for (int p = t; p < K; p += NT) {
+                const unsigned long long kp = key[p];
+                const uint32_t v = (uint32_t)(kp >> 32);
+                int s0 = p, e0 = p + 1;
+                while (s0 > 0 && (uint32_t)(key[s0 - 1] >> 32) == v) --s0;
+                while (e0 < K && (uint32_t)(key[e0] >> 32) == v) ++e0;
+                int rank = p;
+                if (e0 - s0 > 1) {
                     rank = s0;
                     const int j = 0xffff - (int)(kp & 0xffffu);
                     for (int qq = s0; qq < e0; ++qq) {
-                        if (qq == t) continue;
+                        if (qq == p) continue;
                         const int i = 0xffff - (int)(key[qq] & 0xffffu);
                         if (precedes(conf_img, a.C, c, i, 0.f, j, 0.f)) ++rank;
                     }
@@ -267,46 +297,65 @@ __device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigne
                 tmp[rank] = kp;
             }
             __syncthreads();
-            if (t < K) key[t] = tmp[t];
+            for (int p = t; p < K; p += NT) key[p] = tmp[p];
             __syncthreads();
         }
     }
-    float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < K) { bj = load_box(bmin, bmax, 0xffff - (int)(key[t] & 0xffffu)); box[t] = bj; }
-    const float aj = box_area(bj);
+    // boxes in visiting order; thread (warp w, lane l) owns the candidates (w + 8 j) * 32 + l, warp w the alive words w + 8 j
     const int words = (K + 31) / 32;
-    uint32_t alive_w = 0u;                                            // warp w owns word w (uniform across its lanes)
-    if (warp < words) alive_w = (warp * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - warp * 32)) - 1u);
-    if (lane == 0 && warp < words) alive_sm[warp] = alive_w;
+    float4 bj[COOP_R];
+    float aj[COOP_R];
+    uint32_t alive_w[COOP_R];
+#pragma unroll
+    for (int j = 0; j < COOP_R; ++j) {
+        const int wd = warp + NMS_WARPS * j, p = wd * 32 + lane;
+        bj[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < K) { bj[j] = load_box(bmin, bmax, 0xffff - (int)(key[p] & 0xffffu)); box[p] = bj[j]; }
+        aj[j] = box_area(bj[j]);
+        alive_w[j] = 0u;
+        if (wd < words) {
+            alive_w[j] = (wd * 32 + 32 <= K) ? 0xffffffffu : ((1u << (K - wd * 32)) - 1u);
+            if (lane == 0) alive_sm[wd] = alive_w[j];
+        }
+    }
     __syncthreads();
     int kept = 0, g = 0, prev = -1;
     while (g < words) {                                               // CTA-uniform control flow throughout
-        // a reader that sees warp g's update of this step still finds the same lowest bit: only bits above r are cleared
+        // a reader that sees the owner's update of this step still finds the same lowest bit: only bits above r are cleared
         const uint32_t m = alive_sm[g] & (prev >= 31 ? 0u : (0xffffffffu << (prev + 1)));
         if (m == 0u) { ++g; prev = -1; continue; }
         const int bit = __ffs(m) - 1;
         const int r = g * 32 + bit;
         prev = bit;
         const float4 bi = box[r];
+        const float ai = box_area(bi);
         if (t == 0) list[kept] = (uint16_t)(0xffff - (int)(key[r] & 0xffffu));      // kept <= r: slot already consumed
         ++kept;
-        if (warp >= g && warp < words) {
-            const bool kill = t > r && ((alive_w >> lane) & 1u) && iou_hit(bi, box_area(bi), bj, aj, a.thr_iou, thr_lo, quick);
-            const uint32_t km = __ballot_sync(0xffffffffu, kill);
-            alive_w &= ~km;
-            if (lane == 0 && km) alive_sm[warp] = alive_w;
+#pragma unroll
+        for (int j = 0; j < COOP_R; ++j) {
+            const int wd = warp + NMS_WARPS * j;
+            if (wd >= g && wd < words) {                              // warp-uniform
+                const bool kill = wd * 32 + lane > r && ((alive_w[j] >> lane) & 1u) && iou_hit(bi, ai, bj[j], aj[j], a.thr_iou, thr_lo, quick);
+                const uint32_t km = __ballot_sync(0xffffffffu, kill);
+                alive_w[j] &= ~km;
+                if (lane == 0 && km) alive_sm[wd] = alive_w[j];
+            }
         }
         __syncthreads();
     }
-    if (t < K && !((alive_w >> lane) & 1u)) {                         // suppressed candidates = cleared alive bits
-        const int j = 0xffff - (int)(key[t] & 0xffffu);
-        atomicOr(&supp[j >> 5], 1u << (j & 31));
+#pragma unroll
+    for (int j = 0; j < COOP_R; ++j) {                                // suppressed candidates = cleared alive bits
+        const int p = (warp + NMS_WARPS * j) * 32 + lane;
+        if (p < K && !((alive_w[j] >> lane) & 1u)) {
+            const int jx = 0xffff - (int)(key[p] & 0xffffu);
+            atomicOr(&supp[jx >> 5], 1u << (jx & 31));
+        }
     }
     __syncthreads();
     uint16_t* kept_out = a.cand + ((size_t)b * a.C + c) * a.N;
-    if (t < kept) kept_out[t] = list[t];
+    for (int p = t; p < kept; p += NT) kept_out[p] = list[p];
     uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
-    for (int w = t; w < a.W; w += NMS_WARPS * 32) supp_out[w] = supp[w];
+    for (int w = t; w < a.W; w += NT) supp_out[w] = supp[w];
     if (t == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
     __syncthreads();
 }
@@ -318,7 +367,10 @@ __device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigne
 //   supp : suppressed candidates, by box index;  alive : alive candidates, by rank (general path: up to N ranks)
 //   list : per class: candidates as found, later the kept list
 __host__ __device__ inline size_t sel_warp_bytes(int W) { return (size_t)SEL_CAP * 24 + 2 * (size_t)((W + 3) & ~3) * 4; }
-static size_t sel_smem_bytes(int W) { return NMS_WARPS * sel_warp_bytes(W) + 32 * SEL_CAP * sizeof(uint16_t) + 33 * sizeof(int); }
+static size_t sel_smem_bytes(int W) {
+    const size_t warps = NMS_WARPS * sel_warp_bytes(W);              // phase B (select_class_coop) re-uses this area as one pool
+    return (warps > coop_pool_bytes(W) ? warps : coop_pool_bytes(W)) + 32 * SEL_CAP * sizeof(uint16_t) + 33 * sizeof(int);
+}
 
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, int vec4) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
@@ -329,8 +381,9 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     float4* w_box = reinterpret_cast<float4*>(wbase + SEL_CAP * 8);
     uint32_t* w_supp = reinterpret_cast<uint32_t*>(wbase + SEL_CAP * 24);
     uint32_t* w_alive = w_supp + Wp;
-    uint16_t (*s_list)[SEL_CAP] = reinterpret_cast<uint16_t (*)[SEL_CAP]>(sel_smem + NMS_WARPS * sel_warp_bytes(a.W));
-    int* s_cnt = reinterpret_cast<int*>(sel_smem + NMS_WARPS * sel_warp_bytes(a.W) + 32 * SEL_CAP * sizeof(uint16_t));
+    const size_t area = NMS_WARPS * sel_warp_bytes(a.W) > coop_pool_bytes(a.W) ? NMS_WARPS * sel_warp_bytes(a.W) : coop_pool_bytes(a.W);
+    uint16_t (*s_list)[SEL_CAP] = reinterpret_cast<uint16_t (*)[SEL_CAP]>(sel_smem + area);
+    int* s_cnt = reinterpret_cast<int*>(sel_smem + area + 32 * SEL_CAP * sizeof(uint16_t));
     const int c0 = blockIdx.x * 32;                     // this CTA: 32 classes of image b
     const int b = blockIdx.y;
     const float* conf_img = a.conf + (size_t)b * a.N * a.C;
@@ -407,11 +460,11 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
             if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = 0;
             continue;
         }
+        if (coop && K > COOP_MIN && K <= COOP_CAP) continue;          // phase B below
         if (K > SEL_CAP) {
             select_class_general(a, b, c, w_alive, w_supp, lane);
             continue;
         }
-        if (coop && K > COOP_MIN) continue;                           // phase B below
         // 2. keys -> shared memory, bitonic sort (descending), exact re-ranking of equal-value runs
         uint16_t* list = s_list[cl];
         int n2 = 32;
@@ -498,15 +551,11 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     }   // class loop
     if (coop) {                                                       // phase B: the heavy classes, one at a time, all 8 warps
         __syncthreads();
-        unsigned long long* key0 = reinterpret_cast<unsigned long long*>(sel_smem);
-        float4* box0 = reinterpret_cast<float4*>(sel_smem + SEL_CAP * 8);
-        uint32_t* supp0 = reinterpret_cast<uint32_t*>(sel_smem + SEL_CAP * 24);
-        uint32_t* alive0 = supp0 + Wp;                                // warp 0's alive words: Wp >= 8 whenever N >= 225
         for (int cl = 0; cl < 32; ++cl) {
             const int c = c0 + cl;
             if (c >= a.C) break;
             const int K = s_cnt[cl];
-            if (K > COOP_MIN && K <= SEL_CAP) select_class_coop(a, b, c, K, key0, box0, supp0, alive0, s_list[cl], quick, thr_lo);
+            if (K > COOP_MIN && K <= COOP_CAP) select_class_coop(a, b, c, K, sel_smem, K <= SEL_CAP ? s_list[cl] : nullptr, quick, thr_lo);
         }
     }
 }
@@ -539,7 +588,8 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
     __shared__ float4 kbox[8][32];
     __shared__ float karea[8][32];
     __shared__ int tile_cnt[AP_CLASSES];
-    __shared__ int any_kept, dirty;
+    __shared__ int item_start[AP_CLASSES + 1];
+    __shared__ int any_kept, dirty, next_item;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c_tiles = (a.C + AP_CLASSES - 1) / AP_CLASSES;
     const int n_tiles = (a.N + AP_BOXES - 1) / AP_BOXES;
@@ -593,39 +643,73 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
             barea[h] = box_area(bn[h]);
         }
         bool wrote = false;
+        // phase 1: candidates look their fate up in the suppressed mask (a warp per class column)
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
-            const int cnt = tile_cnt[cl];
-            if (cnt == 0) continue;                                  // warp-uniform
-            const uint16_t* kept = a.cand + ((size_t)b * a.C + c0 + cl) * a.N;
+            if (tile_cnt[cl] == 0) continue;                         // warp-uniform
             const uint32_t* supp = a.supp + ((size_t)b * a.C + c0 + cl) * a.W + (n0 >> 5);
+#pragma unroll
+            for (int h = 0; h < AP_H; ++h)
+                if (n_ok[h] && tile[h * 32 + lane][cl] > a.thr && ((__ldg(supp + h) >> lane) & 1u)) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
+        }
+        // work items of phase 2 = (class column, chunk of <= 32 kept boxes): the kept counts of real score matrices are very
+        // uneven (one class may keep 160 boxes, most keep none), so the chunks -- not the columns -- are handed out to the warps
+        // every tile has a CTA of its own (a detection batch): the kernel's time is its slowest warp -> items = chunks of 32 kept
+        // boxes, handed out dynamically; many tiles per CTA (a sweep over hundreds of images): throughput regime -> one item per
+        // class column (a lane that was hit skips the remaining chunks of its class), static round-robin
+        const bool dynamic = a.apply_mode ? a.apply_mode == 1 : total_tiles <= (long long)gridDim.x;
+        if (warp == 0) {
+            const int chunks = dynamic ? (tile_cnt[lane] + 31) >> 5 : (tile_cnt[lane] > 0 ? 1 : 0);
+            int incl = chunks;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            item_start[lane] = incl - chunks;
+            if (lane == 31) { item_start[32] = incl; next_item = 0; }
+        }
+        __syncthreads();                                             // phase 1's zeroes are in place, the item table is built
+        const int items = item_start[32];
+        for (int round = 0;; ++round) {
+            int it = warp + 8 * round;
+            if (dynamic) {
+                if (lane == 0) it = atomicAdd(&next_item, 1);
+                it = __shfl_sync(0xffffffffu, it, 0);
+            }
+            if (it >= items) break;
+            const int cl = __popc(__ballot_sync(0xffffffffu, item_start[lane] <= it)) - 1;      // last column that starts at or before it
+            const int kb = dynamic ? (it - item_start[cl]) << 5 : 0;                   // the item's range of kept boxes [kb, ke)
+            const int ke = dynamic ? min(kb + 32, tile_cnt[cl]) : tile_cnt[cl];
+            const uint16_t* kept = a.cand + ((size_t)b * a.C + c0 + cl) * a.N;
+            // Non-candidates only: a kept candidate (> threshold) is never touched, a suppressed one is already zero.  Other warps
+            // may zero entries of this column while we run: the races are benign (every write is 0.0f, a stale read only costs
+            // a redundant test).
             bool skip[AP_H], hit[AP_H];
             bool all_skip = true;
 #pragma unroll
             for (int h = 0; h < AP_H; ++h) {
-                const bool cand = tile[h * 32 + lane][cl] > a.thr;
+                const float v = tile[h * 32 + lane][cl];
+                skip[h] = !n_ok[h] || v > a.thr || __float_as_uint(v) == 0u;      // candidates, and scores that are +0.0 already (-0.0 must become +0.0)
                 hit[h] = false;
-                if (cand && n_ok[h]) hit[h] = (__ldg(supp + h) >> lane) & 1u;       // suppressed candidate
-                skip[h] = cand || !n_ok[h];
                 all_skip &= skip[h];
             }
-            if (!__all_sync(0xffffffffu, all_skip)) {
-                for (int k0 = 0; k0 < cnt; k0 += 32) {
-                    const int kc = min(32, cnt - k0);
-                    if (lane < kc) {
-                        const float4 kq = load_box(bmin, bmax, kept[k0 + lane]);
-                        kbox[warp][lane] = kq;
-                        karea[warp][lane] = box_area(kq);
-                    }
-                    __syncwarp();
-                    for (int t = 0; t < kc; ++t) {
-                        const float4 kb = kbox[warp][t];
-                        const float ka = karea[warp][t];
-#pragma unroll
-                        for (int h = 0; h < AP_H; ++h)
-                            if (!skip[h] && !hit[h]) hit[h] = iou_hit(kb, ka, bn[h], barea[h], a.thr_iou, thr_lo, quick);
-                    }
-                    __syncwarp();
+            if (__all_sync(0xffffffffu, all_skip)) continue;
+            for (int k0 = kb; k0 < ke; k0 += 32) {
+                const int kc = min(32, ke - k0);
+                if (lane < kc) {
+                    const float4 kq = load_box(bmin, bmax, kept[k0 + lane]);
+                    kbox[warp][lane] = kq;
+                    karea[warp][lane] = box_area(kq);
                 }
+                __syncwarp();
+                for (int t = 0; t < kc; ++t) {
+                    const float4 kq = kbox[warp][t];
+                    const float ka = karea[warp][t];
+#pragma unroll
+                    for (int h = 0; h < AP_H; ++h)
+                        if (!skip[h] && !hit[h]) hit[h] = iou_hit(kq, ka, bn[h], barea[h], a.thr_iou, thr_lo, quick);
+                }
+                __syncwarp();
             }
 #pragma unroll
             for (int h = 0; h < AP_H; ++h)
@@ -684,6 +768,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     a.kept_cnt = reinterpret_cast<int*>(base + 2 * lists + masks);
     a.status = status_out;
     a.order_out = order_out;
+    a.apply_mode = g_nms_apply_mode;
     const int vec4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(conf) & 15) == 0;
     const size_t smem = sel_smem_bytes(a.W);
     static unsigned long long attr_seen = 0;
