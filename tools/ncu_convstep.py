@@ -27,7 +27,7 @@ tscale = {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}
 rd = sum(float(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]] for r in rows)
 wr = sum(float(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]] for r in rows)
 ms = sum(float(r[col["gpu__time_duration.sum"]]) * tscale[units[col["gpu__time_duration.sum"]]] for r in rows)
-out = {"source": "ncu --set full -k regex:conv_tc_kernel -s 63 -c 21 (one inference step, B=32, 416, C=80), tag " + TAG,
+out = {"source": "ncu --set full -k regex:conv_tc_kernel -c 21 of the first timed step (one detection step, B=32, 416, C=80), tag " + TAG,
        "launches": len(rows), "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
        "kernel_time_under_ncu_ms": ms}
 with open("profiles/conv_step_traffic_%s.json" % TAG, "w") as f:
