@@ -16,6 +16,9 @@ except Exception as e:
     print("   unreadable:", e)
 PY
 }
-for n in 1 2 4 8; do run $n gpurun_out/scale_train_${TAG}_n$n.json --workload train --steps 20 --no-cpu-baseline; done
-for n in 8; do run $n gpurun_out/scale_608_${TAG}_n$n.json --size 608 --steps 60 --no-cpu-baseline --no-nms-sweep; done
-if [ "$2" = "infer" ]; then for n in 1 2 4 8; do run $n gpurun_out/scale_infer_${TAG}_n$n.json --steps 200 --no-cpu-baseline --no-nms-sweep; done; fi
+if [ "$2" = "infer" ]; then
+  for n in 1 2 4 8; do run $n gpurun_out/scale_infer_${TAG}_n$n.json --steps 200 --no-cpu-baseline --no-nms-sweep; done
+else
+  for n in 1 2 4 8; do run $n gpurun_out/scale_train_${TAG}_n$n.json --workload train --steps 20 --no-cpu-baseline; done
+  for n in 8; do run $n gpurun_out/scale_608_${TAG}_n$n.json --size 608 --steps 60 --no-cpu-baseline --no-nms-sweep; done
+fi

@@ -25,8 +25,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------------------------------------
 // decode: a CTA stages G consecutive boxes (G*(5+C) contiguous floats) into shared memory with
-// 128-bit loads, one warp decodes one box at a time (lanes over classes, shuffle softmax), results
-// are staged and written back with 128-bit stores.
+// 128-bit loads, one THREAD decodes one box out of its private shared-memory row, results are staged
+// and written back with 128-bit stores.
 struct DecodeArgs {
     const float* net;
     const float* anchors;     // [A][2] float32
@@ -45,13 +45,12 @@ __device__ __forceinline__ void copy_out(float* __restrict__ dst, const float* _
     for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(128) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int D = 5 + a.C;
     float* s_in = sm;                              // [G][D]
     float* s_conf = s_in + (size_t)a.G * D;        // [G][C]
     float* s_box = s_conf + (size_t)a.G * a.C;     // [G][24]: xmin ymin xmax ymax | iou w h area | x y oxmin oymin | oxmax oymax sqw sqh | sx sy w01 h01 | (cx, cy, anchor as ints)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (long long g0 = (long long)blockIdx.x * a.G; g0 < a.boxes; g0 += (long long)gridDim.x * a.G) {
         const int g_cnt = (int)min((long long)a.G, a.boxes - g0);
         // ---- stage in (g0*D*4 bytes is a multiple of 16 because G%4==0)
@@ -62,78 +61,67 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
             for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(src4 + i);
             for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s_in[i] = __ldg(a.net + g0 * D + i);
         }
-        // per-box cell coordinates and anchor index: ONE thread per box does the integer divisions (a warp doing them
-        // redundantly in all 32 lanes was a third of the kernel's instructions)
-        if (threadIdx.x < g_cnt) {
-            const int n = (int)((g0 + threadIdx.x) % ((long long)a.cells * a.A));
-            const int cell = n / a.A;
-            int* meta = reinterpret_cast<int*>(s_box + (size_t)threadIdx.x * 24 + 20);
-            meta[0] = cell % a.Wc; meta[1] = cell / a.Wc; meta[2] = n - cell * a.A;
-        }
         __syncthreads();
-        for (int g = warp; g < g_cnt; g += nw) {
-            const float* in = s_in + g * D;
+        // ---- one THREAD per box (round 2; round 1 ran a warp per box): a box is 5 + C numbers, far too little to keep 32
+        // lanes busy -- every shuffle, index computation and scalar box transform was executed 32-fold (444 warp
+        // instructions per box).  The box's row is private in shared memory (row pitch 5 + C words: odd for the shipped class
+        // counts, so the lanes of a warp hit distinct banks), the class exponentials are written back in place, so the softmax
+        // costs one exp per class.  Hardware exp / reciprocal (ex2.approx, rcp.approx: a few ulp; the parity bar is 1e-4).
+        if (threadIdx.x < g_cnt) {
+            const int g = threadIdx.x;
+            float* in = s_in + g * D;
             const long long gi = g0 + g;
-            const int* meta = reinterpret_cast<const int*>(s_box + g * 24 + 20);
-            const int an = meta[2];
-            // softmax over classes (max-subtracted, as tf.nn.softmax); up to 4 classes per lane stay in registers.
-            // Exponentials and quotients use the hardware approximations (ex2.approx / rcp.approx: a few ulp, 1e-6 relative on
-            // every value that matters -- the parity bar is 1e-4): the libm versions made this kernel instruction-bound
-            // (444 warp instructions per box, profiles/ncu_r2c_hbm_kernels.txt); padded lanes carry -inf -> exp = 0, no branches.
-            float mx = -INFINITY;
-            float ev[4];
+            const int n = (int)(gi % ((long long)a.cells * a.A));
+            const int cell = n / a.A, an = n - cell * a.A;
+            // four independent chains per reduction: the thread's latency, not its instruction count, is what is left
+            const int C4 = a.C & ~3;
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int c = 0; c < C4; c += 4) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int c = lane + 32 * t;
-                ev[t] = (c < a.C) ? in[5 + c] : -INFINITY;
-                mx = fmaxf(mx, ev[t]);
+                for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], in[5 + c + u]);
             }
-            for (int c = lane + 128; c < a.C; c += 32) mx = fmaxf(mx, in[5 + c]);
-            mx = warp_max(mx);
-            float se = 0.f;
+            for (int c = C4; c < a.C; ++c) m4[0] = fmaxf(m4[0], in[5 + c]);
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < C4; c += 4) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                ev[t] = __expf(ev[t] - mx);
-                se += ev[t];
-            }
-            for (int c = lane + 128; c < a.C; c += 32) se += __expf(in[5 + c] - mx);
-            se = warp_sum(se);
-            const float rse = __fdividef(1.0f, se);
-            // the five box logits in parallel: lanes 0..2 sigmoid (iou, x, y), lanes 3..4 exp * anchor (w, h)
-            float bv = 0.f;
-            {
-                const float t5 = in[lane < 5 ? lane : 0];
-                const float e5 = __expf(lane < 3 ? -t5 : t5);
-                bv = lane < 3 ? __fdividef(1.0f, 1.0f + e5) : e5 * __ldg(a.anchors + 2 * an + (lane == 4 ? 1 : 0));
-            }
-            const float iou = __shfl_sync(0xffffffffu, bv, 0);
-            const float sx = __shfl_sync(0xffffffffu, bv, 1), sy = __shfl_sync(0xffffffffu, bv, 2);
-            const float w = __shfl_sync(0xffffffffu, bv, 3), h = __shfl_sync(0xffffffffu, bv, 4);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int c = lane + 32 * t;
-                if (c < a.C) {
-                    const float pr = ev[t] * rse;
-                    s_conf[g * a.C + c] = iou * pr;
-                    if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
+                for (int u = 0; u < 4; ++u) {
+                    const float e = __expf(in[5 + c + u] - mx);
+                    in[5 + c + u] = e;
+                    s4[u] += e;
                 }
             }
-            for (int c = lane + 128; c < a.C; c += 32) {
-                const float pr = __expf(in[5 + c] - mx) * rse;
-                s_conf[g * a.C + c] = iou * pr;
-                if (a.o.prob) a.o.prob[gi * a.C + c] = pr;
+            for (int c = C4; c < a.C; ++c) {
+                const float e = __expf(in[5 + c] - mx);
+                in[5 + c] = e;
+                s4[0] += e;
             }
-            if (lane == 0) {
-                const float hw = w / 2.0f, hh = h / 2.0f;
-                const float oxmin = sx - hw, oymin = sy - hh, oxmax = sx + hw, oymax = sy + hh;
-                const float cx = (float)meta[0], cy = (float)meta[1];
-                float4* bx = reinterpret_cast<float4*>(s_box + g * 24);
-                bx[0] = make_float4(cx + oxmin, cy + oymin, cx + oxmax, cy + oymax);
-                bx[1] = make_float4(iou, w, h, w * h);
-                bx[2] = make_float4(cx + sx, cy + sy, oxmin, oymin);
-                bx[3] = make_float4(oxmax, oymax, sqrtf(w / (float)a.Wc), sqrtf(h / (float)a.Hc));
-                bx[4] = make_float4(sx, sy, w / (float)a.Wc, h / (float)a.Hc);
+            const float se = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            const float rse = __fdividef(1.0f, se);
+            const float iou = __fdividef(1.0f, 1.0f + __expf(-in[0]));
+            const float sx = __fdividef(1.0f, 1.0f + __expf(-in[1])), sy = __fdividef(1.0f, 1.0f + __expf(-in[2]));
+            const float w = __expf(in[3]) * __ldg(a.anchors + 2 * an), h = __expf(in[4]) * __ldg(a.anchors + 2 * an + 1);
+            float* cf = s_conf + g * a.C;
+            if (a.o.prob) {
+                for (int c = 0; c < a.C; ++c) {
+                    const float pr = in[5 + c] * rse;
+                    cf[c] = iou * pr;
+                    a.o.prob[gi * a.C + c] = pr;
+                }
+            } else {
+                const float k = iou;
+#pragma unroll 4
+                for (int c = 0; c < a.C; ++c) cf[c] = k * (in[5 + c] * rse);
             }
+            const float hw = w / 2.0f, hh = h / 2.0f;
+            const float oxmin = sx - hw, oymin = sy - hh, oxmax = sx + hw, oymax = sy + hh;
+            const float cx = (float)(cell % a.Wc), cy = (float)(cell / a.Wc);
+            float4* bx = reinterpret_cast<float4*>(s_box + g * 24);
+            bx[0] = make_float4(cx + oxmin, cy + oymin, cx + oxmax, cy + oymax);
+            bx[1] = make_float4(iou, w, h, w * h);
+            bx[2] = make_float4(cx + sx, cy + sy, oxmin, oymin);
+            bx[3] = make_float4(oxmax, oymax, sqrtf(w / (float)a.Wc), sqrtf(h / (float)a.Hc));
+            bx[4] = make_float4(sx, sy, w / (float)a.Wc, h / (float)a.Hc);
         }
         __syncthreads();
         // ---- stage out
@@ -169,9 +157,9 @@ int head_decode_launch(const float* net, int B, int Hc, int Wc, int A, int C, co
     a.o = *outs;
     if (a.boxes == 0) return 0;
     const int D = 5 + C;
-    // boxes per CTA: enough CTAs to fill the machine at small batches (B = 32: 27 k boxes -> ~1 k CTAs of 28 boxes),
-    // at most 64 boxes, a multiple of 4 (16-byte aligned chunks)
-    int G = (int)std::min<long long>(64, std::max<long long>(8, (a.boxes / (148 * 6)) & ~3LL));
+    // boxes per CTA = threads that decode (the rest only help with the staging copies): 32 .. 128, a multiple of 4
+    // (16-byte aligned chunks), enough CTAs to cover the machine at small batches (B = 32: 27 k boxes -> 423 CTAs of 64)
+    int G = (int)std::min<long long>(128, std::max<long long>(32, (a.boxes / (148 * 2)) & ~31LL));
     while (G > 4 && (size_t)G * (D + C + 24) * 4 > 96 * 1024) G -= 4;
     Y2_REQUIRE((size_t)G * (D + C + 24) * 4 <= 200 * 1024, "head_decode: too many classes (%d)", C);
     a.G = G;
@@ -181,7 +169,7 @@ int head_decode_launch(const float* net, int B, int Hc, int Wc, int A, int C, co
         Y2_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long blocks = (a.boxes + G - 1) / G;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    decode_kernel<<<(int)blocks, 256, smem, s>>>(a);
+    decode_kernel<<<(int)blocks, 128, smem, s>>>(a);
     Y2_CUDA(cudaGetLastError());
     note_launch();
     return 0;
