@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int D = 5 + a.C;
     float* s_in = sm;                              // [G][D]
-    float* s_conf = s_in + (size_t)a.G * D;        // [G][C]
-    float* s_box = s_conf + (size_t)a.G * a.C;     // [G][24]: xmin ymin xmax ymax | iou w h area | x y oxmin oymin | oxmax oymax sqw sqh | sx sy w01 h01 | (cx, cy, anchor as ints)
+    const int CP = a.C + 4;                        // row pitch of s_conf: +4 words keeps the rows 16-byte aligned and spreads a warp's per-class stores over 8 banks instead of 2
+    float* s_conf = s_in + (size_t)a.G * D;        // [G][CP]
+    float* s_box = s_conf + (size_t)a.G * CP;      // [G][24]: xmin ymin xmax ymax | iou w h area | x y oxmin oymin | oxmax oymax sqw sqh | sx sy w01 h01 | (cx, cy, anchor as ints)
     for (long long g0 = (long long)blockIdx.x * a.G; g0 < a.boxes; g0 += (long long)gridDim.x * a.G) {
         const int g_cnt = (int)min((long long)a.G, a.boxes - g0);
         // ---- stage in (g0*D*4 bytes is a multiple of 16 because G%4==0)
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeArgs a) {
             const float iou = __fdividef(1.0f, 1.0f + __expf(-in[0]));
             const float sx = __fdividef(1.0f, 1.0f + __expf(-in[1])), sy = __fdividef(1.0f, 1.0f + __expf(-in[2]));
             const float w = __expf(in[3]) * __ldg(a.anchors + 2 * an), h = __expf(in[4]) * __ldg(a.anchors + 2 * an + 1);
-            float* cf = s_conf + g * a.C;
+            float* cf = s_conf + g * CP;
             if (a.o.prob) {
                 for (int c = 0; c < a.C; ++c) {
                     const float pr = in[5 + c] * rse;
@@ -125,7 +126,21 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeArgs a) {
         }
         __syncthreads();
         // ---- stage out
-        if (a.o.conf) copy_out(a.o.conf + g0 * a.C, s_conf, g_cnt * a.C, threadIdx.x, blockDim.x);
+        if (a.o.conf) {                              // rows of C floats (pitch CP) -> contiguous [g_cnt][C]
+            float* dst = a.o.conf + g0 * a.C;
+            if ((a.C & 3) == 0) {
+                const int c4 = a.C >> 2, n4 = g_cnt * c4;
+                for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                    const int r = i / c4, q = i - r * c4;
+                    reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(s_conf + r * CP + 4 * q);
+                }
+            } else {
+                for (int i = threadIdx.x; i < g_cnt * a.C; i += blockDim.x) {
+                    const int r = i / a.C;
+                    dst[i] = s_conf[r * CP + (i - r * a.C)];
+                }
+            }
+        }
         for (int i = threadIdx.x; i < g_cnt; i += blockDim.x) {
             const float* bx = s_box + (size_t)i * 24;
             const float sx = bx[16], sy = bx[17];
@@ -160,10 +175,10 @@ int head_decode_launch(const float* net, int B, int Hc, int Wc, int A, int C, co
     // boxes per CTA = threads that decode (the rest only help with the staging copies): 32 .. 128, a multiple of 4
     // (16-byte aligned chunks), enough CTAs to cover the machine at small batches (B = 32: 27 k boxes -> 423 CTAs of 64)
     int G = (int)std::min<long long>(128, std::max<long long>(32, (a.boxes / (148 * 2)) & ~31LL));
-    while (G > 4 && (size_t)G * (D + C + 24) * 4 > 96 * 1024) G -= 4;
-    Y2_REQUIRE((size_t)G * (D + C + 24) * 4 <= 200 * 1024, "head_decode: too many classes (%d)", C);
+    while (G > 4 && (size_t)G * (D + C + 4 + 24) * 4 > 96 * 1024) G -= 4;
+    Y2_REQUIRE((size_t)G * (D + C + 4 + 24) * 4 <= 200 * 1024, "head_decode: too many classes (%d)", C);
     a.G = G;
-    const size_t smem = (size_t)G * (D + C + 24) * 4;
+    const size_t smem = (size_t)G * (D + C + 4 + 24) * 4;
     static unsigned long long attr_seen = 0;
     if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
