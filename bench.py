@@ -442,12 +442,17 @@ def run_infer(args, torch, dist, dev, world, rank, local, barrier):
 
     det_shapes = [((B,), torch.int32), ((B, N), torch.int32), ((B, N), torch.int32), ((B, N), torch.float32), ((B, N, 4), torch.float32)]
     e2e_run(host_u8, lambda u8: step_device(u8)[0], det_shapes, 3, False)
-    d2h_bytes = e2e_run(host_u8, lambda u8: step_device(u8)[0], det_shapes, args.steps, True)
-    e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    # three blocks of exactly K steps each, every block timed on the device (max over ranks); the MEDIAN block is reported and all
+    # three are listed: this region is driven by ~35 host-side launches per 3 ms step, so one descheduled host thread on a shared
+    # box shows up as a slow block (profiles/README.md, round 2: one block at 6.4 ms/step between runs at 3.1)
+    e2e_blocks = []
+    for _ in range(3):
+        d2h_bytes = e2e_run(host_u8, lambda u8: step_device(u8)[0], det_shapes, args.steps, True)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_blocks.append(float(t.item()))
+    e2e_ms = sorted(e2e_blocks)[1]
 
     # comparison variant (round 1's e2e path): float32 standardised images in, the full post-NMS score matrix + boxes out
     host_f32 = [torch.from_numpy(np.random.RandomState(200 + rank + i).normal(0, 1, size=(B, size, size, 3)).astype(np.float32)).pin_memory()
@@ -541,7 +546,8 @@ def run_infer(args, torch, dist, dev, world, rank, local, barrier):
         "data": "synthetic", "config": workload_config(args, B),
         "nms_load": {"candidates_per_image": cands_per_image, "detections_per_image": dets_per_image},
         "e2e": {"value": imgs / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "blocks_ms_per_step": [b / args.steps for b in e2e_blocks],
+                "blocks": "3 blocks of K steps; the median block is reported",
                 "path": "pinned host uint8 images -> H2D (copy stream, double-buffered) -> per_image_standardization -> Builder(x) -> "
                         "non_max_suppress_device -> detections_device -> D2H of (count, box, class, score, xywh)",
                 "f32_variant": {"value": B * world * f32_steps / (f32_ms / 1e3), "unit": "images/s", "steps": f32_steps,

@@ -94,6 +94,7 @@ struct NmsArgs {
     int* kept_cnt;       // [B][C]
     int* status;         // [B] nullable: 1 = a reference assert (NaN / xy_min > xy_max) would fire
     int* order_out;      // [B][N] nullable
+    uint16_t* area_perm; // [B][N] boxes of the image in ascending order of area (apply's tile order)
     int apply_mode;      // diagnostics: 0 = choose by regime, 1 = chunk items handed out dynamically, 2 = one item per class column
 };
 
@@ -372,8 +373,62 @@ static size_t sel_smem_bytes(int W) {
     return (warps > coop_pool_bytes(W) ? warps : coop_pool_bytes(W)) + 32 * SEL_CAP * sizeof(uint16_t) + 33 * sizeof(int);
 }
 
+// Boxes of one image in ascending order of quantised area: a stable counting sort on the top 11 bits of ford(area) (sign,
+// exponent, two mantissa bits: buckets 19 % wide), one CTA per image.  apply takes its 128-box tiles in THIS order (see there);
+// the order only has to be roughly by area, and it is deterministic (boxes of one bucket stay in index order).  It runs as one
+// extra CTA per image inside the select launch (blockIdx.x == gridDim.x - 1), on that kernel's dynamic shared memory.
+static constexpr int AREA_BUCKETS = 2048;
+static constexpr size_t AREA_ORDER_SMEM = AREA_BUCKETS * sizeof(int) + NMS_MAX_N * sizeof(uint16_t) + 8 * sizeof(int);
+static_assert(NMS_WARPS == 8 && AREA_BUCKETS == 8 * NMS_WARPS * 32, "area_order: 8 buckets per thread, 8 warp totals");
+static_assert((size_t)NMS_WARPS * SEL_CAP * 24 >= AREA_ORDER_SMEM, "area_order lives in the select kernel's shared memory");
+__device__ void area_order(const NmsArgs& a, int b, unsigned char* smem) {
+    int* start = reinterpret_cast<int*>(smem);                           // [AREA_BUCKETS]
+    uint16_t* bkt = reinterpret_cast<uint16_t*>(smem + AREA_BUCKETS * sizeof(int));      // [N]
+    int* wsum = reinterpret_cast<int*>(smem + AREA_BUCKETS * sizeof(int) + NMS_MAX_N * sizeof(uint16_t));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+    const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+    for (int i = threadIdx.x; i < AREA_BUCKETS; i += 256) start[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.N; i += 256) {
+        const uint32_t k = ford(box_area(load_box(bmin, bmax, i))) >> 21;
+        bkt[i] = (uint16_t)k;
+        atomicAdd(&start[k], 1);
+    }
+    __syncthreads();
+    // exclusive prefix sum of the histogram: 8 buckets per thread, warp scan, 8 warp totals
+    int loc[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = tot; tot += start[threadIdx.x * 8 + j]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int base = incl - tot;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) start[threadIdx.x * 8 + j] = base + loc[j];
+    __syncthreads();
+    if (warp != 0) return;
+    uint16_t* out = a.area_perm + (size_t)b * a.N;
+    for (int i0 = 0; i0 < a.N; i0 += 32) {                              // one warp, in index order: stable
+        const int i = i0 + lane;
+        const uint32_t k = i < a.N ? (uint32_t)bkt[i] : 0xffffffffu;
+        const uint32_t same = __match_any_sync(0xffffffffu, k);
+        if (i < a.N) out[start[k] + __popc(same & ((1u << lane) - 1u))] = (uint16_t)i;
+        __syncwarp();
+        if (i < a.N && (same & ((1u << lane) - 1u)) == 0u) start[k] += __popc(same);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, int vec4) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
+    if (blockIdx.x == gridDim.x - 1) { area_order(a, blockIdx.y, sel_smem); return; }      // block-uniform
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Wp = (a.W + 3) & ~3;
     unsigned char* wbase = sel_smem + warp * sel_warp_bytes(a.W);
@@ -445,7 +500,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
     // Few CTAs in flight (a detection batch, not a sweep over hundreds of images): the machine is idle anyway and the kernel's
     // time is its longest class -- classes with more than COOP_MIN candidates then get the whole CTA (select_class_coop).
-    const bool coop = (int)(gridDim.x * gridDim.y) <= 2 * 148;
+    const bool coop = (int)((gridDim.x - 1) * gridDim.y) <= 2 * 148;      // the last column of CTAs is area_order
     // one warp per class from here on; classes are handed out dynamically (the candidate counts of real score matrices
     // are very uneven: a few classes hold most of an image's candidates)
     for (;;) {
@@ -582,82 +637,132 @@ __global__ void __launch_bounds__(256) nms_order_kernel(NmsArgs a) {
 // across the warp and its boxes are broadcast from shared memory -- the IoU loop has no global loads and no divergence.
 // Candidates look their fate up in the suppressed mask select wrote.  Only tiles of classes that kept something are
 // touched; modified tiles are written back coalesced.
-static constexpr int AP_BOXES = 128, AP_CLASSES = 32, AP_H = AP_BOXES / 32;
-__global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
+// The 128 boxes of a tile are consecutive in the image's AREA order (area_perm), not in index order -- every row is a
+// 128-byte segment of its own either way.  The 32 boxes a warp holds in register slot h then have areas in a narrow
+// range [amin_h, amax_h], and since inter <= min(area) and den >= max(area) (1 - 2^-22),
+//     IoU(k, box) >= thr  needs  0.998 thr amin_h <= area_k <= amax_h / (0.998 thr):
+// two warp-uniform compares rule a kept box out for the whole slot (anchor boxes span three decades of area, so most
+// (kept box, slot) pairs go this way).  Conservative: it only ever drops tests whose answer is "no hit".
+static constexpr int AP_BOXES = 128, AP_CLASSES = 32, AP_H = AP_BOXES / 32, AP_PF = 8;
+static_assert(AP_CLASSES * AP_PF == 256 && AP_CLASSES + AP_BOXES <= 256, "apply's thread roles assume 256 threads");
+__global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) {
     __shared__ float tile[AP_BOXES][AP_CLASSES + 1];                     // +1: column walks are bank-conflict-free
     __shared__ float4 kbox[8][32];
-    __shared__ float karea[8][32];
+    __shared__ float2 karea[8][32];                                      // {area, slot mask}
+    __shared__ float s_lo[AP_H], s_hi[AP_H];
+    __shared__ float4 pf_box[AP_CLASSES][AP_PF];                         // the first kept boxes of every class column, fetched with the tile
     __shared__ int tile_cnt[AP_CLASSES];
     __shared__ int item_start[AP_CLASSES + 1];
     __shared__ int any_kept, dirty, next_item;
+    __shared__ uint16_t s_perm[AP_BOXES];
+    __shared__ float4 s_box[AP_BOXES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c_tiles = (a.C + AP_CLASSES - 1) / AP_CLASSES;
     const int n_tiles = (a.N + AP_BOXES - 1) / AP_BOXES;
-    const long long total_tiles = (long long)a.B * n_tiles * c_tiles;
+    const int total_tiles = a.B * n_tiles * c_tiles;                     // < 2^31: checked by nms_launch
     const bool quick = a.thr_iou > 0.0f;
     const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
-    for (long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
-        const int ct = (int)(tix % c_tiles);
-        const long long r0 = tix / c_tiles;
-        const int ntile = (int)(r0 % n_tiles);
-        const int b = (int)(r0 / n_tiles);
+    const float thr_cull = __fmul_rn(0.998f, a.thr_iou);
+    // threads 32..159 own one row of the tile's slice of area_perm; the next tile's entry is fetched while this one is worked on
+    auto perm_of = [&](int t) -> uint16_t {
+        const int r0 = t / c_tiles;
+        const int r = (r0 % n_tiles) * AP_BOXES + (int)threadIdx.x - AP_CLASSES;
+        return (t < total_tiles && r < a.N) ? __ldg(a.area_perm + (size_t)(r0 / n_tiles) * a.N + r) : (uint16_t)0;
+    };
+    const bool perm_thread = threadIdx.x >= AP_CLASSES && threadIdx.x < AP_CLASSES + AP_BOXES;
+    uint16_t perm_next = perm_thread ? perm_of(blockIdx.x) : (uint16_t)0;
+    auto cnt_of = [&](int t) -> int {                                    // threads 0..31: kept count of the tile's class column
+        const int c = (t % c_tiles) * AP_CLASSES + (int)threadIdx.x;
+        return (t < total_tiles && c < a.C) ? __ldg(a.kept_cnt + (size_t)(t / c_tiles / n_tiles) * a.C + c) : 0;
+    };
+    int cnt_next = threadIdx.x < AP_CLASSES ? cnt_of(blockIdx.x) : 0;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int ct = tix % c_tiles;
+        const int r0 = tix / c_tiles;
+        const int ntile = r0 % n_tiles;
+        const int b = r0 / n_tiles;
         const int c0 = ct * AP_CLASSES, n0 = ntile * AP_BOXES;
         if (threadIdx.x == 0) { any_kept = 0; dirty = 0; }
         __syncthreads();
         if (threadIdx.x < AP_CLASSES) {
-            const int c = c0 + threadIdx.x;
-            const int k = (c < a.C) ? __ldg(a.kept_cnt + (size_t)b * a.C + c) : 0;
+            const int k = cnt_next;
+            cnt_next = cnt_of(tix + gridDim.x);
             tile_cnt[threadIdx.x] = k;
             if (k) any_kept = 1;
+        } else if (perm_thread) {
+            s_perm[threadIdx.x - AP_CLASSES] = perm_next;
+            perm_next = perm_of(tix + gridDim.x);
         }
         __syncthreads();
         const int ak = any_kept;
         __syncthreads();                                             // everyone has read it before the next tile resets it
         if (!ak) continue;                                           // block-uniform
         float* conf_img = a.conf + (size_t)b * a.N * a.C;
+        const float* bmin = a.xy_min + (size_t)b * a.N * 2;
+        const float* bmax = a.xy_max + (size_t)b * a.N * 2;
+        // thread = (class column, slot): index of the column's slot-th kept box now, its coordinates after the tile's loads are issued
+        const int pf_cl = threadIdx.x >> 3, pf_slot = threadIdx.x & (AP_PF - 1);
+        const bool pf_on = pf_slot < tile_cnt[pf_cl];
+        const int pf_idx = pf_on ? __ldg(a.cand + ((size_t)b * a.C + c0 + pf_cl) * a.N + pf_slot) : 0;
+        if (threadIdx.x < AP_BOXES)
+            s_box[threadIdx.x] = n0 + threadIdx.x < a.N ? load_box(bmin, bmax, s_perm[threadIdx.x]) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (vec4) {                                                  // thread = (box row, 4 classes): 8 threads cover a 128-byte row
             const int q = (threadIdx.x & 7) * 4;
             for (int r = threadIdx.x >> 3; r < AP_BOXES; r += 32) {
-                const int n = n0 + r;
+                const int n = s_perm[r];
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < a.N && c0 + q < a.C) v = *reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + q);
+                if (n0 + r < a.N && c0 + q < a.C) v = *reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + q);
                 tile[r][q] = v.x; tile[r][q + 1] = v.y; tile[r][q + 2] = v.z; tile[r][q + 3] = v.w;
             }
         } else {
             for (int r = warp; r < AP_BOXES; r += 8) {
-                const int n = n0 + r, c = c0 + lane;
-                tile[r][lane] = (n < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
+                const int n = s_perm[r], c = c0 + lane;
+                tile[r][lane] = (n0 + r < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
             }
         }
+        if (pf_on) pf_box[pf_cl][pf_slot] = load_box(bmin, bmax, pf_idx);
         __syncthreads();
-        const float* bmin = a.xy_min + (size_t)b * a.N * 2;
-        const float* bmax = a.xy_max + (size_t)b * a.N * 2;
         float4 bn[AP_H];
         float barea[AP_H];
         bool n_ok[AP_H];
 #pragma unroll
         for (int h = 0; h < AP_H; ++h) {
-            const int n = n0 + h * 32 + lane;
-            n_ok[h] = n < a.N;
-            bn[h] = n_ok[h] ? load_box(bmin, bmax, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            n_ok[h] = n0 + h * 32 + lane < a.N;
+            bn[h] = s_box[h * 32 + lane];
             barea[h] = box_area(bn[h]);
         }
         bool wrote = false;
         // phase 1: candidates look their fate up in the suppressed mask (a warp per class column)
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
             if (tile_cnt[cl] == 0) continue;                         // warp-uniform
-            const uint32_t* supp = a.supp + ((size_t)b * a.C + c0 + cl) * a.W + (n0 >> 5);
+            const uint32_t* supp = a.supp + ((size_t)b * a.C + c0 + cl) * a.W;
 #pragma unroll
-            for (int h = 0; h < AP_H; ++h)
-                if (n_ok[h] && tile[h * 32 + lane][cl] > a.thr && ((__ldg(supp + h) >> lane) & 1u)) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
+            for (int h = 0; h < AP_H; ++h) {
+                const int n = s_perm[h * 32 + lane];
+                if (n_ok[h] && tile[h * 32 + lane][cl] > a.thr && ((__ldg(supp + (n >> 5)) >> (n & 31)) & 1u)) { tile[h * 32 + lane][cl] = 0.0f; wrote = true; }
+            }
         }
         // work items of phase 2 = (class column, chunk of <= 32 kept boxes): the kept counts of real score matrices are very
         // uneven (one class may keep 160 boxes, most keep none), so the chunks -- not the columns -- are handed out to the warps
         // every tile has a CTA of its own (a detection batch): the kernel's time is its slowest warp -> items = chunks of 32 kept
         // boxes, handed out dynamically; many tiles per CTA (a sweep over hundreds of images): throughput regime -> one item per
         // class column (a lane that was hit skips the remaining chunks of its class), static round-robin
-        const bool dynamic = a.apply_mode ? a.apply_mode == 1 : total_tiles <= (long long)gridDim.x;
+        const bool dynamic = a.apply_mode ? a.apply_mode == 1 : total_tiles <= (int)gridDim.x;
         if (warp == 0) {
+            // per register slot: the window of kept-box areas that can reach thr_iou against its 32 boxes (all areas when thr_iou <= 0)
+#pragma unroll
+            for (int h = 0; h < AP_H; ++h) {
+                float mn = n_ok[h] ? barea[h] : __int_as_float(0x7f800000), mx = n_ok[h] ? barea[h] : __int_as_float(0xff800000);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                if (lane == 0) {
+                    s_lo[h] = quick ? __fmul_rn(thr_cull, mn) : __int_as_float(0xff800000);
+                    s_hi[h] = quick ? __fdiv_rn(mx, thr_cull) : __int_as_float(0x7f800000);
+                }
+            }
             const int chunks = dynamic ? (tile_cnt[lane] + 31) >> 5 : (tile_cnt[lane] > 0 ? 1 : 0);
             int incl = chunks;
 #pragma unroll
@@ -695,19 +800,32 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
             }
             if (__all_sync(0xffffffffu, all_skip)) continue;
             for (int k0 = kb; k0 < ke; k0 += 32) {
-                const int kc = min(32, ke - k0);
-                if (lane < kc) {
-                    const float4 kq = load_box(bmin, bmax, kept[k0 + lane]);
-                    kbox[warp][lane] = kq;
-                    karea[warp][lane] = box_area(kq);
+                // stage the chunk's kept boxes in shared memory -- only those whose area lies in the window of some slot
+                int m = 0;
+                float4 kq0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float ka0 = 0.f;
+                if (k0 + lane < ke) {
+                    kq0 = k0 + lane < AP_PF ? pf_box[cl][k0 + lane] : load_box(bmin, bmax, kept[k0 + lane]);
+                    ka0 = box_area(kq0);
+#pragma unroll
+                    for (int h = 0; h < AP_H; ++h) m |= (ka0 >= s_lo[h] && ka0 <= s_hi[h]) ? 1 << h : 0;
                 }
+                const uint32_t live = __ballot_sync(0xffffffffu, m != 0);
+                if (m) {
+                    const int pos = __popc(live & ((1u << lane) - 1u));
+                    kbox[warp][pos] = kq0;
+                    karea[warp][pos] = make_float2(ka0, __int_as_float(m));
+                }
+                const int kc = __popc(live);
                 __syncwarp();
                 for (int t = 0; t < kc; ++t) {
                     const float4 kq = kbox[warp][t];
-                    const float ka = karea[warp][t];
+                    const float2 am = karea[warp][t];
+                    const float ka = am.x;
+                    const int mt = __float_as_int(am.y);
 #pragma unroll
                     for (int h = 0; h < AP_H; ++h)
-                        if (!skip[h] && !hit[h]) hit[h] = iou_hit(kq, ka, bn[h], barea[h], a.thr_iou, thr_lo, quick);
+                        if (((mt >> h) & 1) && !skip[h] && !hit[h]) hit[h] = iou_hit(kq, ka, bn[h], barea[h], a.thr_iou, thr_lo, quick);
                 }
                 __syncwarp();
             }
@@ -721,14 +839,14 @@ __global__ void __launch_bounds__(256) nms_apply_kernel(NmsArgs a, int vec4) {
             if (vec4) {
                 const int q = (threadIdx.x & 7) * 4;
                 for (int r = threadIdx.x >> 3; r < AP_BOXES; r += 32) {
-                    const int n = n0 + r;
-                    if (n < a.N && c0 + q < a.C)
+                    const int n = s_perm[r];
+                    if (n0 + r < a.N && c0 + q < a.C)
                         *reinterpret_cast<float4*>(conf_img + (size_t)n * a.C + c0 + q) = make_float4(tile[r][q], tile[r][q + 1], tile[r][q + 2], tile[r][q + 3]);
                 }
             } else {
                 for (int r = warp; r < AP_BOXES; r += 8) {
-                    const int n = n0 + r, c = c0 + lane;
-                    if (n < a.N && c < a.C) conf_img[(size_t)n * a.C + c] = tile[r][lane];
+                    const int n = s_perm[r], c = c0 + lane;
+                    if (n0 + r < a.N && c < a.C) conf_img[(size_t)n * a.C + c] = tile[r][lane];
                 }
             }
         }
@@ -740,7 +858,7 @@ static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 size_t nms_workspace_bytes(int B, int N, int C) {
     const size_t lists = al16((size_t)B * C * N * sizeof(uint16_t));
     const size_t masks = al16((size_t)B * C * ((N + 31) / 32) * sizeof(uint32_t));
-    return 2 * lists + masks + al16((size_t)B * C * sizeof(int));
+    return 2 * lists + masks + al16((size_t)B * C * sizeof(int)) + al16((size_t)B * N * sizeof(uint16_t));
 }
 
 int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int N, int C, float threshold,
@@ -766,6 +884,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     a.sorted = reinterpret_cast<uint16_t*>(base + lists);
     a.supp = reinterpret_cast<uint32_t*>(base + 2 * lists);
     a.kept_cnt = reinterpret_cast<int*>(base + 2 * lists + masks);
+    a.area_perm = reinterpret_cast<uint16_t*>(base + 2 * lists + masks + al16((size_t)B * C * sizeof(int)));
     a.status = status_out;
     a.order_out = order_out;
     a.apply_mode = g_nms_apply_mode;
@@ -774,7 +893,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     static unsigned long long attr_seen = 0;
     if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(NMS_MAX_N / 32)));
-    dim3 grid((C + 31) / 32, B);
+    dim3 grid((C + 31) / 32 + 1, B);                                     // + one area_order CTA per image
     nms_select_kernel<<<grid, NMS_WARPS * 32, smem, s>>>(a, vec4);
     Y2_CUDA(cudaGetLastError());
     note_launch();
@@ -784,6 +903,7 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
         note_launch();
     }
     long long blocks = (long long)B * ((N + AP_BOXES - 1) / AP_BOXES) * ((C + AP_CLASSES - 1) / AP_CLASSES);
+    Y2_REQUIRE(blocks < (1ll << 31) - 148 * 8, "nms: B x N x C too large for one launch");
     if (blocks > 148 * 8) blocks = 148 * 8;
     nms_apply_kernel<<<(int)blocks, 256, 0, s>>>(a, vec4);
     Y2_CUDA(cudaGetLastError());
