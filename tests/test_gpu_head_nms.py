@@ -212,6 +212,42 @@ def test_nms_vs_c_oracle(cuda, B, hc, wc, C, K, quant):
     assert np.array_equal(order, ref_order)
 
 
+@pytest.mark.parametrize("thr_iou", [0.4, 1.0, 0.0, -0.5])
+def test_nms_area_culling_at_the_boundary(cuda, thr_iou):
+    """nms_apply_kernel drops IoU tests by an area window (CPU fuzz of the bound: tests/test_nms_cull_bound.py).  Inputs
+    where the window is tight or degenerate: nested boxes whose area ratio is within ulps of threshold_iou, identical boxes,
+    zero-area boxes, areas that overflow float32 / are denormal, and threshold_iou <= 0 (every pair "hits": no culling allowed)
+    and = 1 (identical boxes only)."""
+    rs = np.random.RandomState(31)
+    B, N, C = 2, 1500, 8
+    t = thr_iou if thr_iou > 0 else 0.4
+    c = rs.uniform(0, 13, size=(B, N, 2))
+    wh = np.exp(rs.uniform(-2, 2.5, size=(B, N, 2)))
+    parent = rs.randint(0, 40, size=(B, N))                           # most boxes are nested copies of one of 40 "parents"
+    nested = rs.rand(B, N) < 0.7
+    ratio = t * (1.0 + rs.uniform(-2e-6, 2e-6, size=(B, N)))
+    ratio = np.where(rs.rand(B, N) < 0.2, 1.0, ratio)                 # identical to the parent
+    split = np.where(ratio == 1.0, 1.0, np.exp(rs.uniform(-0.2, 0.2, size=(B, N))))
+    s = np.minimum(np.stack([np.sqrt(ratio) * split, np.sqrt(ratio) / split], -1), 1.0)
+    bi = np.arange(B)[:, None]
+    c = np.where(nested[..., None], c[bi, parent], c)
+    wh = np.where(nested[..., None], wh[bi, parent] * s, wh)
+    wh[:, 50:60, 1] = 0.0                                             # zero-area boxes
+    wh[:, 60:64] *= 1e25                                              # area overflows to inf
+    wh[:, 64:68] *= 1e-25                                             # denormal / zero area
+    lo, hi = (c - wh / 2).astype(np.float32), (c + wh / 2).astype(np.float32)
+    conf = rs.uniform(0, 0.29, size=(B, N, C)).astype(np.float32)
+    conf[:, :40] = rs.uniform(0.3, 1.0, size=(B, 40, C))              # the parents are candidates of every class
+    conf[:, 50:68:3] = 0.95
+    ref = conf.copy()
+    ref_order = nms_c_batch(ref, lo, hi, 0.3, thr_iou)
+    got, order, status = _run_nms(cuda, conf, lo, hi, 0.3, thr_iou)
+    assert not status.any()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(order, ref_order)
+    assert (ref != conf).sum() > (1000 if thr_iou < 1 else 100)      # the case suppresses a lot
+
+
 def test_nms_many_images_takes_the_per_warp_path_for_heavy_classes(cuda):
     """With few CTAs in flight (every test above) a class with more than 64 candidates is handled by the whole CTA; a batch of
     hundreds of images (BASELINE configs[4]) keeps one warp per class.  B = 128, ~125 candidates per class with ties: both paths

@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t ford(float v) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+static constexpr int KEPT_HAS_SUPP = 1 << 30;
 struct NmsArgs {
     float* conf;
     const float* xy_min;
@@ -91,7 +92,7 @@ struct NmsArgs {
     uint16_t* cand;      // [B][C][N] kept list (general path: candidates in index order first)
     uint16_t* sorted;    // [B][C][N] scratch of the general path: candidates in visiting order
     uint32_t* supp;      // [B][C][W] bit n = candidate n of this class was suppressed (written for classes with candidates)
-    int* kept_cnt;       // [B][C]
+    int* kept_cnt;       // [B][C] kept boxes of the class | KEPT_HAS_SUPP if some candidate of it was suppressed
     int* status;         // [B] nullable: 1 = a reference assert (NaN / xy_min > xy_max) would fire
     int* order_out;      // [B][N] nullable
     uint16_t* area_perm; // [B][N] boxes of the image in ascending order of area (apply's tile order)
@@ -154,7 +155,7 @@ __device__ void select_class_general(const NmsArgs& a, int b, int c, uint32_t* a
     }
     uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
     for (int w = lane; w < a.W; w += 32) supp_out[w] = supp[w];
-    if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+    if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept | (kept < K ? KEPT_HAS_SUPP : 0);
     __syncwarp();
 }
 
@@ -357,7 +358,7 @@ __device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigne
     for (int p = t; p < kept; p += NT) kept_out[p] = list[p];
     uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
     for (int w = t; w < a.W; w += NT) supp_out[w] = supp[w];
-    if (t == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+    if (t == 0) a.kept_cnt[(size_t)b * a.C + c] = kept | (kept < K ? KEPT_HAS_SUPP : 0);
     __syncthreads();
 }
 
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
         for (int p = lane; p < kept; p += 32) kept_out[p] = list[p];
         uint32_t* supp_out = a.supp + ((size_t)b * a.C + c) * a.W;
         for (int w = lane; w < a.W; w += 32) supp_out[w] = w_supp[w];
-        if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept;
+        if (lane == 0) a.kept_cnt[(size_t)b * a.C + c] = kept | (kept < K ? KEPT_HAS_SUPP : 0);
         __syncwarp();
     }   // class loop
     if (coop) {                                                       // phase B: the heavy classes, one at a time, all 8 warps
@@ -654,6 +655,8 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
     __shared__ int tile_cnt[AP_CLASSES];
     __shared__ int item_start[AP_CLASSES + 1];
     __shared__ int any_kept, dirty, next_item;
+    __shared__ uint32_t supp_cols;                                       // class columns with suppressed candidates (phase 1)
+    __shared__ float pf_area[AP_PF][AP_CLASSES];
     __shared__ uint16_t s_perm[AP_BOXES];
     __shared__ float4 s_box[AP_BOXES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -663,35 +666,40 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
     const bool quick = a.thr_iou > 0.0f;
     const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
     const float thr_cull = __fmul_rn(0.998f, a.thr_iou);
-    // threads 32..159 own one row of the tile's slice of area_perm; the next tile's entry is fetched while this one is worked on
-    auto perm_of = [&](int t) -> uint16_t {
-        const int r0 = t / c_tiles;
-        const int r = (r0 % n_tiles) * AP_BOXES + (int)threadIdx.x - AP_CLASSES;
-        return (t < total_tiles && r < a.N) ? __ldg(a.area_perm + (size_t)(r0 / n_tiles) * a.N + r) : (uint16_t)0;
+    // The CTA walks tiles blockIdx.x, + gridDim.x, ... of [B][n_tiles][c_tiles]; the step is decomposed once so that the walk needs no
+    // division, and the coordinates of the NEXT tile are known one tile ahead: its kept counts (threads 0..31) and its slice of
+    // area_perm (threads 32..159) are fetched while this tile is worked on.
+    const int d_ct = (int)gridDim.x % c_tiles, d_nt = ((int)gridDim.x / c_tiles) % n_tiles, d_b = (int)gridDim.x / c_tiles / n_tiles;
+    int ct = (int)blockIdx.x % c_tiles, ntile = ((int)blockIdx.x / c_tiles) % n_tiles, b = (int)blockIdx.x / c_tiles / n_tiles;
+    int ct2 = 0, ntile2 = 0, b2 = 0;
+    auto perm_at = [&](int bb, int nt) -> uint16_t {
+        const int r = nt * AP_BOXES + (int)threadIdx.x - AP_CLASSES;
+        return (bb < a.B && r < a.N) ? __ldg(a.area_perm + (size_t)bb * a.N + r) : (uint16_t)0;
+    };
+    auto cnt_at = [&](int bb, int c_tile) -> int {
+        const int c = c_tile * AP_CLASSES + (int)threadIdx.x;
+        return (bb < a.B && c < a.C) ? __ldg(a.kept_cnt + (size_t)bb * a.C + c) : 0;
     };
     const bool perm_thread = threadIdx.x >= AP_CLASSES && threadIdx.x < AP_CLASSES + AP_BOXES;
-    uint16_t perm_next = perm_thread ? perm_of(blockIdx.x) : (uint16_t)0;
-    auto cnt_of = [&](int t) -> int {                                    // threads 0..31: kept count of the tile's class column
-        const int c = (t % c_tiles) * AP_CLASSES + (int)threadIdx.x;
-        return (t < total_tiles && c < a.C) ? __ldg(a.kept_cnt + (size_t)(t / c_tiles / n_tiles) * a.C + c) : 0;
-    };
-    int cnt_next = threadIdx.x < AP_CLASSES ? cnt_of(blockIdx.x) : 0;
-    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
-        const int ct = tix % c_tiles;
-        const int r0 = tix / c_tiles;
-        const int ntile = r0 % n_tiles;
-        const int b = r0 / n_tiles;
+    uint16_t perm_next = perm_thread ? perm_at(b, ntile) : (uint16_t)0;
+    int cnt_next = threadIdx.x < AP_CLASSES ? cnt_at(b, ct) : 0;
+    for (; b < a.B; b = b2, ntile = ntile2, ct = ct2) {
+        ct2 = ct + d_ct; ntile2 = ntile + d_nt; b2 = b + d_b;
+        if (ct2 >= c_tiles) { ct2 -= c_tiles; ++ntile2; }
+        if (ntile2 >= n_tiles) { ntile2 -= n_tiles; ++b2; }
         const int c0 = ct * AP_CLASSES, n0 = ntile * AP_BOXES;
         if (threadIdx.x == 0) { any_kept = 0; dirty = 0; }
         __syncthreads();
         if (threadIdx.x < AP_CLASSES) {
-            const int k = cnt_next;
-            cnt_next = cnt_of(tix + gridDim.x);
+            const int k = cnt_next & ~KEPT_HAS_SUPP;
+            const uint32_t has_supp = __ballot_sync(0xffffffffu, cnt_next & KEPT_HAS_SUPP);      // threads 0..31 = warp 0
+            cnt_next = cnt_at(b2, ct2);
             tile_cnt[threadIdx.x] = k;
             if (k) any_kept = 1;
+            if (lane == 0) supp_cols = has_supp;
         } else if (perm_thread) {
             s_perm[threadIdx.x - AP_CLASSES] = perm_next;
-            perm_next = perm_of(tix + gridDim.x);
+            perm_next = perm_at(b2, ntile2);
         }
         __syncthreads();
         const int ak = any_kept;
@@ -720,7 +728,11 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
                 tile[r][lane] = (n0 + r < a.N && c < a.C) ? conf_img[(size_t)n * a.C + c] : 0.f;
             }
         }
-        if (pf_on) pf_box[pf_cl][pf_slot] = load_box(bmin, bmax, pf_idx);
+        if (pf_on) {
+            const float4 q4 = load_box(bmin, bmax, pf_idx);
+            pf_box[pf_cl][pf_slot] = q4;
+            pf_area[pf_slot][pf_cl] = box_area(q4);
+        }
         __syncthreads();
         float4 bn[AP_H];
         float barea[AP_H];
@@ -734,7 +746,7 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
         bool wrote = false;
         // phase 1: candidates look their fate up in the suppressed mask (a warp per class column)
         for (int cl = warp; cl < AP_CLASSES; cl += 8) {
-            if (tile_cnt[cl] == 0) continue;                         // warp-uniform
+            if (!((supp_cols >> cl) & 1u)) continue;                 // warp-uniform: no candidate of this class was suppressed
             const uint32_t* supp = a.supp + ((size_t)b * a.C + c0 + cl) * a.W;
 #pragma unroll
             for (int h = 0; h < AP_H; ++h) {
@@ -750,6 +762,7 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
         const bool dynamic = a.apply_mode ? a.apply_mode == 1 : total_tiles <= (int)gridDim.x;
         if (warp == 0) {
             // per register slot: the window of kept-box areas that can reach thr_iou against its 32 boxes (all areas when thr_iou <= 0)
+            float lo_t = __int_as_float(0x7f800000), hi_t = __int_as_float(0xff800000);
 #pragma unroll
             for (int h = 0; h < AP_H; ++h) {
                 float mn = n_ok[h] ? barea[h] : __int_as_float(0x7f800000), mx = n_ok[h] ? barea[h] : __int_as_float(0xff800000);
@@ -758,12 +771,19 @@ __global__ void __launch_bounds__(256, 4) nms_apply_kernel(NmsArgs a, int vec4) 
                     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 }
-                if (lane == 0) {
-                    s_lo[h] = quick ? __fmul_rn(thr_cull, mn) : __int_as_float(0xff800000);
-                    s_hi[h] = quick ? __fdiv_rn(mx, thr_cull) : __int_as_float(0x7f800000);
-                }
+                const float lo = quick ? __fmul_rn(thr_cull, mn) : __int_as_float(0xff800000);
+                const float hi = quick ? __fdiv_rn(mx, thr_cull) : __int_as_float(0x7f800000);
+                if (lane == 0) { s_lo[h] = lo; s_hi[h] = hi; }
+                lo_t = fminf(lo_t, lo);
+                hi_t = fmaxf(hi_t, hi);
             }
-            const int chunks = dynamic ? (tile_cnt[lane] + 31) >> 5 : (tile_cnt[lane] > 0 ? 1 : 0);
+            // a class column is worked on only if one of its kept boxes lies in the window of some slot (columns with up to AP_PF
+            // kept boxes: decided here from the prefetched areas; the others: when their chunks are staged)
+            const int cnt = tile_cnt[lane];
+            bool rel = cnt > AP_PF;
+            for (int j = 0; j < AP_PF; ++j)
+                if (j < cnt) { const float ar = pf_area[j][lane]; rel |= ar >= lo_t && ar <= hi_t; }
+            const int chunks = !rel ? 0 : dynamic ? (cnt + 31) >> 5 : 1;
             int incl = chunks;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
