@@ -189,6 +189,10 @@ int y2_conv2d(const float* x, int B, int H, int W, int cin, const float* w_hwio,
 int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* dy, int ksize, int cout, float* dw,
                     int max_ctas, void* stream);
 
+/* ---- leaky_relu -- model/yolo/function.py:21-24 (`leaky_relu(inputs, alpha=.1)` = max(x, alpha*x)), float32, n elements; out may
+ * alias in.  Inside the network the activation is fused into every conv epilogue; this is the standalone op. */
+int y2_leaky_relu(const float* in, size_t n, float alpha, float* out, void* stream);
+
 /* ---- reorg -- model/yolo2/function.py:22-29 (`reorg(net, stride=2)`), float32 NHWC.
  * out[b, y, x, (dy*stride+dx)*C + c] = in[b, stride*y+dy, stride*x+dx, c]. */
 int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream);

@@ -66,6 +66,9 @@ def test_null_handle_is_rejected_everywhere():
 def test_reorg_validation():
     """model/yolo2/function.py:22-29 reshapes [B, H/stride, stride, W/stride, stride, C]: H, W must divide."""
     L = _lib.lib()
+    assert L.y2_leaky_relu(None, 16, 0.1, P, None) == -1 and "null" in _err()
+    assert L.y2_leaky_relu(P, 16, 0.1, None, None) == -1
+    assert L.y2_leaky_relu(P, 0, 0.1, P, None) == 0                  # nothing to do, nothing launched
     assert L.y2_reorg(None, 1, 4, 4, 4, 2, P, None) == -1 and "null" in _err()
     assert L.y2_reorg(P, 1, 4, 4, 4, 2, None, None) == -1
     assert L.y2_reorg(P, 1, 5, 4, 4, 2, P, None) == -1 and "divisible" in _err()

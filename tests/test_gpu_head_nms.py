@@ -48,6 +48,31 @@ def test_reorg_random_bit_exact(cuda, shape):
     assert np.array_equal(y.cpu().numpy().view(np.uint32), reorg_oracle(a).view(np.uint32))
 
 
+# ------------------------------------------------------------------ leaky_relu (standalone op; fused everywhere inside the network)
+@pytest.mark.parametrize("shape,alpha", [((2, 13, 13, 1024), 0.1), ((3, 7, 5, 3), 0.1), ((1001,), 0.25), ((4, 416, 416, 32), 0.1)])
+def test_leaky_relu_standalone_bit_exact(cuda, shape, alpha):
+    """model/yolo/function.py:21-24: max(x, alpha * x) in float32, incl. -0.0, +-inf, NaN, a size that is no multiple of 4 and an
+    unaligned view (scalar path)."""
+    import torch
+    from yolo_tf_b200.model.yolo.function import leaky_relu
+    rs = np.random.RandomState(1)
+    a = rs.normal(0, 3, size=shape).astype(np.float32)
+    flat = a.reshape(-1)
+    flat[:6] = [0.0, -0.0, np.inf, -np.inf, np.nan, -1e-45]
+    with np.errstate(invalid="ignore"):
+        want = np.maximum(a, np.float32(alpha) * a)
+    got = leaky_relu(_t(a, cuda), alpha).cpu().numpy()
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
+    if flat.size > 8:                                                  # 4-byte-aligned view: the scalar path
+        x = _t(flat, cuda)[1:]
+        got1 = leaky_relu(x, alpha).cpu().numpy()
+        w1 = want.reshape(-1)[1:]
+        ok = ~np.isnan(w1)
+        assert np.array_equal(got1[ok].view(np.uint32), w1[ok].view(np.uint32))
+
+
 # ------------------------------------------------------------------ decode
 @pytest.mark.parametrize("B,hc,wc,C,anchors", [(2, 13, 13, 20, ho.ANCHORS_VOC), (3, 19, 19, 80, ho.ANCHORS_COCO),
                                                (1, 3, 5, 7, ho.ANCHORS_VOC[:3]), (5, 13, 13, 1, ho.ANCHORS_COCO)])

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "y2_darknet_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_i, c_p]),
     "y2_get_activation": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "y2_conv2d": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
+    "y2_leaky_relu": (c_i, [c_p, c_sz, c_f, c_p, c_p]),
     "y2_reorg": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "y2_head_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, ctypes.POINTER(HeadOutputs), c_p]),
     "y2_loss_workspace_bytes": (c_sz, [c_i, c_i, c_i]),

@@ -717,6 +717,10 @@ int y2_conv2d_wgrad(const float* x, int B, int H, int W, int cin, const float* d
     return rc;
 }
 
+int y2_leaky_relu(const float* in, size_t n, float alpha, float* out, void* stream) {
+    return leaky_relu_launch(in, out, n, alpha, static_cast<cudaStream_t>(stream));
+}
+
 int y2_reorg(const float* in, int B, int H, int W, int C, int stride, float* out, void* stream) {
     Y2_REQUIRE(in && out, "y2_reorg: null argument");
     Y2_REQUIRE(stride >= 1 && H % stride == 0 && W % stride == 0, "y2_reorg: H, W must be divisible by stride");

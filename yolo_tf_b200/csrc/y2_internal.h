@@ -206,6 +206,7 @@ int maxpool_planes_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf
                           int C, cudaStream_t s, int stride = 2, int f16 = 0);
 int pad_weights_launch(const float* w_hwio, float* out, int ksize, int cin, int cout, int cin_s, int cout_s, cudaStream_t s);
 // reorg (space-to-depth 2) on 16-byte vectors; elem_bytes in {2,4}; out row pitch in elements.
+int leaky_relu_launch(const float* in, float* out, size_t n, float alpha, cudaStream_t s);
 int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes,
                  long long out_ld, cudaStream_t s);
 

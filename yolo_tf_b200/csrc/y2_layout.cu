@@ -277,6 +277,35 @@ static int reorg_dispatch(const void* in, void* out, int B, int H, int W, size_t
     return 0;
 }
 // Widest vector (16/8/4/2 bytes) that divides the channel run, the output pitch and both base addresses.
+// leaky_relu(inputs, alpha) = max(x, alpha * x), float32 -- model/yolo/function.py:21-24 as a standalone op (inside the network it is
+// fused into every conv epilogue).  HBM-bound: 8 bytes per element, 128-bit accesses where the pointers allow, grid-stride.
+__global__ void __launch_bounds__(256) leaky_relu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float alpha, int vec4) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec4) {
+        const size_t n4 = n / 4;
+        for (size_t i = t; i < n4; i += stride) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+            reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(v.x, __fmul_rn(alpha, v.x)), fmaxf(v.y, __fmul_rn(alpha, v.y)),
+                                                             fmaxf(v.z, __fmul_rn(alpha, v.z)), fmaxf(v.w, __fmul_rn(alpha, v.w)));
+        }
+        for (size_t i = n4 * 4 + t; i < n; i += stride) out[i] = fmaxf(in[i], __fmul_rn(alpha, in[i]));
+    } else {
+        for (size_t i = t; i < n; i += stride) out[i] = fmaxf(in[i], __fmul_rn(alpha, in[i]));
+    }
+}
+int leaky_relu_launch(const float* in, float* out, size_t n, float alpha, cudaStream_t s) {
+    Y2_REQUIRE(in && out, "leaky_relu: null argument");
+    if (n == 0) return 0;
+    const int vec4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    size_t blocks = (n / (vec4 ? 4 : 1) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks == 0) blocks = 1;
+    leaky_relu_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, n, alpha, vec4);
+    Y2_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
 int reorg_launch(const void* in, void* out, int B, int H, int W, int C, int stride, int elem_bytes, long long out_ld,
                  cudaStream_t s) {
     Y2_REQUIRE(stride >= 1 && H % stride == 0 && W % stride == 0, "reorg: H, W must be divisible by stride");
