@@ -273,6 +273,29 @@ def test_nms_area_culling_at_the_boundary(cuda, thr_iou):
     assert (ref != conf).sum() > (1000 if thr_iou < 1 else 100)      # the case suppresses a lot
 
 
+@pytest.mark.parametrize("C,quant", [(80, 16), (20, None), (6, 8)])
+def test_nms_select_class_group_width(cuda, C, quant):
+    """nms_select_kernel gives a CTA 8, 16 or 32 classes of an image (by regime; y2_debug_set key 13 forces it): all three must give
+    the oracle's bits, incl. C % 4 != 0 (scalar loads) and a last group that is only partly filled."""
+    import ctypes
+    from yolo_tf_b200 import _lib
+    L = _lib.lib()
+    L.y2_debug_set.argtypes = [ctypes.c_int, ctypes.c_double]
+    rs = np.random.RandomState(17)
+    conf, lo, hi = _sweep_inputs(rs, 3, 13, 13, C, 40 * C, quant)
+    ref = conf.copy()
+    ref_order = nms_c_batch(ref, lo, hi, 0.3, 0.4)
+    try:
+        for cg in (8, 16, 32):
+            L.y2_debug_set(13, float(cg))
+            got, order, status = _run_nms(cuda, conf, lo, hi, 0.3, 0.4)
+            assert not status.any()
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), cg
+            assert np.array_equal(order, ref_order), cg
+    finally:
+        L.y2_debug_set(13, 0.0)
+
+
 def test_nms_many_images_takes_the_per_warp_path_for_heavy_classes(cuda):
     """With few CTAs in flight (every test above) a class with more than 64 candidates is handled by the whole CTA; a batch of
     hundreds of images (BASELINE configs[4]) keeps one warp per class.  B = 128, ~125 candidates per class with ties: both paths

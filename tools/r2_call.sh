@@ -1,14 +1,13 @@
 #!/bin/bash
 # scratch driver for one gpurun visit (edited per call)
 mkdir -p gpurun_out
-timeout 900 ncu --metrics sm__cycles_elapsed.max,smsp__inst_executed.sum,gpu__time_duration.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:conv0_tc_pool -c 64 --csv --log-file gpurun_out/conv0_variants.csv python tools/ab_conv0.py > gpurun_out/c35_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/c35_ncu.log
+timeout 900 python -m pytest tests/test_gpu_head_nms.py tests/test_dropin.py tests/test_abi_and_host.py tests/test_prepost.py -q -m gpu > gpurun_out/c39_pytest.log 2>&1; echo "pytest rc=$?"; grep -v "^$" gpurun_out/c39_pytest.log | grep "passed\|failed\|Error\|error\|assert \|FAILED" | tail -10 | cut -c1-300
+timeout 300 python __graft_entry__.py smoke > gpurun_out/c39_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/c39_smoke.log
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/c39_bench.json 2> gpurun_out/c39_bench.err; echo "bench rc=$?"
 python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/conv0_variants.csv')) if len(r)>10]
-h=rows[0]; ik=h.index('Kernel Name'); im=h.index('Metric Name'); iv=h.index('Metric Value'); iid=h.index('ID')
-d={}
-for r in rows[1:]:
-    d.setdefault(int(r[iid]),{'k':r[ik][:48]})[r[im]]=r[iv]
-for i in sorted(d):
-    if i in (1,2,5,10,20,25,30,40,45,50,60,63): print(i, d[i])
+import json
+d=json.loads(open('gpurun_out/c39_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['e2e'].get('blocks_ms_per_step'), d['ms_per_step'], d['gpu_launches'], d['roofline']['frac'])
+print([ (p['N'],p['K'],round(p['ms'],3),p['bit_exact_vs_c_oracle_2_images']) for p in d['nms']['points']])
 PY
+timeout 900 tools/profile_hbm.sh r2s --skip-train

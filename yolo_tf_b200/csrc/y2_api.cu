@@ -667,6 +667,7 @@ int y2_debug_set(int key, double value) {
     else if (key == 1) g_sched_handoff_kb = value;
     else if (key == 3) g_conv_dbg_flags = (int)value;       // ConvParams::dbg_flags of the convs planned from now on
     else if (key == 4) g_conv_force_halo = (int)value;
+    else if (key == 13) g_nms_select_cg = (int)value;       // nms_select_kernel: classes per CTA (0 by regime, 8 | 16 | 32)
     else if (key == 11) g_nms_apply_mode = (int)value;      // nms_apply_kernel work items: 0 by regime, 1 dynamic chunks, 2 one per class column
     else if (key == 9) g_conv_fmt = (int)value;             // FMT_* bits of the convs planned from now on (y2_conv2d sets them itself)
     else if (key == 10) g_wgrad_fmt = (int)value;           // FMT_* bits of y2_conv2d_wgrad: 3 = x planes in fp16

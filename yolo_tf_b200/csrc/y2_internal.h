@@ -114,6 +114,7 @@ struct ConvParams {
     int fmt;                 // FMT_* bits (y2_ptx.cuh): element format of the A (activation) and B (weight) hi / lo planes; 0 = all bf16
 };
 extern int g_conv_tma_store;   // 1 = TMA-store epilogue where the layout allows it
+extern int g_nms_select_cg;            // diagnostics (y2_debug_set key 13): classes per nms_select_kernel CTA (0 = by regime)
 extern int g_nms_apply_mode;           // diagnostics (y2_debug_set key 11): work-item scheme of nms_apply_kernel
 extern int g_conv_fmt, g_wgrad_fmt;   // FMT_* bits of the GEMMs planned from now on (diagnostic entry points; the network sets them per launch)
 extern int g_conv_kcap;        // ConvParams::kcap of the convs planned from now on (default 32)

@@ -32,6 +32,7 @@
 namespace y2 {
 
 int g_nms_apply_mode = 0;
+int g_nms_select_cg = 0;          // y2_debug_set(13, 0 | 8 | 16 | 32): classes per select CTA (0 = by regime)
 static constexpr int NMS_WARPS = 8;
 static constexpr int NMS_MAX_N = 8192;     // bitmasks: 256 words per warp
 static constexpr int SEL_CAP = 256;        // candidates per class handled out of shared memory
@@ -97,6 +98,8 @@ struct NmsArgs {
     int* order_out;      // [B][N] nullable
     uint16_t* area_perm; // [B][N] boxes of the image in ascending order of area (apply's tile order)
     int apply_mode;      // diagnostics: 0 = choose by regime, 1 = chunk items handed out dynamically, 2 = one item per class column
+    int cg;              // select: classes per CTA (32, 16 or 8: narrower groups when the batch alone cannot fill the machine)
+    int coop;            // select: latency regime -- a class with more than COOP_MIN candidates gets the whole CTA
 };
 
 // General path for one (image, class), one warp: any number of candidates, lists in global memory, rank sort.
@@ -321,30 +324,50 @@ __device__ void select_class_coop(const NmsArgs& a, int b, int c, int K, unsigne
         }
     }
     __syncthreads();
-    int kept = 0, g = 0, prev = -1;
-    while (g < words) {                                               // CTA-uniform control flow throughout
-        // a reader that sees the owner's update of this step still finds the same lowest bit: only bits above r are cleared
-        const uint32_t m = alive_sm[g] & (prev >= 31 ? 0u : (0xffffffffu << (prev + 1)));
-        if (m == 0u) { ++g; prev = -1; continue; }
-        const int bit = __ffs(m) - 1;
-        const int r = g * 32 + bit;
-        prev = bit;
-        const float4 bi = box[r];
-        const float ai = box_area(bi);
-        if (t == 0) list[kept] = (uint16_t)(0xffff - (int)(key[r] & 0xffffu));      // kept <= r: slot already consumed
-        ++kept;
+    // Greedy sweep, one 32-candidate word per round (round 2: was one kept box per round, i.e. a CTA barrier and two dependent
+    // shared-memory round trips per kept box -- 0.3 us each, measured): the warp that owns word g settles it alone (boxes of the word
+    // suppress later boxes of the word, strictly in order), publishes the survivors, and every warp then tests its later words
+    // against all of them without further synchronisation.  A candidate is still suppressed only by earlier boxes that are
+    // themselves alive when their turn comes: the reference's order of events.
+    int kept = 0;
+    for (int g = 0; g < words; ++g) {                                 // CTA-uniform control flow throughout
+        const int ow = g % NMS_WARPS, oj = g / NMS_WARPS;
+        if (warp == ow) {
+#pragma unroll
+            for (int j = 0; j < COOP_R; ++j)
+                if (j == oj) {
+                    uint32_t al = alive_w[j], todo = al;
+                    while (todo) {                                    // warp-uniform
+                        const int bit = __ffs(todo) - 1;
+                        todo &= todo - 1u;
+                        const float4 bi = box[g * 32 + bit];
+                        const bool kill = lane > bit && ((al >> lane) & 1u) && iou_hit(bi, box_area(bi), bj[j], aj[j], a.thr_iou, thr_lo, quick);
+                        const uint32_t km = __ballot_sync(0xffffffffu, kill);
+                        al &= ~km;
+                        todo &= ~km;
+                    }
+                    alive_w[j] = al;
+                    if ((al >> lane) & 1u) list[kept + __popc(al & ((1u << lane) - 1u))] = (uint16_t)(0xffff - (int)(key[g * 32 + lane] & 0xffffu));
+                    if (lane == 0) alive_sm[g] = al;
+                }
+        }
+        __syncthreads();
+        const uint32_t surv = alive_sm[g];
+        kept += __popc(surv);
 #pragma unroll
         for (int j = 0; j < COOP_R; ++j) {
             const int wd = warp + NMS_WARPS * j;
-            if (wd >= g && wd < words) {                              // warp-uniform
-                const bool kill = wd * 32 + lane > r && ((alive_w[j] >> lane) & 1u) && iou_hit(bi, ai, bj[j], aj[j], a.thr_iou, thr_lo, quick);
-                const uint32_t km = __ballot_sync(0xffffffffu, kill);
-                alive_w[j] &= ~km;
-                if (lane == 0 && km) alive_sm[wd] = alive_w[j];
+            if (wd > g && wd < words && alive_w[j]) {                 // warp-uniform
+                bool dead = !((alive_w[j] >> lane) & 1u);
+                for (uint32_t sv = surv; sv; sv &= sv - 1u) {
+                    const float4 bi = box[g * 32 + __ffs(sv) - 1];
+                    if (!dead && iou_hit(bi, box_area(bi), bj[j], aj[j], a.thr_iou, thr_lo, quick)) dead = true;
+                }
+                alive_w[j] &= ~__ballot_sync(0xffffffffu, dead);
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < COOP_R; ++j) {                                // suppressed candidates = cleared alive bits
         const int p = (warp + NMS_WARPS * j) * 32 + lane;
@@ -440,7 +463,9 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     const size_t area = NMS_WARPS * sel_warp_bytes(a.W) > coop_pool_bytes(a.W) ? NMS_WARPS * sel_warp_bytes(a.W) : coop_pool_bytes(a.W);
     uint16_t (*s_list)[SEL_CAP] = reinterpret_cast<uint16_t (*)[SEL_CAP]>(sel_smem + area);
     int* s_cnt = reinterpret_cast<int*>(sel_smem + area + 32 * SEL_CAP * sizeof(uint16_t));
-    const int c0 = blockIdx.x * 32;                     // this CTA: 32 classes of image b
+    const int cg = a.cg;
+    const int c0 = blockIdx.x * cg;                     // this CTA: cg (32 | 16 | 8) classes of image b
+    const int c_end = min(c0 + cg, a.C);
     const int b = blockIdx.y;
     const float* conf_img = a.conf + (size_t)b * a.N * a.C;
     const float* bmin = a.xy_min + (size_t)b * a.N * 2;
@@ -451,19 +476,20 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     if (threadIdx.x <= 32) s_cnt[threadIdx.x] = 0;        // [32] = next class to hand out
     __syncthreads();
     if (vec4) {                                          // C % 4 == 0, 16-byte aligned rows: lane = (box, 4 classes)
-        const int q = lane & 7, cl = 4 * q;
-        if (c0 + cl < a.C) {
+        const int lpr = cg >> 2, rows = 32 / lpr;        // lanes per row (8 | 4 | 2), rows per warp-wide load (4 | 8 | 16)
+        const int q = lane % lpr, cl = 4 * q;
+        if (c0 + cl < c_end) {
             // four rows of loads in flight per lane (the shared-memory atomics below would otherwise serialise the loads)
-            for (int n0 = warp * 4 + (lane >> 3); n0 < a.N; n0 += NMS_WARPS * 4 * 4) {
+            for (int n0 = warp * rows + lane / lpr; n0 < a.N; n0 += NMS_WARPS * rows * 4) {
                 float4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int n = n0 + u * NMS_WARPS * 4;
+                    const int n = n0 + u * NMS_WARPS * rows;
                     v[u] = n < a.N ? __ldg(reinterpret_cast<const float4*>(conf_img + (size_t)n * a.C + c0 + cl)) : make_float4(a.thr, a.thr, a.thr, a.thr);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int n = n0 + u * NMS_WARPS * 4;
+                    const int n = n0 + u * NMS_WARPS * rows;
                     const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
@@ -474,13 +500,15 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
                 }
             }
         }
-    } else if (c0 + lane < a.C) {                        // lane = class, a warp reads 32 consecutive classes of one box
-        for (int n = warp; n < a.N; n += NMS_WARPS) {
-            if (__ldg(conf_img + (size_t)n * a.C + c0 + lane) > a.thr) {
-                const int slot = atomicAdd(&s_cnt[lane], 1);
-                if (slot < SEL_CAP) s_list[lane][slot] = (uint16_t)n;
+    } else {                                             // lane = (box, class): a warp reads cg consecutive classes of 32 / cg boxes
+        const int rows = 32 / cg, cl = lane % cg;
+        if (c0 + cl < c_end)
+            for (int n = warp * rows + lane / cg; n < a.N; n += NMS_WARPS * rows) {
+                if (__ldg(conf_img + (size_t)n * a.C + c0 + cl) > a.thr) {
+                    const int slot = atomicAdd(&s_cnt[cl], 1);
+                    if (slot < SEL_CAP) s_list[cl][slot] = (uint16_t)n;
+                }
             }
-        }
     }
     __syncthreads();
     // reference asserts fire as soon as one live box is compared with the rest: with any candidate in this CTA's classes
@@ -501,14 +529,14 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     const float thr_lo = __fmul_rn(0.999f, a.thr_iou);
     // Few CTAs in flight (a detection batch, not a sweep over hundreds of images): the machine is idle anyway and the kernel's
     // time is its longest class -- classes with more than COOP_MIN candidates then get the whole CTA (select_class_coop).
-    const bool coop = (int)((gridDim.x - 1) * gridDim.y) <= 2 * 148;      // the last column of CTAs is area_order
+    const bool coop = a.coop != 0;
     // one warp per class from here on; classes are handed out dynamically (the candidate counts of real score matrices
     // are very uneven: a few classes hold most of an image's candidates)
     for (;;) {
         int cl = 0;
         if (lane == 0) cl = atomicAdd(&s_cnt[32], 1);
         cl = __shfl_sync(0xffffffffu, cl, 0);
-        if (cl >= 32) break;
+        if (cl >= cg) break;
         const int c = c0 + cl;
         if (c >= a.C) continue;
         const int K = s_cnt[cl];
@@ -607,7 +635,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_select_kernel(NmsArgs a, i
     }   // class loop
     if (coop) {                                                       // phase B: the heavy classes, one at a time, all 8 warps
         __syncthreads();
-        for (int cl = 0; cl < 32; ++cl) {
+        for (int cl = 0; cl < cg; ++cl) {
             const int c = c0 + cl;
             if (c >= a.C) break;
             const int K = s_cnt[cl];
@@ -913,7 +941,12 @@ int nms_launch(float* conf, const float* xy_min, const float* xy_max, int B, int
     static unsigned long long attr_seen = 0;
     if (first_use_on_current_device(attr_seen))
         Y2_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(NMS_MAX_N / 32)));
-    dim3 grid((C + 31) / 32 + 1, B);                                     // + one area_order CTA per image
+    // Latency regime (a detection batch): with 32 classes per CTA a batch of 32 images is 96 CTAs, and the kernel's time is the CTA that
+    // happens to hold the image's three heaviest classes, one after the other.  Narrower class groups spread them (a CTA reads whole
+    // 32-byte sectors either way); a sweep over hundreds of images keeps 32 (fewer, fuller CTAs).
+    a.coop = (long long)B * ((C + 31) / 32) <= 2 * 148;
+    a.cg = (g_nms_select_cg == 8 || g_nms_select_cg == 16 || g_nms_select_cg == 32) ? g_nms_select_cg : (long long)B * ((C + 7) / 8) <= 3 * 148 ? 8 : (long long)B * ((C + 15) / 16) <= 3 * 148 ? 16 : 32;
+    dim3 grid((C + a.cg - 1) / a.cg + 1, B);                             // + one area_order CTA per image
     nms_select_kernel<<<grid, NMS_WARPS * 32, smem, s>>>(a, vec4);
     Y2_CUDA(cudaGetLastError());
     note_launch();
