@@ -17,8 +17,11 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        try:
+            build()                                   # make: a no-op when libnms_oracle.so is newer than nms_oracle.c
+        except Exception:
+            if not os.path.exists(_SO):
+                raise
         _lib = ctypes.CDLL(_SO)
         _lib.y2o_nms_batch.restype = ctypes.c_int
         _lib.y2o_nms_batch.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p]

@@ -28,7 +28,10 @@ float y2o_pair_iou(const float *min1, const float *max1, const float *min2, cons
     float iw = f_max(f_min(max1[0], max2[0]) - f_max(min1[0], min2[0]), 0.0f);
     float ih = f_max(f_min(max1[1], max2[1]) - f_max(min1[1], min2[1]), 0.0f);
     float inter = iw * ih;
-    float den = f_max((a1 + a2) - inter, (float)1e-10);
+    float d0 = (a1 + a2) - inter;
+    /* np.maximum propagates NaN (utils/postprocess.py:36): inf + inf - inf (boxes whose areas overflow float32) gives iou = nan,
+     * and nan >= threshold_iou is False -- no suppression.  f_max alone would turn the NaN into 1e-10 and the pair into a hit. */
+    float den = (d0 != d0) ? d0 : f_max(d0, (float)1e-10);
     return inter / den;
 }
 

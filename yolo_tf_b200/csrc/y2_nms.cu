@@ -43,7 +43,8 @@ __device__ __forceinline__ float iou_ref(float4 a, float4 b) {   // (xmin, ymin,
     const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
     const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
     const float inter = __fmul_rn(iw, ih);
-    const float den = fmaxf(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-10f);
+    const float d0 = __fsub_rn(__fadd_rn(a1, a2), inter);
+    const float den = (d0 != d0) ? d0 : fmaxf(d0, 1e-10f);           // np.maximum propagates NaN (inf + inf - inf), fmaxf does not
     return __fdiv_rn(inter, den);
 }
 __device__ __forceinline__ float box_area(float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
@@ -55,7 +56,9 @@ __device__ __forceinline__ bool iou_hit(float4 a, float aa, float4 b, float ba, 
     const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
     const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
     const float inter = __fmul_rn(iw, ih);
-    const float den = fmaxf(__fsub_rn(__fadd_rn(aa, ba), inter), 1e-10f);
+    const float d0 = __fsub_rn(__fadd_rn(aa, ba), inter);
+    if (d0 != d0) return false;                                       // the reference's np.maximum(nan, 1e-10) is nan: nan >= thr_iou is False
+    const float den = fmaxf(d0, 1e-10f);
     if (quick && inter < __fmul_rn(thr_lo, den)) return false;
     return __fdiv_rn(inter, den) >= thr;
 }
