@@ -28,6 +28,7 @@
 //            a non-candidate (it sorts after every candidate) is zeroed iff any kept box overlaps it >= threshold_iou.
 // Scores are read once by select and once by apply, both coalesced; only tiles that change are written back.
 #include "y2_internal.h"
+#include "y2_nms_iou.cuh"
 
 namespace y2 {
 
@@ -37,31 +38,6 @@ static constexpr int NMS_WARPS = 8;
 static constexpr int NMS_MAX_N = 8192;     // bitmasks: 256 words per warp
 static constexpr int SEL_CAP = 256;        // candidates per class handled out of shared memory
 
-__device__ __forceinline__ float iou_ref(float4 a, float4 b) {   // (xmin, ymin, xmax, ymax)
-    const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-    const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-    const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-    const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-    const float inter = __fmul_rn(iw, ih);
-    const float d0 = __fsub_rn(__fadd_rn(a1, a2), inter);
-    const float den = (d0 != d0) ? d0 : fmaxf(d0, 1e-10f);           // np.maximum propagates NaN (inf + inf - inf), fmaxf does not
-    return __fdiv_rn(inter, den);
-}
-__device__ __forceinline__ float box_area(float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
-// iou_ref(a, b) >= thr with the areas precomputed.  Same float32 operations as iou_ref up to the divide (bit-identical
-// inter and den), then a conservative filter when thr > 0 (quick): rn(inter/den) >= thr needs inter >= thr*(1-2^-24)*den,
-// so anything below 0.999*thr*den is certainly no hit and skips the IEEE division; disjoint pairs (inter == 0) fall out
-// here too.  NaNs fail the '<' and take the exact path.
-__device__ __forceinline__ bool iou_hit(float4 a, float aa, float4 b, float ba, float thr, float thr_lo, bool quick) {
-    const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-    const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-    const float inter = __fmul_rn(iw, ih);
-    const float d0 = __fsub_rn(__fadd_rn(aa, ba), inter);
-    if (d0 != d0) return false;                                       // the reference's np.maximum(nan, 1e-10) is nan: nan >= thr_iou is False
-    const float den = fmaxf(d0, 1e-10f);
-    if (quick && inter < __fmul_rn(thr_lo, den)) return false;
-    return __fdiv_rn(inter, den) >= thr;
-}
 __device__ __forceinline__ float4 load_box(const float* __restrict__ xy_min, const float* __restrict__ xy_max,
                                            size_t i) {
     const float2 lo = __ldg(reinterpret_cast<const float2*>(xy_min) + i);
@@ -80,12 +56,6 @@ __device__ __forceinline__ bool precedes(const float* __restrict__ conf_img, int
     }
     return i < j;
 }
-// order-preserving map float -> uint32 (a > b  <=>  ford(a) > ford(b) for non-NaN a, b; -0 is canonicalised to +0 first)
-__device__ __forceinline__ uint32_t ford(float v) {
-    const uint32_t u = __float_as_uint(v + 0.0f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
 static constexpr int KEPT_HAS_SUPP = 1 << 30;
 struct NmsArgs {
     float* conf;
